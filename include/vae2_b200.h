@@ -1,0 +1,159 @@
+/*
+ * vae2_b200.h -- C ABI of the B200-native VAE^2 hot path (libvae2_b200.so).
+ *
+ * The reference has no FFI registry; its boundary for this path is the nn.Module surface
+ * (lib/models/enc_hrnet.py:1185-1210, lib/utils/utils.py:39-155, lib/core/criterion.py:61-103)
+ * and, for native ops, the free-function op convention of its vendored extension
+ * (lib/models/sync_bn/inplace_abn/src/inplace_abn.cpp:7-75: one function per op, device
+ * pointers borrowed from the caller, errors reported to Python as RuntimeError).  This header
+ * is that convention as a plain C ABI: raw DEVICE pointers + sizes + a cudaStream_t, an int
+ * status back (0 = ok).  No torch types.  Every entry point names the reference call site(s)
+ * whose arithmetic it replaces.  The Python mirror of the reference interface
+ * (vae-2_b200/lib/...) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Tensor convention: "act" tensors are channels-last [B][H][W][ld] in fp32 (dtype 0) or bf16
+ * (dtype 1); Cp = padded channel lanes actually used (multiple of 4 / 8), ld >= Cp the pixel
+ * pitch in elements (so a tensor may be a channel slice of a concat buffer).  Pad lanes are 0.
+ * "nchw" tensors are the reference's own layout: contiguous fp32 [B][C][H][W].
+ * All functions are asynchronous on `stream` and re-entrant (no global state).
+ */
+#ifndef VAE2_B200_H_
+#define VAE2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAE2_ABI_VERSION 1
+
+typedef void* vae2_stream_t; /* cudaStream_t */
+
+/* status codes */
+enum { VAE2_STATUS_OK = 0, VAE2_STATUS_BAD_ARG = 1, VAE2_STATUS_CUDA = 2, VAE2_STATUS_UNSUPPORTED = 3 };
+
+int vae2_abi_version(void);
+const char* vae2_status_string(int status);
+/* last CUDA error string seen by this library on the calling thread's device */
+const char* vae2_last_cuda_error(void);
+
+/* ---- layout: the reference's NCHW fp32 tensors <-> internal channels-last ------------------ */
+/* xs[i].to(device) inputs, lib/core/function.py:487-489; torch.cat inputs, lib/utils/utils.py:77,105 */
+int vae2_nchw_to_act(const float* src, void* dst, int dtype, int B, int C, int Cp, int H, int W, int ld,
+                     int src_ctot, int src_coff, vae2_stream_t stream);
+/* network outputs (predictions, mu/logvar maps), torch.cat of head outputs enc_hrnet.py:845 */
+int vae2_act_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, int W, int ld, int dst_ctot,
+                     int dst_coff, int accumulate, vae2_stream_t stream);
+/* torch.cat along channels (enc_hrnet.py:825-826, 839, 885, 943) done as slice writes */
+int vae2_slice_copy(const void* src, void* dst, int dtype, int64_t npix, int Cp, int ld_src, int ld_dst,
+                    int accumulate, vae2_stream_t stream);
+/* HighResolutionNet._gen_code_map, enc_hrnet.py:454-462 */
+int vae2_code_broadcast(const float* code, void* dst, int dtype, int B, int Z, int Zp, int H, int W, int ld,
+                        vae2_stream_t stream);
+
+/* ---- weights: OIHW nn.Conv2d parameters <-> GEMM operand layouts ---------------------------- */
+typedef struct {
+    const float* w;      /* OIHW fp32 (pack: source, unpack: destination gradient) */
+    float* wp;           /* [tap][Cin_p][Cout_p] fp32 (pack: dest, unpack: source) or NULL */
+    float* wpT;          /* [tap][Cout_p][Cin_p] fp32 or NULL */
+    void* wq;            /* [tap][Cout_p][Cin_p] bf16 or NULL */
+    void* wqT;           /* [tap][Cin_p][Cout_p] bf16 or NULL */
+    const int32_t* cin_map; /* logical input channel -> physical lane (concat inputs), NULL = identity */
+    int32_t Cout, Cin, k, Cin_p, Cout_p, reserved;
+} vae2_pack_desc;        /* array lives in DEVICE memory */
+int vae2_pack_weights(const vae2_pack_desc* descs_dev, int n, vae2_stream_t stream);
+int vae2_unpack_wgrad(const vae2_pack_desc* descs_dev, int n, int accumulate, vae2_stream_t stream);
+
+/* ---- convolution: every nn.Conv2d site of enc_hrnet.py (3x3 s1/s2 p1, 1x1) ------------------ */
+typedef struct {
+    int32_t B, H, W, Cin_p, ldx;
+    int32_t Ho, Wo, Cout_p, ldy;
+    int32_t k, stride, pad;
+} vae2_conv_geom;
+/* engine: 0 = CUDA-core fp32 FMA (exact fp32), 1 = tcgen05/TMEM/TMA (bf16 operands, dtype must be 1) */
+int vae2_conv2d_fwd(const void* x, const void* w_packed, const float* bias, void* y, int dtype,
+                    const vae2_conv_geom* g, int engine, vae2_stream_t stream);
+int vae2_conv2d_dgrad(const void* dy, const void* w_packed_t, void* dx, int dtype, const vae2_conv_geom* g,
+                      int accumulate, int engine, vae2_stream_t stream);
+/* dw_packed fp32 [tap][Cin_p][Cout_p], must be zeroed by the caller (split-K accumulation) */
+int vae2_conv2d_wgrad(const void* x, const void* dy, float* dw_packed, int dtype, const vae2_conv_geom* g,
+                      int engine, vae2_stream_t stream);
+int vae2_bias_grad(const void* dy, float* dbias, int dtype, int64_t npix, int C, int ld, int accumulate,
+                   vae2_stream_t stream);
+int vae2_conv2d_tc_supported(const vae2_conv_geom* g);
+
+/* ---- batch norm: BatchNorm2d(momentum=0.01) / SyncBatchNorm, enc_hrnet.py:22-23, train.py:217 - */
+int vae2_bn_max_partials(void);
+/* per-CTA Welford partials [n_partials][3][Cp] = (count, mean, M2); *n_partials is a HOST out */
+int vae2_bn_stats(const void* y, float* partials, int* n_partials, int dtype, int64_t npix, int Cp, int ld,
+                  vae2_stream_t stream);
+/* merge partial sets into one [3][Cp] set (the per-rank message of the SyncBN all-gather) */
+int vae2_bn_merge(const float* partials, int n_partials, int Cp, float* merged, vae2_stream_t stream);
+/* merge + mean/invstd + scale=gamma*invstd, shift=beta-mean*scale + running stats + num_batches_tracked */
+int vae2_bn_finalize(const float* partials, int n_partials, int C, int Cp, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                     float eps, float* mean, float* invstd, float* scale, float* shift, vae2_stream_t stream);
+int vae2_bn_eval_coeffs(int C, int Cp, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift, vae2_stream_t stream);
+/* out = [relu](scale*y + shift [+ res])   (BasicBlock/Bottleneck tails, enc_hrnet.py:46-62, 83-103) */
+int vae2_bn_apply(const void* y, const void* res, void* out, int dtype, int64_t npix, int Cp, int ld_y,
+                  int ld_res, int ld_out, const float* scale, const float* shift, int relu, vae2_stream_t stream);
+int vae2_bn_bwd_reduce(const void* g, const void* a, const void* y, float* partials, int* n_partials, int dtype,
+                       int64_t npix, int Cp, int ld_g, int ld_a, int ld_y, const float* mean, const float* invstd,
+                       int relu, vae2_stream_t stream);
+int vae2_bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, vae2_stream_t stream);
+int vae2_bn_bwd_coeffs(const float* sums_global, int C, int Cp, float inv_count, float* dgamma, float* dbeta,
+                       int accumulate_param, const float* sums_local, float* c1, float* c2, vae2_stream_t stream);
+int vae2_bn_bwd_elemt(const void* g, const void* a, const void* y, void* dy, void* dres, int dtype, int64_t npix,
+                      int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                      const float* invstd, const float* scale, const float* c1, const float* c2, int relu,
+                      int acc_dy, int acc_dres, vae2_stream_t stream);
+
+/* ---- branch fusion / upsampling: HighResolutionModule.forward enc_hrnet.py:233-248, :833-839 -- */
+typedef struct { const void* ptr; int32_t H, W, ld; } vae2_fuse_src;        /* HOST array */
+typedef struct { void* ptr; int32_t ld, accumulate; } vae2_fuse_dst;         /* HOST array */
+int vae2_fuse_sum(const vae2_fuse_src* srcs, int nsrc, void* out, int dtype, int B, int H, int W, int Cp,
+                  int ld_out, int relu, vae2_stream_t stream);
+int vae2_fuse_bwd_same(const void* g, const void* out, const vae2_fuse_dst* dsts, int ndst, int dtype,
+                       int64_t npix, int Cp, int ld_g, int ld_out, int relu, vae2_stream_t stream);
+int vae2_fuse_bwd_up(const void* g, const void* out, void* gsrc, int dtype, int B, int H, int W, int Hs, int Ws,
+                     int Cp, int ld_g, int ld_out, int ld_gsrc, int relu, int accumulate, vae2_stream_t stream);
+
+/* ---- ELBO terms: utils.py:78-119 (reparam, finite check), criterion.py:61-103 (L1, KL, LSGAN) - */
+typedef struct {
+    int32_t kind, slot;   /* kind 0 = L1, 1 = reparam+KL, 2 = LSGAN; slot = output accumulator */
+    const float* a;       /* L1: predict | KL: eps (or NULL) | GAN: sample        (nchw fp32) */
+    const float* b;       /* L1: target  | KL: muvar [B,2Z,H,W]                   (nchw fp32) */
+    float* out;           /* KL: z [B,Z,H,W] or NULL */
+    float target, scale;
+    int32_t Z, HW;
+    int64_t n;
+    int32_t prior, reserved;
+} vae2_elbo_seg;          /* DEVICE array */
+typedef struct {
+    int32_t kind, reserved0;
+    const float* a;
+    const float* b;
+    const float* gz;      /* KL: dL/dz or NULL */
+    float* grad;          /* L1/GAN: d/d a ; KL: d/d muvar */
+    const float* gout;    /* device scalar upstream gradient of the term (NULL = 1) */
+    float target, scale;
+    int32_t Z, HW;
+    int64_t n;
+    int32_t accumulate, prior;
+} vae2_elbo_bwd_seg;      /* DEVICE array */
+int vae2_elbo_acc_floats(void);  /* floats the caller must provide in `acc` */
+/* acc[0..nslots) receive the term sums; nonfinite[seg] counts inf/nan in z / predictions */
+int vae2_elbo_terms(const vae2_elbo_seg* segs_dev, int nseg, float* acc, int nslots, int32_t* nonfinite,
+                    vae2_stream_t stream);
+int vae2_elbo_terms_bwd(const vae2_elbo_bwd_seg* segs_dev, int nseg, vae2_stream_t stream);
+
+/* ---- optimizer: torch.optim.Adam as configured at tools/train.py:251-261 --------------------- */
+int vae2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, const int64_t* step_dev, float grad_scale, vae2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAE2_B200_H_ */

@@ -1,0 +1,117 @@
+// Internal C++ declarations of the kernel launchers (one translation unit per family).
+// The public, reference-facing boundary is the C ABI in include/vae2_b200.h (api.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vae2 {
+
+struct PackDesc {
+    const float* w;        // OIHW fp32 parameter (pack source / unpack destination)
+    float* wp;             // [tap][Cin_p][Cout_p] fp32 (pack dest / unpack source), may be null
+    float* wpT;            // [tap][Cout_p][Cin_p] fp32, may be null
+    __nv_bfloat16* wq;     // [tap][Cout_p][Cin_p] bf16, may be null
+    __nv_bfloat16* wqT;    // [tap][Cin_p][Cout_p] bf16, may be null
+    const int* cin_map;    // logical input channel -> physical lane, null = identity
+    int Cout, Cin, k, Cin_p, Cout_p;
+    int _pad;
+};
+
+struct ConvGeom {
+    int B, H, W, Cin_p, ldx;     // input  [B][H][W][ldx], Cin_p lanes used
+    int Ho, Wo, Cout_p, ldy;     // output [B][Ho][Wo][ldy], Cout_p lanes used
+    int k, stride, pad;
+};
+
+// layout.cu
+int nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int Cp, int H, int W, int ld,
+                 int src_ctot, int src_coff, cudaStream_t st);
+int nhwc_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, int W, int ld, int dst_ctot,
+                 int dst_coff, int accumulate, cudaStream_t st);
+int slice_copy(const void* src, void* dst, int dtype, long long P, int Cp, int ld_src, int ld_dst, int accumulate,
+               cudaStream_t st);
+int code_broadcast(const float* code, void* dst, int dtype, int B, int Z, int Zp, int H, int W, int ld, cudaStream_t st);
+int pack_weights(const PackDesc* descs_dev, int n, cudaStream_t st);
+int unpack_wgrad(const PackDesc* descs_dev, int n, int accumulate, cudaStream_t st);
+
+// conv_simt.cu  (CUDA-core fp32-accumulate implicit GEMM; exact-fp32 path and cross-check)
+int conv_fwd_simt(const void* x, const float* wp, const float* bias, void* y, int dtype, const ConvGeom& g, cudaStream_t st);
+int conv_dgrad_simt(const void* dy, const float* wpT, void* dx, int dtype, const ConvGeom& g, int accumulate, cudaStream_t st);
+int conv_wgrad_simt(const void* x, const void* dy, float* dwp, int dtype, const ConvGeom& g, cudaStream_t st);
+int bias_grad(const void* dy, float* dbias, int dtype, long long P, int C, int ld, int accumulate, cudaStream_t st);
+
+// bn.cu
+int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, long long P, int Cp, int ld, cudaStream_t st);
+int bn_stats_max_partials();
+int bn_merge(const float* partials, int n_partials, int Cp, float* merged, cudaStream_t st);
+int bn_finalize(const float* parts, int n_parts, int C, int Cp, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
+int bn_eval_coeffs(int C, int Cp, const float* gamma, const float* beta, const float* running_mean,
+                   const float* running_var, float eps, float* scale, float* shift, cudaStream_t st);
+int bn_apply(const void* y, const void* res, void* out, int dtype, long long P, int Cp, int ld_y, int ld_res, int ld_out,
+             const float* scale, const float* shift, int relu, cudaStream_t st);
+int bn_bwd_reduce(const void* g, const void* a, const void* y, float* partials, int* n_partials_out, int dtype,
+                  long long P, int Cp, int ld_g, int ld_a, int ld_y, const float* mean, const float* invstd, int relu,
+                  cudaStream_t st);
+int bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, cudaStream_t st);
+int bn_bwd_coeffs(const float* sums, int C, int Cp, float inv_count, float* dgamma, float* dbeta, int accumulate_param,
+                  const float* sums_for_param, float* c1, float* c2, cudaStream_t st);
+int bn_bwd_elemt(const void* g, const void* a, const void* y, void* dy, void* dres, int dtype, long long P, int Cp,
+                 int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean, const float* invstd,
+                 const float* scale, const float* c1, const float* c2, int relu, int acc_dy, int acc_dres,
+                 cudaStream_t st);
+
+// fuse.cu
+struct FuseSrc { const void* ptr; int H, W, ld; };
+int fuse_sum(const FuseSrc* srcs, int nsrc, void* out, int dtype, int B, int H, int W, int Cp, int ld_out, int relu,
+             cudaStream_t st);
+struct FuseDst { void* ptr; int ld; int accumulate; };
+int fuse_bwd_same(const void* g, const void* out, const FuseDst* dsts, int ndst, int dtype, long long P, int Cp,
+                  int ld_g, int ld_out, int relu, cudaStream_t st);
+int fuse_bwd_up(const void* g, const void* out, void* gsrc, int dtype, int B, int H, int W, int Hs, int Ws, int Cp,
+                int ld_g, int ld_out, int ld_gsrc, int relu, int accumulate, cudaStream_t st);
+
+// elbo.cu
+struct ElboSeg {
+    int kind;            // 0 = L1, 1 = reparam+KL, 2 = LSGAN
+    int slot;            // which accumulator the term adds into
+    const float* a;      // L1: predict (NCHW fp32) | KL: eps (NCHW fp32) or null | GAN: sample (NCHW fp32)
+    const float* b;      // L1: target           | KL: muvar (NCHW fp32 [B,2Z,H,W])
+    float* out;          // KL: z out (NCHW fp32), may be null
+    float target;        // GAN: 1 (real) / 0 (fake)
+    float scale;         // term multiplier (1/B, 0.5/B ...)
+    int Z, HW;           // KL: latent channels and pixels per map
+    long long n;         // elements (L1/GAN: numel ; KL: B*Z*HW)
+    int prior;           // KL: 1 = z = eps (prior sampling, utils.py:88-90)
+    int _pad;
+};
+int elbo_terms(const ElboSeg* segs_dev, int nseg, float* acc, int nslots, int* nonfinite, cudaStream_t st);
+int elbo_acc_floats();
+struct ElboBwdSeg {
+    int kind;            // 0 = L1, 1 = reparam+KL, 2 = LSGAN
+    int _pad0;
+    const float* a;      // as forward
+    const float* b;
+    const float* gz;     // KL: upstream dL/dz (NCHW fp32) or null
+    float* grad;         // L1/GAN: d/d predict|sample ; KL: d/d muvar
+    const float* gout;   // device scalar: upstream gradient of the term's loss value (or null = 1)
+    float target, scale; // as forward; scale already includes lambda
+    int Z, HW;
+    long long n;
+    int accumulate;
+    int prior;
+};
+int elbo_terms_bwd(const ElboBwdSeg* segs_dev, int nseg, cudaStream_t st);
+
+// adam.cu
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, const long long* step_dev, float grad_scale, cudaStream_t st);
+
+// conv_tc.cu (tcgen05 / TMEM / TMA implicit GEMM, bf16)
+int conv_fwd_tc(const void* x, const void* wq, const float* bias, void* y, const ConvGeom& g, float* stats_partials,
+                cudaStream_t st);
+int conv_tc_supported(const ConvGeom& g);
+
+}  // namespace vae2
