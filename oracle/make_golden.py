@@ -93,6 +93,7 @@ def hrnet_case(fname, cfg_name, B, H, W, wmode, enc_hrnet, rutils, rcrit, keep_g
     sd = g.state_dict()
     O.fill_state_dict(sd, seed_tag=fname, mode=wmode)
     g.load_state_dict(sd)
+    sd0 = {k: v.clone() for k, v in sd.items()}   # state_dict() aliases the live buffers: keep a snapshot
     Z = cfg.MODEL.EXTRA.Z_DIM
     xt, x2t, x3t = O.make_clips(fname, B, H, W)
     eps_z, code = O.make_eps(fname, B, Z, H, W)
@@ -125,7 +126,7 @@ def hrnet_case(fname, cfg_name, B, H, W, wmode, enc_hrnet, rutils, rcrit, keep_g
     out["d_grad_names"], out["d_grad_norms"], out["d_grad_sums"] = n, nr, sm
 
     # --- eval-mode prior sampling (inference path, function.py:125-136) ---
-    g.load_state_dict(sd)  # back to the pre-step running stats
+    g.load_state_dict(sd0)  # back to the pre-step running stats
     g.eval()
     with torch.no_grad(), RandnQueue(eps_z + [code]):
         losses, x1e, x2e, x3e = g(xt=xt, x2t=x2t, x3t=x3t, multiplier=1.0, sampling_mode="prior_sampling")

@@ -1,0 +1,660 @@
+"""Static execution plans for the VAE^2 networks.
+
+A network (or a single block) is *recorded* once per (input shapes, mode) into a Plan: a
+flat list of kernel launches over pre-allocated channels-last buffers.  Forward and backward
+are then replays of that list on one CUDA stream -- eagerly, or as a captured CUDA graph --
+with no per-op Python/autograd work on the hot path.  This replaces the reference's
+op-by-op nn.Module execution (lib/models/enc_hrnet.py forward methods) while keeping its
+parameters, state_dict and autograd-visible inputs/outputs.
+
+Only plumbing uses torch here (device memory, streams, torch.distributed for SyncBN
+all-gathers); every arithmetic op is a call into libvae2_b200.so through the C ABI.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import native as N
+
+BN_EPS_DEFAULT = 1e-5
+
+
+class Precision:
+    def __init__(self, name, code, tdtype, seg_align, tot_align):
+        self.name, self.code, self.tdtype = name, code, tdtype
+        self.seg_align, self.tot_align = seg_align, tot_align
+        self.esize = 4 if code == 0 else 2
+
+
+PRECISIONS = {
+    "fp32": Precision("fp32", 0, torch.float32, 4, 4),
+    "bf16": Precision("bf16", 1, torch.bfloat16, 8, 16),
+}
+
+
+def pad_to(c, a):
+    return (c + a - 1) // a * a
+
+
+def conv_out(n, k, s):
+    p = k // 2
+    return (n + 2 * p - k) // s + 1
+
+
+class Act:
+    """A channels-last activation [B][H][W][ld] (possibly a channel slice of a wider root)."""
+
+    def __init__(self, plan, C_, H, W, root=None, c_off=0, Cp=None, name=""):
+        self.plan, self.C, self.H, self.W, self.B = plan, C_, H, W, plan.B
+        self.name = name
+        pr = plan.prec
+        if root is None:
+            self.Cp = pad_to(C_, pr.tot_align) if Cp is None else Cp
+            self.buf = torch.zeros(self.B * H * W * self.Cp, dtype=pr.tdtype, device=plan.device)
+            self.ld, self.c_off, self.parent = self.Cp, 0, None
+        else:
+            self.Cp = Cp
+            self.buf, self.ld, self.c_off, self.parent = root.buf, root.ld, root.c_off + c_off, root
+        self._grad = None
+        self.needs_grad = plan.training
+        self.cin_map = None      # logical channel -> physical lane, for concat roots
+        self.grad_written = False
+
+    @property
+    def npix(self):
+        return self.B * self.H * self.W
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + self.c_off * self.plan.prec.esize
+
+    @property
+    def root(self):
+        a = self
+        while a.parent is not None:
+            a = a.parent
+        return a
+
+    def grad(self):
+        """Gradient buffer with the same geometry (a slice of the root's gradient for slices)."""
+        if self._grad is None:
+            if self.parent is None:
+                g = Act.__new__(Act)
+                g.__dict__.update(self.__dict__)
+                g.buf = torch.zeros_like(self.buf)
+                g._grad, g.parent = None, None
+                self._grad = g
+            else:
+                pg = self.parent.grad()
+                g = Act.__new__(Act)
+                g.__dict__.update(self.__dict__)
+                g.buf, g.parent, g._grad = pg.buf, pg, None
+                self._grad = g
+        return self._grad
+
+    # gradient "first write vs accumulate" bookkeeping lives on the root buffer
+    def take_acc_flag(self):
+        r = self.root
+        acc = r.grad_written
+        r.grad_written = True
+        return 1 if acc else 0
+
+    def to_nchw(self):
+        """Debug/test helper: logical NCHW fp32 copy of this activation."""
+        v = self.buf.view(self.B, self.H, self.W, self.ld)[..., self.c_off:self.c_off + self.C]
+        return v.permute(0, 3, 1, 2).float().contiguous()
+
+
+class Plan:
+    """Recorded launch list + buffers for one network call signature."""
+
+    def __init__(self, device, B, prec, training, bn_batch_stats=None, world_size=1, process_group=None):
+        self.device, self.B, self.prec, self.training = device, B, PRECISIONS[prec], training
+        # training: record a backward program.  bn_batch_stats: BN normalises with batch statistics
+        # (module.training), which also holds for a train-mode forward under torch.no_grad().
+        self.bn_batch_stats = training if bn_batch_stats is None else bn_batch_stats
+        self.world_size, self.group = world_size, process_group
+        self.fwd, self.bwd = [], []          # lists of zero-arg callables taking (stream_ptr)
+        self.pre_fwd, self.post_fwd = [], []  # eager: input conversion / output conversion
+        self.pre_bwd, self.post_bwd = [], []
+        self.ops = []
+        self.params = []                      # nn.Parameters in registration order
+        self._param_index = {}
+        self._grad_off = []
+        self.flat_grad = None
+        self._wp_sizes, self._wpT_sizes = [], []
+        self.wp_flat = self.wpT_flat = self.dwp_flat = None
+        self.pack_descs = []                  # filled at finalize
+        self.inputs, self.outputs = [], []
+        self.keep = []                        # keep-alive for ctypes arrays / tensors
+        self.busy = False
+        self.graph_fwd = self.graph_bwd = None
+        self.n_launch_fwd = self.n_launch_bwd = 0
+
+    # ---- registration ------------------------------------------------------------------
+    def param(self, p):
+        key = id(p)
+        if key not in self._param_index:
+            self._param_index[key] = len(self.params)
+            self.params.append(p)
+        return self._param_index[key]
+
+    def new_act(self, C_, H, W, name=""):
+        return Act(self, C_, H, W, name=name)
+
+    def concat(self, Cs, H, W, name="cat"):
+        """A buffer made of padded channel segments; returns (root, [slice acts])."""
+        pr = self.prec
+        seg_p = [pad_to(c, pr.seg_align) for c in Cs]
+        total = pad_to(sum(seg_p), pr.tot_align)
+        root = Act(self, sum(Cs), H, W, Cp=total, name=name)
+        cmap, off, slices = [], 0, []
+        for c, cp in zip(Cs, seg_p):
+            slices.append(Act(self, c, H, W, root=root, c_off=off, Cp=cp, name="%s[%d]" % (name, off)))
+            cmap += list(range(off, off + c))
+            off += cp
+        root.cin_map = cmap
+        return root, slices
+
+    def add(self, op):
+        self.ops.append(op)
+        return op
+
+    # ---- build -------------------------------------------------------------------------
+    def finalize(self):
+        dev = self.device
+        # flat parameter-gradient arena
+        off = 0
+        for p in self.params:
+            self._grad_off.append(off)
+            off += pad_to(p.numel(), 4)
+        self.flat_grad = torch.zeros(max(off, 4), dtype=torch.float32, device=dev)
+        # packed weight arenas
+        convs = [o for o in self.ops if isinstance(o, ConvOp)]
+        tot = 0
+        for o in convs:
+            o.w_off = tot
+            tot += pad_to(o.taps * o.x.root_cp() * o.y.Cp, 4)
+        self.wp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev)
+        self.wpT_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
+        self.dwp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
+        # pack / unpack descriptor tables (device resident)
+        pk = (N.PackDesc * max(len(convs), 1))()
+        up = (N.PackDesc * max(len(convs), 1))()
+        for i, o in enumerate(convs):
+            w = o.conv.weight
+            cmap_ptr = None
+            if o.x.cin_map is not None:
+                t = torch.tensor(o.x.cin_map, dtype=torch.int32, device=dev)
+                self.keep.append(t)
+                cmap_ptr = t.data_ptr()
+            cin_p, cout_p = o.x.root_cp(), o.y.Cp
+            common = dict(cin_map=cmap_ptr, Cout=w.shape[0], Cin=w.shape[1], k=w.shape[2], Cin_p=cin_p, Cout_p=cout_p)
+            pk[i] = N.PackDesc(w=w.data_ptr(), wp=self.wp_flat.data_ptr() + 4 * o.w_off,
+                               wpT=(self.wpT_flat.data_ptr() + 4 * o.w_off) if self.training else None, **common)
+            if self.training:
+                gi = self.param(w)
+                up[i] = N.PackDesc(w=self.flat_grad.data_ptr() + 4 * self._grad_off[gi],
+                                   wp=self.dwp_flat.data_ptr() + 4 * o.w_off, **common)
+        self._pk_host, self._up_host = pk, up
+        self.pk_dev = torch.frombuffer(bytearray(bytes(pk)), dtype=torch.uint8).to(dev)
+        self.up_dev = torch.frombuffer(bytearray(bytes(up)), dtype=torch.uint8).to(dev)
+        self.n_convs = len(convs)
+        # forward program
+        self.fwd.append(lambda st: N.call.vae2_pack_weights(self.pk_dev.data_ptr(), self.n_convs, st))
+        for o in self.ops:
+            o.emit_fwd(self)
+        # backward program (reverse order; accumulate flags resolved statically)
+        if self.training:
+            nbytes = self.dwp_flat.numel() * 4
+            dptr = self.dwp_flat
+            self.bwd.append(lambda st: dptr.zero_())
+            for o in reversed(self.ops):
+                o.emit_bwd(self)
+            self.bwd.append(lambda st: N.call.vae2_unpack_wgrad(self.up_dev.data_ptr(), self.n_convs, 0, st))
+        self.n_launch_fwd, self.n_launch_bwd = len(self.fwd), len(self.bwd)
+        return self
+
+    def grad_view(self, p):
+        i = self._param_index[id(p)]
+        return self.flat_grad[self._grad_off[i]:self._grad_off[i] + p.numel()].view(p.shape)
+
+    def grad_ptr(self, p):
+        return self.flat_grad.data_ptr() + 4 * self._grad_off[self.param(p)]
+
+    # ---- run ---------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def run_forward(self, use_graph=False):
+        st = self._stream()
+        for f in self.pre_fwd:
+            f(st)
+        if use_graph:
+            if self.graph_fwd is None:
+                self.graph_fwd = self._capture(self.fwd)
+            self.graph_fwd.replay()
+        else:
+            for f in self.fwd:
+                f(st)
+        for f in self.post_fwd:
+            f(st)
+
+    def run_backward(self, use_graph=False):
+        st = self._stream()
+        for f in self.pre_bwd:
+            f(st)
+        if use_graph:
+            if self.graph_bwd is None:
+                self.graph_bwd = self._capture(self.bwd)
+            self.graph_bwd.replay()
+        else:
+            for f in self.bwd:
+                f(st)
+        for f in self.post_bwd:
+            f(st)
+
+    def _capture(self, prog):
+        # warm-up run on a side stream, then capture the same launch list
+        torch.cuda.synchronize(self.device)
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for f in prog:
+                f(s.cuda_stream)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for f in prog:
+                f(s.cuda_stream)
+        return g
+
+
+def _root_cp(self):
+    return self.Cp
+
+
+Act.root_cp = _root_cp
+
+
+# =============================================================================================
+# ops
+# =============================================================================================
+class InputOp:
+    """External NCHW fp32 tensor (channel window) -> channels-last activation(s).  Eager."""
+
+    def __init__(self, plan, slot, C_, H, W, src_ctot, src_coff, dsts, needs_grad):
+        self.slot, self.C, self.H, self.W = slot, C_, H, W
+        self.src_ctot, self.src_coff, self.dsts, self.needs_grad = src_ctot, src_coff, dsts, needs_grad
+        for d in dsts:
+            d.needs_grad = needs_grad and plan.training
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+
+        def run(st, self=self):
+            src = plan.cur_inputs[self.slot]
+            for d in self.dsts:
+                N.call.vae2_nchw_to_act(src.data_ptr(), d.ptr, pr.code, plan.B, self.C, d.Cp, self.H, self.W, d.ld,
+                                        self.src_ctot, self.src_coff, st)
+        plan.pre_fwd.append(run)
+
+    def emit_bwd(self, plan):
+        if not (self.needs_grad and plan.training):
+            return
+        pr = plan.prec
+
+        def run(st, self=self):
+            dst = plan.cur_input_grads[self.slot]
+            for i, d in enumerate(self.dsts):
+                N.call.vae2_act_to_nchw(d.grad().ptr, dst.data_ptr(), pr.code, plan.B, self.C, self.H, self.W, d.ld,
+                                        self.src_ctot, self.src_coff, 1, st)   # dst starts zero-filled
+        plan.post_bwd.append(run)
+
+
+class CodeOp:
+    """Per-sample code [B,Z,1,1] broadcast over H x W into a slice (enc_hrnet.py:454-462). Eager."""
+
+    def __init__(self, plan, slot, Z, dst):
+        self.slot, self.Z, self.dst = slot, Z, dst
+        dst.needs_grad = False
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+
+        def run(st, self=self):
+            code = plan.cur_inputs[self.slot]
+            d = self.dst
+            N.call.vae2_code_broadcast(code.data_ptr(), d.ptr, pr.code, plan.B, self.Z, d.Cp, d.H, d.W, d.ld, st)
+        plan.pre_fwd.append(run)
+
+    def emit_bwd(self, plan):
+        pass
+
+
+class OutputOp:
+    """Channels-last activation -> channel window of an external NCHW fp32 tensor.  Eager."""
+
+    def __init__(self, plan, slot, act, dst_ctot, dst_coff):
+        self.slot, self.act, self.dst_ctot, self.dst_coff = slot, act, dst_ctot, dst_coff
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+
+        def run(st, self=self):
+            a = self.act
+            dst = plan.cur_outputs[self.slot]
+            N.call.vae2_act_to_nchw(a.ptr, dst.data_ptr(), pr.code, plan.B, a.C, a.H, a.W, a.ld, self.dst_ctot,
+                                    self.dst_coff, 0, st)
+        plan.post_fwd.append(run)
+
+    def emit_bwd(self, plan):
+        pr = plan.prec
+        a = self.act
+        g = a.grad()
+        a.take_acc_flag()   # the upstream gradient is the first writer of this buffer
+
+        def run(st, self=self):
+            src = plan.cur_output_grads[self.slot]
+            if src is None:           # output unused by the loss: its gradient is zero
+                g.buf.zero_()
+                return
+            N.call.vae2_nchw_to_act(src.data_ptr(), g.ptr, pr.code, plan.B, a.C, a.Cp, a.H, a.W, a.ld, self.dst_ctot,
+                                    self.dst_coff, st)
+        plan.pre_bwd.append(run)
+
+
+class ConvOp:
+    """nn.Conv2d 3x3 (s1/s2, p1) or 1x1, optional bias."""
+
+    def __init__(self, plan, x, conv, y=None):
+        k, s = conv.kernel_size[0], conv.stride[0]
+        self.conv, self.x, self.k, self.s, self.taps = conv, x, k, s, k * k
+        Ho, Wo = conv_out(x.H, k, s), conv_out(x.W, k, s)
+        self.y = y if y is not None else plan.new_act(conv.out_channels, Ho, Wo, name="conv")
+        assert (self.y.H, self.y.W) == (Ho, Wo)
+        assert conv.in_channels == x.C, (conv.in_channels, x.C)
+        plan.param(conv.weight)
+        if conv.bias is not None:
+            plan.param(conv.bias)
+        self.w_off = 0
+        self.engine = 0
+
+    def _geom(self):
+        x, y = self.x, self.y
+        return N.ConvGeom(B=x.B, H=x.H, W=x.W, Cin_p=x.Cp, ldx=x.ld, Ho=y.H, Wo=y.W, Cout_p=y.Cp, ldy=y.ld,
+                          k=self.k, stride=self.s, pad=self.k // 2)
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+        g = self._geom()
+        plan.keep.append(g)
+        x, y = self.x, self.y
+        wp = plan.wp_flat.data_ptr() + 4 * self.w_off
+        bias = None
+        if self.conv.bias is not None:
+            # bias padded to Cout_p lanes (pad = 0); refreshed from the parameter every forward
+            bp = torch.zeros(y.Cp, dtype=torch.float32, device=plan.device)
+            plan.keep.append(bp)
+            b = self.conv.bias
+            n = b.numel()
+            plan.fwd.append(lambda st: bp[:n].copy_(b.detach()))
+            bias = bp.data_ptr()
+        gp = C.byref(g)
+        xp, yp, eng = x.ptr, y.ptr, self.engine
+        plan.fwd.append(lambda st: N.call.vae2_conv2d_fwd(xp, wp, bias, yp, pr.code, gp, eng, st))
+
+    def emit_bwd(self, plan):
+        pr = plan.prec
+        g = self._geom()
+        plan.keep.append(g)
+        gp = C.byref(g)
+        x, y = self.x, self.y
+        dy = y.grad()
+        dyp, xp = dy.ptr, x.ptr
+        dwp = plan.dwp_flat.data_ptr() + 4 * self.w_off
+        plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad(xp, dyp, dwp, pr.code, gp, 0, st))
+        if self.conv.bias is not None:
+            db = plan.grad_ptr(self.conv.bias)
+            npix, cb, ldy = y.npix, y.C, y.ld
+            plan.bwd.append(lambda st: N.call.vae2_bias_grad(dyp, db, pr.code, npix, cb, ldy, 0, st))
+        if x.needs_grad:
+            wpT = plan.wpT_flat.data_ptr() + 4 * self.w_off
+            acc = x.take_acc_flag()
+            dxp = x.grad().ptr
+            plan.bwd.append(lambda st: N.call.vae2_conv2d_dgrad(dyp, wpT, dxp, pr.code, gp, acc, 0, st))
+
+
+class BnOp:
+    """BatchNorm2d (+residual)(+ReLU) on a raw conv output; training or eval statistics."""
+
+    def __init__(self, plan, y, bn, relu, residual=None, out=None):
+        self.y, self.bn, self.relu, self.res = y, bn, relu, residual
+        self.out = out if out is not None else plan.new_act(y.C, y.H, y.W, name="bn")
+        assert self.out.Cp == y.Cp or out is not None
+        plan.param(bn.weight)
+        plan.param(bn.bias)
+        self.sync = isinstance(bn, torch.nn.SyncBatchNorm) and plan.world_size > 1
+
+    def emit_fwd(self, plan):
+        pr, dev = plan.prec, plan.device
+        y, out, bn, res = self.y, self.out, self.bn, self.res
+        Cp, C_ = y.Cp, y.C
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.mean, self.invstd = torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
+        self.scale, self.shift = torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
+        eps = float(bn.eps)
+        mom = 0.0 if bn.momentum is None else float(bn.momentum)
+        lanes = min(Cp, out.Cp)
+        if plan.bn_batch_stats or not bn.track_running_stats:
+            maxp = N.lib().vae2_bn_max_partials()
+            self.partials = torch.zeros(maxp * 3 * Cp, **f32)
+            npart = C.c_int(0)
+            plan.keep.append(npart)
+            pp, yp = self.partials.data_ptr(), y.ptr
+            npix, ld = y.npix, y.ld
+            plan.fwd.append(lambda st: N.call.vae2_bn_stats(yp, pp, C.byref(npart), pr.code, npix, Cp, ld, st))
+            rm = bn.running_mean.data_ptr() if bn.running_mean is not None else None
+            rv = bn.running_var.data_ptr() if bn.running_var is not None else None
+            nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
+            gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
+            outs = (self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr())
+            if self.sync:
+                merged = torch.zeros(3 * Cp, **f32)
+                gathered = torch.zeros(plan.world_size * 3 * Cp, **f32)
+                plan.keep += [merged, gathered]
+                mp, gtp, ws, grp = merged.data_ptr(), gathered.data_ptr(), plan.world_size, plan.group
+                plan.fwd.append(lambda st: N.call.vae2_bn_merge(pp, npart.value, Cp, mp, st))
+                plan.fwd.append(lambda st: dist.all_gather_into_tensor(gathered, merged, group=grp))
+                plan.fwd.append(lambda st: N.call.vae2_bn_finalize(gtp, ws, C_, Cp, gp, bp, rm, rv, nbt, mom, eps,
+                                                                   *outs, st))
+            else:
+                plan.fwd.append(lambda st: N.call.vae2_bn_finalize(pp, npart.value, C_, Cp, gp, bp, rm, rv, nbt, mom,
+                                                                   eps, *outs, st))
+        else:
+            gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
+            rm, rv = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            sp, hp = self.scale.data_ptr(), self.shift.data_ptr()
+            plan.fwd.append(lambda st: N.call.vae2_bn_eval_coeffs(C_, Cp, gp, bp, rm, rv, eps, sp, hp, st))
+        yp, op_, rp = y.ptr, out.ptr, (res.ptr if res is not None else None)
+        ldr = res.ld if res is not None else 0
+        sp, hp, relu = self.scale.data_ptr(), self.shift.data_ptr(), 1 if self.relu else 0
+        npix, ldy, ldo = y.npix, y.ld, out.ld
+        plan.fwd.append(lambda st: N.call.vae2_bn_apply(yp, rp, op_, pr.code, npix, lanes, ldy, ldr, ldo, sp, hp,
+                                                        relu, st))
+
+    def emit_bwd(self, plan):
+        pr, dev = plan.prec, plan.device
+        y, out, bn, res = self.y, self.out, self.bn, self.res
+        Cp, C_ = y.Cp, y.C
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = out.grad()
+        maxp = N.lib().vae2_bn_max_partials()
+        parts = torch.zeros(maxp * 2 * Cp, **f32)
+        sums, c1, c2 = torch.zeros(2 * Cp, **f32), torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
+        plan.keep += [parts, sums, c1, c2]
+        npart = C.c_int(0)
+        plan.keep.append(npart)
+        lanes = min(Cp, out.Cp)
+        gp_, ap, yp = g.ptr, out.ptr, y.ptr
+        npix = y.npix
+        relu = 1 if self.relu else 0
+        mp, ip = self.mean.data_ptr(), self.invstd.data_ptr()
+        pp, sp = parts.data_ptr(), sums.data_ptr()
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_reduce(gp_, ap, yp, pp, C.byref(npart), pr.code, npix, lanes,
+                                                             g.ld, out.ld, y.ld, mp, ip, relu, st))
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_finalize(pp, npart.value, C_, lanes, sp, st))
+        dgam, dbet = plan.grad_ptr(bn.weight), plan.grad_ptr(bn.bias)
+        c1p, c2p = c1.data_ptr(), c2.data_ptr()
+        count = npix * (plan.world_size if self.sync else 1)
+        if self.sync:
+            gsum = torch.zeros(2 * Cp, **f32)
+            plan.keep.append(gsum)
+            gsp, grp = gsum.data_ptr(), plan.group
+            plan.bwd.append(lambda st: gsum.copy_(sums))
+            plan.bwd.append(lambda st: dist.all_reduce(gsum, group=grp))
+            plan.bwd.append(lambda st: N.call.vae2_bn_bwd_coeffs(gsp, C_, lanes, 1.0 / count, dgam, dbet, 0, sp, c1p,
+                                                                 c2p, st))
+        else:
+            plan.bwd.append(lambda st: N.call.vae2_bn_bwd_coeffs(sp, C_, lanes, 1.0 / count, dgam, dbet, 0, sp, c1p,
+                                                                 c2p, st))
+        dy = y.grad()
+        acc_dy = y.take_acc_flag()
+        dres_p, ld_dres, acc_res = None, 0, 0
+        if res is not None and res.needs_grad:
+            acc_res = res.take_acc_flag()
+            dres_p, ld_dres = res.grad().ptr, res.ld
+        dyp, scp = dy.ptr, self.scale.data_ptr()
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_elemt(gp_, ap, yp, dyp, dres_p, pr.code, npix, lanes, g.ld,
+                                                            out.ld, y.ld, dy.ld, ld_dres, mp, ip, scp, c1p, c2p, relu,
+                                                            acc_dy, acc_res, st))
+
+
+class FuseOp:
+    """out = [relu](sum_j resize(src_j)); sources at the output size are added as they are,
+    others are bilinearly resized (align_corners=False).  enc_hrnet.py:233-248 / :833-839."""
+
+    def __init__(self, plan, srcs, H, W, relu, out=None):
+        self.srcs, self.relu = srcs, relu
+        C_ = srcs[0].C
+        self.out = out if out is not None else plan.new_act(C_, H, W, name="fuse")
+        self.lanes = min([s.Cp for s in srcs] + [self.out.Cp])
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+        arr = (N.FuseSrc * len(self.srcs))()
+        for i, s in enumerate(self.srcs):
+            arr[i] = N.FuseSrc(ptr=s.ptr, H=s.H, W=s.W, ld=s.ld)
+        plan.keep.append(arr)
+        o, n, relu, lanes = self.out, len(self.srcs), 1 if self.relu else 0, self.lanes
+        op_ = o.ptr
+        plan.fwd.append(lambda st: N.call.vae2_fuse_sum(arr, n, op_, pr.code, o.B, o.H, o.W, lanes, o.ld, relu, st))
+
+    def emit_bwd(self, plan):
+        pr = plan.prec
+        o = self.out
+        g = o.grad()
+        relu, lanes = 1 if self.relu else 0, self.lanes
+        same = [s for s in self.srcs if (s.H, s.W) == (o.H, o.W) and s.needs_grad]
+        ups = [s for s in self.srcs if (s.H, s.W) != (o.H, o.W) and s.needs_grad]
+        gp_, op_ = g.ptr, o.ptr
+        if same:
+            arr = (N.FuseDst * len(same))()
+            for i, s in enumerate(same):
+                acc = s.take_acc_flag()
+                arr[i] = N.FuseDst(ptr=s.grad().ptr, ld=s.ld, accumulate=acc)
+            plan.keep.append(arr)
+            n, npix = len(same), o.npix
+            plan.bwd.append(lambda st: N.call.vae2_fuse_bwd_same(gp_, op_, arr, n, pr.code, npix, lanes, g.ld, o.ld,
+                                                                 relu, st))
+        for s in ups:
+            acc = s.take_acc_flag()
+            sp = s.grad().ptr
+            plan.bwd.append(lambda st, s=s, sp=sp, acc=acc: N.call.vae2_fuse_bwd_up(
+                gp_, op_, sp, pr.code, o.B, o.H, o.W, s.H, s.W, lanes, g.ld, o.ld, s.ld, relu, acc, st))
+
+
+class CopyOp:
+    """dst slice (=) src   (channel concat done as a slice write)."""
+
+    def __init__(self, plan, src, dst):
+        self.src, self.dst = src, dst
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+        s, d = self.src, self.dst
+        lanes = min(s.Cp, d.Cp)
+        plan.fwd.append(lambda st: N.call.vae2_slice_copy(s.ptr, d.ptr, pr.code, s.npix, lanes, s.ld, d.ld, 0, st))
+
+    def emit_bwd(self, plan):
+        pr = plan.prec
+        s, d = self.src, self.dst
+        if not s.needs_grad:
+            return
+        lanes = min(s.Cp, d.Cp)
+        acc = s.take_acc_flag()
+        gs, gd = s.grad().ptr, d.grad().ptr
+        plan.bwd.append(lambda st: N.call.vae2_slice_copy(gd, gs, pr.code, s.npix, lanes, d.ld, s.ld, acc, st))
+
+
+# =============================================================================================
+# recording front-end used by the nn.Module mirrors
+# =============================================================================================
+class Recorder:
+    def __init__(self, plan):
+        self.plan = plan
+        self.n_in = 0
+        self.n_out = 0
+
+    # inputs / outputs ---------------------------------------------------------------------
+    def input(self, C_, H, W, needs_grad, src_ctot=None, src_coff=0, slot=None, into=None):
+        """Declare (a channel window of) external input #slot; `into` lists slice acts to fill."""
+        p = self.plan
+        if slot is None:
+            slot = self.n_in
+            self.n_in += 1
+        dsts = into if into is not None else [p.new_act(C_, H, W, name="in%d" % slot)]
+        p.add(InputOp(p, slot, C_, H, W, src_ctot if src_ctot is not None else C_, src_coff, dsts, needs_grad))
+        return dsts[0] if into is None else dsts
+
+    def new_input_slot(self):
+        s = self.n_in
+        self.n_in += 1
+        return s
+
+    def code(self, slot, Z, dst):
+        self.plan.add(CodeOp(self.plan, slot, Z, dst))
+
+    def output(self, act, dst_ctot=None, dst_coff=0, slot=None):
+        if slot is None:
+            slot = self.n_out
+            self.n_out += 1
+        self.plan.add(OutputOp(self.plan, slot, act, dst_ctot if dst_ctot is not None else act.C, dst_coff))
+        return slot
+
+    def new_output_slot(self):
+        s = self.n_out
+        self.n_out += 1
+        return s
+
+    # compute ------------------------------------------------------------------------------
+    def conv(self, x, conv, y=None):
+        return self.plan.add(ConvOp(self.plan, x, conv, y)).y
+
+    def bn(self, y, bn, relu=False, residual=None, out=None):
+        return self.plan.add(BnOp(self.plan, y, bn, relu, residual, out)).out
+
+    def conv_bn(self, x, conv, bn, relu=False, residual=None, out=None):
+        return self.bn(self.conv(x, conv), bn, relu, residual, out)
+
+    def fuse(self, srcs, H, W, relu=True, out=None):
+        return self.plan.add(FuseOp(self.plan, srcs, H, W, relu, out)).out
+
+    def copy(self, src, dst):
+        self.plan.add(CopyOp(self.plan, src, dst))
+        return dst
+
+    def concat(self, Cs, H, W, name="cat"):
+        return self.plan.concat(Cs, H, W, name)

@@ -1,0 +1,150 @@
+"""nn.Module <-> Plan glue: plan cache, autograd node, precision / graph switches.
+
+An ``EngineModule`` keeps the reference's parameter tree (so ``state_dict`` keys, SyncBN
+conversion, DDP hooks and optimizers all see ordinary nn.Parameters) but executes
+``forward`` as ONE autograd node that replays a recorded Plan (engine/graph.py).
+"""
+import os
+import weakref
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .graph import Plan, Recorder
+
+_STATE = {
+    "precision": os.environ.get("VAE2_PRECISION", "fp32"),
+    "cuda_graphs": os.environ.get("VAE2_CUDA_GRAPHS", "0") == "1",
+    "launches": 0,
+}
+
+
+def set_precision(name):
+    """'fp32' (exact-fp32 storage and FMA) or 'bf16' (bf16 storage, tensor-core convs)."""
+    assert name in ("fp32", "bf16")
+    _STATE["precision"] = name
+
+
+def get_precision():
+    return _STATE["precision"]
+
+
+def use_cuda_graphs(flag):
+    _STATE["cuda_graphs"] = bool(flag)
+
+
+def launch_count():
+    """Kernel-launching calls replayed so far (bench.py's gpu_launches)."""
+    return _STATE["launches"]
+
+
+class _Lease:
+    """Marks a plan busy between forward and the end of backward (or graph destruction)."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        plan.busy = True
+
+    def release(self):
+        if self.plan is not None:
+            self.plan.busy = False
+            self.plan = None
+
+    def __del__(self):
+        self.release()
+
+
+class _PlanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, n_in, *args):
+        inputs = [a.detach().contiguous().float() for a in args[:n_in]]
+        plan.cur_inputs = inputs
+        dev = plan.device
+        outs = [torch.empty((plan.B,) + tuple(s), dtype=torch.float32, device=dev) for s in plan.out_shapes]
+        plan.cur_outputs = outs
+        plan.run_forward(_STATE["cuda_graphs"])
+        _STATE["launches"] += plan.n_launch_fwd + len(plan.pre_fwd) + len(plan.post_fwd)
+        ctx.plan, ctx.n_in, ctx.n_args = plan, n_in, len(args)
+        ctx.in_shapes = [tuple(a.shape) for a in args[:n_in]]
+        ctx.in_needs = [bool(a.requires_grad) for a in args[:n_in]]
+        if plan.training and torch.is_grad_enabled():
+            ctx.lease = _Lease(plan)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan = ctx.plan
+        if not plan.training:
+            raise RuntimeError("vae2_b200: backward through an eval-mode plan is not supported")
+        dev = plan.device
+        plan.cur_output_grads = [None if g is None else g.contiguous().float() for g in gouts]
+        plan.cur_input_grads = [torch.zeros(s, dtype=torch.float32, device=dev) if need else None
+                                for s, need in zip(ctx.in_shapes, ctx.in_needs)]
+        plan.run_backward(_STATE["cuda_graphs"])
+        _STATE["launches"] += plan.n_launch_bwd + len(plan.pre_bwd) + len(plan.post_bwd)
+        flat = plan.flat_grad.clone()
+        pgrads = []
+        for p, off in zip(plan.params, plan._grad_off):
+            pgrads.append(flat[off:off + p.numel()].view(p.shape) if p.requires_grad else None)
+        in_grads = plan.cur_input_grads
+        plan.cur_output_grads = plan.cur_input_grads = None
+        lease = getattr(ctx, "lease", None)
+        if lease is not None:
+            lease.release()
+        return (None, None) + tuple(in_grads) + tuple(pgrads)
+
+
+class EngineModule(nn.Module):
+    """Base for the module mirrors.  Subclasses implement
+
+        _record(self, rec: Recorder, in_shapes, in_needs_grad) -> list of output (C,H,W)
+
+    declaring inputs with ``rec.input``, emitting ops, and declaring outputs with ``rec.output``.
+    """
+
+    def _plans(self):
+        d = self.__dict__.get("_plan_cache")
+        if d is None:
+            d = {}
+            self.__dict__["_plan_cache"] = d   # bypass nn.Module attribute registration
+        return d
+
+    def reset_plans(self):
+        self.__dict__["_plan_cache"] = {}
+
+    def _sync_world(self):
+        if dist.is_available() and dist.is_initialized():
+            if any(isinstance(m, nn.SyncBatchNorm) for m in self.modules()):
+                return dist.get_world_size()
+        return 1
+
+    def _run(self, inputs, tag=""):
+        dev = inputs[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("vae2_b200: this path runs on CUDA devices only (got %s); there is no CPU fallback"
+                               % dev)
+        training = self.training
+        grad_on = torch.is_grad_enabled()
+        needs = tuple(bool(t.requires_grad) and grad_on for t in inputs)
+        shapes = tuple(tuple(t.shape) for t in inputs)
+        world = self._sync_world() if training else 1
+        key = (tag, shapes, needs, training, grad_on, _STATE["precision"], dev.index, world)
+        pool = self._plans().setdefault(key, [])
+        plan = next((p for p in pool if not p.busy), None)
+        if plan is not None and plan.param_ptrs != tuple(p.data_ptr() for p in plan.params):
+            pool.clear()      # parameters were re-allocated (.to(), .cuda(), ...): recorded pointers are stale
+            plan = None
+        if plan is None:
+            with torch.cuda.device(dev):
+                plan = Plan(dev, shapes[0][0], _STATE["precision"], training and grad_on, bn_batch_stats=training,
+                            world_size=world)
+                rec = Recorder(plan)
+                plan.out_shapes = self._record(rec, shapes, needs, tag)
+                plan.finalize()
+                plan.param_ptrs = tuple(p.data_ptr() for p in plan.params)
+            pool.append(plan)
+        params = [p for p in plan.params]
+        with torch.cuda.device(dev):
+            outs = _PlanFn.apply(plan, len(inputs), *inputs, *params)
+        return outs
