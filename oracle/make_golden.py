@@ -117,6 +117,17 @@ def hrnet_case(fname, cfg_name, B, H, W, wmode, enc_hrnet, rutils, rcrit, keep_g
               "D_model_frame.bn1.num_batches_tracked"):
         out["after:" + k] = sd_after[k].numpy().copy()
 
+    # --- the same G step with the reference in float64: the exact-arithmetic yardstick that tells
+    #     rounding noise of a deep fp32 net apart from real disagreement (stored rounded to fp32) ---
+    g64, _ = build_reference(cfg, enc_hrnet, rutils, rcrit)
+    g64.load_state_dict(sd0)
+    g64 = g64.double().train()
+    with RandnQueue([e.double() for e in eps_z] + [code.double()]):
+        l64, a64, b64, c64 = g64(xt=xt.double(), x2t=x2t.double(), x3t=x3t.double(), multiplier=1.0)
+    out["g_losses64"] = np.array([float(l) for l in l64], dtype=np.float64)
+    out["x1p64"], out["x2p64"], out["x3p64"] = (t.detach().float().numpy() for t in (a64, b64, c64))
+    del g64
+
     # --- D step, training mode (continues from the updated BN running stats) ---
     dl = d(x2t=x2t, x2t_predict=x2p.detach())
     d.zero_grad()

@@ -37,7 +37,8 @@ __device__ __forceinline__ float kl_elem(const ElboSeg& s, long long e, int& bad
         if (!finite_f(z)) ++bad;
         s.out[e] = z;
     }
-    return 0.5f * (mu * mu + expf(lv) - lv - 1.f);
+    // expm1f(lv) - lv instead of expf(lv) - lv - 1: no cancellation against 1 when |lv| is small
+    return 0.5f * (mu * mu + (expm1f(lv) - lv));
 }
 
 __global__ void __launch_bounds__(ELBO_THREADS)
@@ -127,7 +128,7 @@ elbo_terms_bwd_kernel(const ElboBwdSeg* __restrict__ segs, int nseg) {
                 const long long im = b * 2 * zhw + rem, iv = im + zhw;
                 const float mu = s.b[im], lv = s.b[iv];
                 float dmu = go * mu;
-                float dlv = go * 0.5f * (expf(lv) - 1.f);
+                float dlv = go * 0.5f * expm1f(lv);
                 if (s.gz != nullptr && !s.prior) {
                     const float gz = s.gz[e];
                     dmu += gz;

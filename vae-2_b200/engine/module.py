@@ -68,7 +68,7 @@ class _PlanFn(torch.autograd.Function):
         ctx.plan, ctx.n_in, ctx.n_args = plan, n_in, len(args)
         ctx.in_shapes = [tuple(a.shape) for a in args[:n_in]]
         ctx.in_needs = [bool(a.requires_grad) for a in args[:n_in]]
-        if plan.training and torch.is_grad_enabled():
+        if plan.training:   # plan.training already implies grad mode at the call site (grad mode is off in here)
             ctx.lease = _Lease(plan)
         return tuple(outs)
 
