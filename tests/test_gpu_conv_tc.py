@@ -1,0 +1,94 @@
+"""GPU: the tcgen05/TMEM/TMA convolution (engine 1) against torch CPU conv2d on bf16-rounded data."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import E, O, rel_err
+from test_gpu_kernels import dev, st, pad, to_act, from_act, table
+
+N = E.native
+pytestmark = pytest.mark.gpu
+
+TC_CASES = [  # (B, Cin, Cout, H, W, k, bias)
+    (1, 64, 64, 8, 128, 3, False),     # one full-width strip per tile, KC=64 (SWIZZLE_128B)
+    (1, 64, 64, 32, 64, 3, False),     # TW=64, TH=2
+    (2, 18, 18, 17, 23, 3, False),     # odd size, Cin_p=32 (SWIZZLE_64B), patches overhang the image
+    (1, 36, 36, 16, 32, 3, False),     # Cin_p=48 -> KC=16 (SWIZZLE_32B), 3 chunks per tap
+    (1, 64, 256, 9, 11, 1, False),     # 1x1, N=256
+    (1, 256, 64, 12, 40, 1, False),    # 1x1, K=256 (4 chunks)
+    (2, 270, 270, 16, 32, 1, True),    # head conv: Cp=272, two N tiles of 144, bias
+    (1, 144, 144, 8, 8, 3, False),     # low-res branch, TW=8 TH=16
+    (1, 72, 72, 33, 47, 3, False),
+    (3, 9, 64, 20, 36, 3, False),      # stem
+]
+
+
+def pack_bf16(w, Cin_p, Cout_p):
+    Cout, Cin, k, _ = w.shape
+    wd = w.contiguous().to(dev())
+    n = k * k * Cin_p * Cout_p
+    wq = torch.zeros(n, dtype=torch.bfloat16, device=dev())
+    wqT = torch.zeros(n, dtype=torch.bfloat16, device=dev())
+    d = (N.PackDesc * 1)()
+    d[0] = N.PackDesc(w=wd.data_ptr(), wq=wq.data_ptr(), wqT=wqT.data_ptr(), Cout=Cout, Cin=Cin, k=k, Cin_p=Cin_p, Cout_p=Cout_p)
+    t = table(d)
+    N.call.vae2_pack_weights(t.data_ptr(), 1, st())
+    torch.cuda.synchronize()
+    return wq, wqT
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_fwd_dgrad(case):
+    B, Cin, Cout, H, W, k, use_bias = case
+    tag = "tc%s" % (case,)
+    x = O.det_normal(tag + "x", (B, Cin, H, W)).bfloat16().float()
+    w = O.det_normal(tag + "w", (Cout, Cin, k, k), (2.0 / (Cin * k * k)) ** 0.5).bfloat16().float()
+    bias = O.det_normal(tag + "b", (Cout,), 0.1) if use_bias else None
+    xr = x.clone().requires_grad_(True)
+    yr = F.conv2d(xr, w, bias, stride=1, padding=k // 2)
+    gy = O.det_normal(tag + "gy", tuple(yr.shape)).bfloat16().float()
+    yr.backward(gy)
+
+    xa, Cin_p = to_act(x, "bf16", pad(Cin, 16))
+    Cout_p = pad(Cout, 16)
+    wq, wqT = pack_bf16(w, Cin_p, Cout_p)
+    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin_p, ldx=Cin_p, Ho=H, Wo=W, Cout_p=Cout_p, ldy=Cout_p, k=k, stride=1, pad=k // 2)
+    assert N.lib().vae2_conv2d_tc_supported(C.byref(g)) == 1
+    ya = torch.zeros(B * H * W * Cout_p, dtype=torch.bfloat16, device=dev())
+    bp = None
+    if bias is not None:
+        bp = torch.zeros(Cout_p, dtype=torch.float32, device=dev())
+        bp[:Cout] = bias.to(dev())
+    N.call.vae2_conv2d_fwd(xa.data_ptr(), wq.data_ptr(), bp.data_ptr() if bp is not None else None, ya.data_ptr(), 1,
+                           C.byref(g), 1, st())
+    torch.cuda.synchronize()
+    y = from_act(ya, "bf16", B, Cout, H, W, Cout_p)
+    assert rel_err(y, yr.detach()) < 6e-3, "tc fwd rel err %.3e" % rel_err(y, yr.detach())
+    assert float(ya.view(-1, Cout_p)[:, Cout:].float().abs().sum()) == 0.0
+
+    gya, _ = to_act(gy, "bf16", Cout_p)
+    dxa = torch.zeros_like(xa)
+    N.call.vae2_conv2d_dgrad(gya.data_ptr(), wqT.data_ptr(), dxa.data_ptr(), 1, C.byref(g), 0, 1, st())
+    torch.cuda.synchronize()
+    dx = from_act(dxa, "bf16", B, Cin, H, W, Cin_p)
+    assert rel_err(dx, xr.grad) < 6e-3, "tc dgrad rel err %.3e" % rel_err(dx, xr.grad)
+    N.call.vae2_conv2d_dgrad(gya.data_ptr(), wqT.data_ptr(), dxa.data_ptr(), 1, C.byref(g), 1, 1, st())
+    torch.cuda.synchronize()
+    assert rel_err(from_act(dxa, "bf16", B, Cin, H, W, Cin_p), 2 * xr.grad) < 1e-2, "tc dgrad accumulate"
+
+
+def test_conv_tc_many_tiles_persistent():
+    """More tiles than SMs (persistent loop, both TMEM accumulator stages, stage ring wrap-around)."""
+    B, Cin, Cout, H, W, k = 2, 64, 64, 128, 256, 3
+    x = O.det_normal("tcbig:x", (B, Cin, H, W)).bfloat16().float()
+    w = O.det_normal("tcbig:w", (Cout, Cin, k, k), 0.05).bfloat16().float()
+    yr = F.conv2d(x, w, None, 1, 1)
+    xa, Cin_p = to_act(x, "bf16", 64)
+    wq, _ = pack_bf16(w, 64, 64)
+    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=64, ldx=64, Ho=H, Wo=W, Cout_p=64, ldy=64, k=k, stride=1, pad=1)
+    ya = torch.zeros(B * H * W * 64, dtype=torch.bfloat16, device=dev())
+    N.call.vae2_conv2d_fwd(xa.data_ptr(), wq.data_ptr(), None, ya.data_ptr(), 1, C.byref(g), 1, st())
+    torch.cuda.synchronize()
+    assert rel_err(from_act(ya, "bf16", B, Cout, H, W, 64), yr) < 6e-3

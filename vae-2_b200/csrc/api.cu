@@ -64,7 +64,10 @@ int vae2_conv2d_fwd(const void* x, const void* w_packed, const float* bias, void
 }
 int vae2_conv2d_dgrad(const void* dy, const void* w_packed_t, void* dx, int dtype, const vae2_conv_geom* g, int accumulate,
                       int engine, vae2_stream_t stream) {
-    if (engine != 0) return VAE2_ERR_UNSUPPORTED;
+    if (engine == 1) {
+        if (dtype != VAE2_DT_BF16) return VAE2_ERR_ARG;
+        return conv_dgrad_tc(dy, w_packed_t, dx, G(g), accumulate, S(stream));
+    }
     return conv_dgrad_simt(dy, reinterpret_cast<const float*>(w_packed_t), dx, dtype, G(g), accumulate, S(stream));
 }
 int vae2_conv2d_wgrad(const void* x, const void* dy, float* dw_packed, int dtype, const vae2_conv_geom* g, int engine,

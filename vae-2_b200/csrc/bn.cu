@@ -95,16 +95,40 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
     n = nn;
 }
 
-// merge n_parts partial sets -> one (count, mean, M2) set  (per-rank partial for SyncBN all-gather)
-__global__ void bn_merge_kernel(const float* __restrict__ parts, int n_parts, int Cp, float* __restrict__ merged) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cp) return;
-    float n = 0.f, mean = 0.f, m2 = 0.f;
-    for (int k = 0; k < n_parts; ++k) {
+// One WARP per channel: lanes fold partials lane, lane+32, ... then a 5-step shuffle tree of Chan
+// merges (the merge is associative), so the latency is ~n_parts/32 dependent loads, not n_parts.
+__device__ __forceinline__ void warp_merge_parts(const float* __restrict__ parts, int n_parts, int Cp, int c,
+                                                 float& n, float& mean, float& m2) {
+    const int lane = threadIdx.x & 31;
+    n = 0.f; mean = 0.f; m2 = 0.f;
+    for (int k = lane; k < n_parts; k += 32) {
         const float* p = parts + (long long)k * 3 * Cp;
         chan_merge(n, mean, m2, p[c], p[Cp + c], p[2 * Cp + c]);
     }
-    merged[c] = n; merged[Cp + c] = mean; merged[2 * Cp + c] = m2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+        const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+        const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+        // symmetric form so that both partners end with the same value
+        const float nn = n + nb;
+        if (nn > 0.f) {
+            const float d = mb - mean;
+            const float f = nb / nn;
+            mean = (nb > 0.f && n > 0.f) ? mean + d * f : (nb > 0.f ? mb : mean);
+            m2 = m2 + m2b + ((nb > 0.f && n > 0.f) ? d * d * n * f : 0.f);
+        }
+        n = nn;
+    }
+}
+
+// merge n_parts partial sets -> one (count, mean, M2) set  (per-rank partial for SyncBN all-gather)
+__global__ void bn_merge_kernel(const float* __restrict__ parts, int n_parts, int Cp, float* __restrict__ merged) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= Cp) return;
+    float n, mean, m2;
+    warp_merge_parts(parts, n_parts, Cp, c, n, mean, m2);
+    if ((threadIdx.x & 31) == 0) { merged[c] = n; merged[Cp + c] = mean; merged[2 * Cp + c] = m2; }
 }
 
 // merge + produce normalisation coefficients + running-stat update
@@ -114,15 +138,18 @@ __global__ void bn_finalize_kernel(const float* __restrict__ parts, int n_parts,
                                    long long* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ mean_o, float* __restrict__ invstd_o,
                                    float* __restrict__ scale_o, float* __restrict__ shift_o) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt != nullptr) *nbt += 1;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = gt >> 5;
+    if (gt == 0 && nbt != nullptr) *nbt += 1;
     if (c >= Cp) return;
-    if (c >= C) { mean_o[c] = 0.f; invstd_o[c] = 0.f; scale_o[c] = 0.f; shift_o[c] = 0.f; return; }
-    float n = 0.f, mean = 0.f, m2 = 0.f;
-    for (int k = 0; k < n_parts; ++k) {
-        const float* p = parts + (long long)k * 3 * Cp;
-        chan_merge(n, mean, m2, p[c], p[Cp + c], p[2 * Cp + c]);
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (c >= C) {
+        if (lead) { mean_o[c] = 0.f; invstd_o[c] = 0.f; scale_o[c] = 0.f; shift_o[c] = 0.f; }
+        return;
     }
+    float n, mean, m2;
+    warp_merge_parts(parts, n_parts, Cp, c, n, mean, m2);
+    if (!lead) return;
     const float var = m2 / n;
     const float invstd = rsqrtf(var + eps);
     const float sc = gamma[c] * invstd;
@@ -228,15 +255,17 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* 
     }
 }
 
-// sums[2][Cp] = sum over partials
+// sums[2][Cp] = sum over partials (one warp per channel)
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_parts, int C, int Cp,
                                        float* __restrict__ sums) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= Cp) return;
+    const int lane = threadIdx.x & 31;
     float a = 0.f, b = 0.f;
     if (c < C)
-        for (int k = 0; k < n_parts; ++k) { a += partials[(long long)k * 2 * Cp + c]; b += partials[(long long)k * 2 * Cp + Cp + c]; }
-    sums[c] = a; sums[Cp + c] = b;
+        for (int k = lane; k < n_parts; k += 32) { a += partials[(long long)k * 2 * Cp + c]; b += partials[(long long)k * 2 * Cp + Cp + c]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { sums[c] = a; sums[Cp + c] = b; }
 }
 
 // parameter grads from the LOCAL sums, normalisation coefficients from the (all-reduced) GLOBAL sums
@@ -327,14 +356,14 @@ int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, lon
 }
 
 int bn_merge(const float* partials, int n_partials, int Cp, float* merged, cudaStream_t st) {
-    bn_merge_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(partials, n_partials, Cp, merged);
+    bn_merge_kernel<<<(Cp * 32 + 127) / 128, 128, 0, st>>>(partials, n_partials, Cp, merged);
     return check_launch();
 }
 
 int bn_finalize(const float* parts, int n_parts, int C, int Cp, const float* gamma, const float* beta,
                 float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                 float* mean, float* invstd, float* scale, float* shift, cudaStream_t st) {
-    bn_finalize_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(parts, n_parts, C, Cp, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<(Cp * 32 + 127) / 128, 128, 0, st>>>(parts, n_parts, C, Cp, gamma, beta, running_mean, running_var,
                                                         num_batches_tracked, momentum, eps, mean, invstd, scale, shift);
     return check_launch();
 }
@@ -373,7 +402,7 @@ int bn_bwd_reduce(const void* g, const void* a, const void* y, float* partials, 
 }
 
 int bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, cudaStream_t st) {
-    bn_bwd_finalize_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(partials, n_partials, C, Cp, sums);
+    bn_bwd_finalize_kernel<<<(Cp * 32 + 127) / 128, 128, 0, st>>>(partials, n_partials, C, Cp, sums);
     return check_launch();
 }
 

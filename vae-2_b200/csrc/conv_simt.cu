@@ -141,17 +141,23 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
                 }
                 if (b_active) *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = br;
                 __syncthreads();
+                // only the channels that exist in this chunk (Cch is a multiple of 4): an 18->20-lane
+                // tensor costs 20 k-steps per tap, not 32
+                const int kmax = (Cch - kc) < BK ? (Cch - kc) : BK;
+                for (int k4 = 0; k4 < kmax; k4 += 4) {
 #pragma unroll
-                for (int kk = 0; kk < BK; ++kk) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
-                    const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float bv[4] = {b.x, b.y, b.z, b.w};
+                    for (int kq = 0; kq < 4; ++kq) {
+                        const int kk = k4 + kq;
+                        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+                        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
+                        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
+                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int i = 0; i < TM; ++i)
+                        for (int i = 0; i < TM; ++i)
 #pragma unroll
-                        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    }
                 }
             }
         }

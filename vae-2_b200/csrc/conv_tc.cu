@@ -1,11 +1,394 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution (bf16 operands, fp32 accumulate).
-// Placeholder until the tensor-core path lands: reports "unsupported" so callers use conv_simt.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Replaces cuDNN behind the reference's stride-1 nn.Conv2d sites (3x3 p1 and 1x1;
+// lib/models/enc_hrnet.py:27-30, 38-41, 70-76, 188-195, 324-337, 381-390, 1010-1017) on the bf16
+// path, for the forward pass and -- with the transposed weight pack and mirrored tap offsets -- for
+// the data gradient.  (Stride-2 convs, 8 % of the MACs, and the weight gradient use conv_simt.cu.)
+//
+//   D[pixel][n] = sum_{tap} sum_{c}  A[pixel + off(tap)][c] * Wq[tap][n][c]
+//
+// Mapping onto the hardware:
+//   * M tile = 128 output pixels = a TH x TW patch of one image (TW*TH = 128), which is one TMA
+//     box [KC ch][TW][TH][1] of the channels-last activation shifted by the tap offset; TMA's
+//     out-of-bounds zero fill IS the conv padding.  The box lands in shared memory as 128 rows of
+//     KC*2 bytes with the 128/64/32-byte swizzle, i.e. exactly the K-major canonical layout a
+//     tcgen05 shared-memory descriptor reads.
+//   * N tile = NT output channels (<= 256): a TMA box [KC][NT][1] of the packed weights.
+//   * one elected thread issues tcgen05.mma (M=128, N=NT, K=16) per 16 channels; the fp32
+//     accumulator (128 lanes x NT columns) lives in TMEM, double buffered so the epilogue of tile
+//     i overlaps the MMAs of tile i+1.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//     (tcgen05.ld 32 lanes x 16 columns -> +bias -> bf16 -> 32-byte global stores, one pixel row
+//     per thread).  Persistent CTAs (one per SM) walk the tile list.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vae2 {
-int conv_tc_supported(const ConvGeom&) { return 0; }
-int conv_fwd_tc(const void*, const void*, const float*, void*, const ConvGeom&, float*, cudaStream_t) {
-    return VAE2_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int kThreads = 192;          // 6 warps
+constexpr int kEpiWarp0 = 2;           // first epilogue warp
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct Params {
+    int B, H, W;              // OUTPUT spatial extent (== input extent, stride 1)
+    int Cn;                   // output channel lanes (N extent), multiple of 16
+    int ldo;                  // output pixel pitch (elements)
+    int taps, ksz, pad;       // 9/3/1 or 1/1/0
+    int tap_sign;             // +1: input pixel = out + (k - pad)  (forward); -1: out - (k - pad) (dgrad)
+    int kchunks;              // K chunks of KC channels per tap
+    int KC;                   // 16 / 32 / 64 channels per stage
+    int NT;                   // N tile (multiple of 16, <= 256)
+    int n_tiles;              // tiles along N
+    int TW, TH;               // pixel patch, TW*TH = 128
+    int tiles_w, tiles_h;     // patches per image
+    int total_tiles;
+    int stages;
+    int tmem_cols;            // power of two >= 2*NT (or >= NT when single buffered)
+    int acc_stages;           // 1 or 2
+    int accumulate;           // epilogue adds to the existing output (dgrad +=)
+    const float* bias;        // per output channel (padded to Cn) or null
+    __nv_bfloat16* out;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): rows of
+// `row_bytes` (= the swizzle span), 8-row groups `8*row_bytes` apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);   // SWIZZLE_128B / 64B / 32B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= layout << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][A tile | B tile] (1024-aligned), then barriers
+    const uint32_t row_bytes = p.KC * 2;
+    const uint32_t a_bytes = 128 * row_bytes;
+    const uint32_t b_bytes = ((p.NT * row_bytes + 1023) / 1024) * 1024;
+    const uint32_t stage_bytes = a_bytes + b_bytes;   // a_bytes is a multiple of 1024 for KC >= 16? 128*32 = 4096 yes
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                       // [stages]
+    uint64_t* empty = bars + kMaxStages;         // [stages]
+    uint64_t* acc_full = bars + 2 * kMaxStages;  // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int pt = tile / p.n_tiles;
+                const int b = pt / per_img;
+                const int r = pt - b * per_img;
+                const int h0 = (r / p.tiles_w) * p.TH, w0 = (r % p.tiles_w) * p.TW;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int ky = tap / p.ksz, kx = tap - ky * p.ksz;
+                    const int dh = p.tap_sign * (ky - p.pad), dw = p.tap_sign * (kx - p.pad);
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&full[stage], a_bytes + p.NT * row_bytes);
+                        tma_load_4d(sa, &map_a, &full[stage], kc * p.KC, w0 + dw, h0 + dh, b);
+                        tma_load_3d(sa + a_bytes, &map_w, &full[stage], kc * p.KC, nt * p.NT, tap);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int as = p.acc_stages == 2 ? (it & 1) : 0;
+                const uint32_t use = p.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(&acc_empty[as], (use & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.NT);
+                uint32_t accum = 0;
+                for (int ks = 0; ks < p.taps * p.kchunks; ++ks) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    for (int k = 0; k < p.KC / 16; ++k) {
+                        umma_bf16(d_tmem, make_desc(sa + k * 32, row_bytes), make_desc(sb + k * 32, row_bytes), idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs finish
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[as]);                     // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ================= epilogue warps (TMEM -> registers -> global) =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;          // tile row == TMEM lane == pixel within the patch
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int as = p.acc_stages == 2 ? (it & 1) : 0;
+            const uint32_t use = p.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+            const int nt = tile % p.n_tiles;
+            const int pt = tile / p.n_tiles;
+            const int b = pt / per_img;
+            const int r = pt - b * per_img;
+            const int h = (r / p.tiles_w) * p.TH + row / p.TW, w = (r % p.tiles_w) * p.TW + row % p.TW;
+            const bool in_img = h < p.H && w < p.W;
+            mbar_wait(&acc_full[as], use & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.NT);
+            __nv_bfloat16* orow = p.out + (((long long)b * p.H + h) * p.W + w) * p.ldo;
+            for (int c0 = 0; c0 < p.NT; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t0 + c0, v);
+                tmem_ld_wait();
+                const int n = nt * p.NT + c0;
+                if (in_img && n < p.Cn) {
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + n + i);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(orow + n);
+                    if (p.accumulate) {
+                        uint4 o[2] = {dst[0], dst[1]};
+                        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(o);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { float2 t = __bfloat1622float2(oh[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+                    }
+                    uint4 o[2];
+                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                    dst[0] = o[0];
+                    dst[1] = o[1];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);     // 4 epilogue warps -> count 4
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swz(int kc) {
+    return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+
+static int next_pow2_cols(int n) {
+    int c = 32;
+    while (c < n) c <<= 1;
+    return c;
+}
+
+}  // namespace tc
+
+int conv_tc_supported(const ConvGeom& g) {
+    if (g.stride != 1) return 0;
+    if (!(g.k == 1 || g.k == 3)) return 0;
+    if (g.Cin_p % 16 || g.Cout_p % 16 || g.ldx % 8 || g.ldy % 8) return 0;
+    if (g.H != g.Ho || g.W != g.Wo) return 0;
+    return tc::encode_fn() != nullptr ? 1 : 0;
+}
+
+// Generic launcher: `a` is the gathered tensor [B][H][W][lda] with Ck lanes on the K axis, `wq` the
+// packed bf16 weights [taps][Cn][Ck] (K contiguous), `out` [B][H][W][ldo] with Cn lanes.
+static int launch_tc(const void* a, int lda, int Ck, const void* wq, int Cn, void* out, int ldo, const float* bias, int B,
+                     int H, int W, int ksz, int tap_sign, int accumulate, cudaStream_t st) {
+    using namespace tc;
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return VAE2_ERR_UNSUPPORTED;
+    Params p;
+    p.B = B; p.H = H; p.W = W; p.Cn = Cn; p.ldo = ldo;
+    p.ksz = ksz; p.taps = ksz * ksz; p.pad = ksz / 2; p.tap_sign = tap_sign;
+    p.KC = pick_kc(Ck);
+    p.kchunks = Ck / p.KC;
+    p.n_tiles = (Cn + 255) / 256;
+    p.NT = (((Cn + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
+    // pixel patch: widest power-of-two strip that does not overshoot the row by more than 2x
+    int tw = 128;
+    while (tw > 8 && tw / 2 >= W) tw >>= 1;
+    p.TW = tw; p.TH = 128 / tw;
+    p.tiles_w = (W + p.TW - 1) / p.TW;
+    p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.total_tiles = B * p.tiles_w * p.tiles_h * p.n_tiles;
+    const int row_bytes = p.KC * 2;
+    const int a_bytes = 128 * row_bytes;
+    const int b_bytes = ((p.NT * row_bytes + 1023) / 1024) * 1024;
+    int stages = kSmemBudget / (a_bytes + b_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return VAE2_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.acc_stages = (2 * p.NT <= 512) ? 2 : 1;
+    p.tmem_cols = next_pow2_cols(p.acc_stages * p.NT);
+    p.accumulate = accumulate;
+    p.bias = bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+
+    CUtensorMap map_a, map_w;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Ck, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)W * lda * 2, (cuuint64_t)H * W * lda * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return VAE2_ERR_ARG;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Ck, (cuuint64_t)Cn, (cuuint64_t)p.taps};
+        cuuint64_t strides[2] = {(cuuint64_t)Ck * 2, (cuuint64_t)Cn * Ck * 2};
+        cuuint32_t box[3] = {(cuuint32_t)p.KC, (cuuint32_t)p.NT, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wq), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return VAE2_ERR_ARG;
+    }
+    const size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return VAE2_ERR_CUDA;
+        attr_set = true;
+    }
+    int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_w, p);
+    return check_launch();
+}
+
+int conv_fwd_tc(const void* x, const void* wq, const float* bias, void* y, const ConvGeom& g, float*, cudaStream_t st) {
+    if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
+    return launch_tc(x, g.ldx, g.Cin_p, wq, g.Cout_p, y, g.ldy, bias, g.B, g.H, g.W, g.k, +1, 0, st);
+}
+
+// dx (=|+=) conv_transpose(dy): same kernel, A = dy, weights = wqT [tap][Cin_p][Cout_p], mirrored taps
+int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st) {
+    if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
+    return launch_tc(dy, g.ldy, g.Cout_p, wqT, g.Cin_p, dx, g.ldx, nullptr, g.B, g.H, g.W, g.k, -1, accumulate, st);
+}
+
 }  // namespace vae2

@@ -12,6 +12,7 @@ import torch
 from . import native as N
 
 _pending_flags = []   # (names, device int32 tensor) from earlier steps, checked lazily
+LAUNCHES = {"n": 0}
 
 
 def _table(structs, dev):
@@ -64,6 +65,7 @@ class _Terms(torch.autograd.Function):
         acc = torch.zeros(N.lib().vae2_elbo_acc_floats(), dtype=torch.float32, device=dev)
         flags = torch.zeros(len(spec), dtype=torch.int32, device=dev)
         N.call.vae2_elbo_terms(table.data_ptr(), len(spec), acc.data_ptr(), nslots, flags.data_ptr(), st)
+        LAUNCHES["n"] += 2
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         _pending_flags.append((names, flags, ev))
@@ -114,6 +116,7 @@ class _Terms(torch.autograd.Function):
         if n:
             table = _table(segs, dev)
             N.call.vae2_elbo_terms_bwd(table.data_ptr(), n, st)
+            LAUNCHES["n"] += 1
             ctx.keep += (table, gvals)
         return (None, None) + tuple(grads)
 

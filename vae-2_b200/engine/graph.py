@@ -11,6 +11,7 @@ Only plumbing uses torch here (device memory, streams, torch.distributed for Syn
 all-gathers); every arithmetic op is a call into libvae2_b200.so through the C ABI.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -129,6 +130,7 @@ class Plan:
         self.inputs, self.outputs = [], []
         self.keep = []                        # keep-alive for ctypes arrays / tensors
         self.busy = False
+        self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
         self.graph_fwd = self.graph_bwd = None
         self.n_launch_fwd = self.n_launch_bwd = 0
 
@@ -176,9 +178,18 @@ class Plan:
         for o in convs:
             o.w_off = tot
             tot += pad_to(o.taps * o.x.root_cp() * o.y.Cp, 4)
+        # tensor-core eligibility (bf16 path, stride-1 convs): decided once per conv at plan build
+        if self.prec.code == 1 and dev.type == "cuda" and self.use_tc:
+            for o in convs:
+                g = o._geom()
+                o.engine = 1 if N.lib().vae2_conv2d_tc_supported(C.byref(g)) else 0
+        self.n_tc_convs = sum(o.engine for o in convs)
         self.wp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev)
         self.wpT_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
         self.dwp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
+        any_tc = self.n_tc_convs > 0
+        self.wq_flat = torch.zeros(max(tot, 8), dtype=torch.bfloat16, device=dev) if any_tc else None
+        self.wqT_flat = torch.zeros(max(tot, 8), dtype=torch.bfloat16, device=dev) if (any_tc and self.training) else None
         # pack / unpack descriptor tables (device resident)
         pk = (N.PackDesc * max(len(convs), 1))()
         up = (N.PackDesc * max(len(convs), 1))()
@@ -191,8 +202,12 @@ class Plan:
                 cmap_ptr = t.data_ptr()
             cin_p, cout_p = o.x.root_cp(), o.y.Cp
             common = dict(cin_map=cmap_ptr, Cout=w.shape[0], Cin=w.shape[1], k=w.shape[2], Cin_p=cin_p, Cout_p=cout_p)
-            pk[i] = N.PackDesc(w=w.data_ptr(), wp=self.wp_flat.data_ptr() + 4 * o.w_off,
-                               wpT=(self.wpT_flat.data_ptr() + 4 * o.w_off) if self.training else None, **common)
+            if o.engine == 1:
+                pk[i] = N.PackDesc(w=w.data_ptr(), wq=self.wq_flat.data_ptr() + 2 * o.w_off,
+                                   wqT=(self.wqT_flat.data_ptr() + 2 * o.w_off) if self.training else None, **common)
+            else:
+                pk[i] = N.PackDesc(w=w.data_ptr(), wp=self.wp_flat.data_ptr() + 4 * o.w_off,
+                                   wpT=(self.wpT_flat.data_ptr() + 4 * o.w_off) if self.training else None, **common)
             if self.training:
                 gi = self.param(w)
                 up[i] = N.PackDesc(w=self.flat_grad.data_ptr() + 4 * self._grad_off[gi],
@@ -228,32 +243,51 @@ class Plan:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def run_forward(self, use_graph=False):
+        """Returns the number of native (C-ABI) launches this replay performed."""
         st = self._stream()
+        c0 = N.COUNTERS["native_calls"]
         for f in self.pre_fwd:
             f(st)
+        eager = N.COUNTERS["native_calls"] - c0
         if use_graph:
             if self.graph_fwd is None:
+                c1 = N.COUNTERS["native_calls"]
                 self.graph_fwd = self._capture(self.fwd)
+                self.native_fwd = (N.COUNTERS["native_calls"] - c1) // 2   # warm-up pass + capture pass
             self.graph_fwd.replay()
+            body = self.native_fwd
         else:
+            c1 = N.COUNTERS["native_calls"]
             for f in self.fwd:
                 f(st)
+            body = N.COUNTERS["native_calls"] - c1
+        c2 = N.COUNTERS["native_calls"]
         for f in self.post_fwd:
             f(st)
+        return eager + body + N.COUNTERS["native_calls"] - c2
 
     def run_backward(self, use_graph=False):
         st = self._stream()
+        c0 = N.COUNTERS["native_calls"]
         for f in self.pre_bwd:
             f(st)
+        eager = N.COUNTERS["native_calls"] - c0
         if use_graph:
             if self.graph_bwd is None:
+                c1 = N.COUNTERS["native_calls"]
                 self.graph_bwd = self._capture(self.bwd)
+                self.native_bwd = (N.COUNTERS["native_calls"] - c1) // 2
             self.graph_bwd.replay()
+            body = self.native_bwd
         else:
+            c1 = N.COUNTERS["native_calls"]
             for f in self.bwd:
                 f(st)
+            body = N.COUNTERS["native_calls"] - c1
+        c2 = N.COUNTERS["native_calls"]
         for f in self.post_bwd:
             f(st)
+        return eager + body + N.COUNTERS["native_calls"] - c2
 
     def _capture(self, prog):
         # warm-up run on a side stream, then capture the same launch list
@@ -392,7 +426,7 @@ class ConvOp:
         g = self._geom()
         plan.keep.append(g)
         x, y = self.x, self.y
-        wp = plan.wp_flat.data_ptr() + 4 * self.w_off
+        wp = (plan.wq_flat.data_ptr() + 2 * self.w_off) if self.engine == 1 else (plan.wp_flat.data_ptr() + 4 * self.w_off)
         bias = None
         if self.conv.bias is not None:
             # bias padded to Cout_p lanes (pad = 0); refreshed from the parameter every forward
@@ -421,10 +455,11 @@ class ConvOp:
             npix, cb, ldy = y.npix, y.C, y.ld
             plan.bwd.append(lambda st: N.call.vae2_bias_grad(dyp, db, pr.code, npix, cb, ldy, 0, st))
         if x.needs_grad:
-            wpT = plan.wpT_flat.data_ptr() + 4 * self.w_off
+            eng = self.engine
+            wpT = (plan.wqT_flat.data_ptr() + 2 * self.w_off) if eng == 1 else (plan.wpT_flat.data_ptr() + 4 * self.w_off)
             acc = x.take_acc_flag()
             dxp = x.grad().ptr
-            plan.bwd.append(lambda st: N.call.vae2_conv2d_dgrad(dyp, wpT, dxp, pr.code, gp, acc, 0, st))
+            plan.bwd.append(lambda st: N.call.vae2_conv2d_dgrad(dyp, wpT, dxp, pr.code, gp, acc, eng, st))
 
 
 class BnOp:

@@ -35,8 +35,9 @@ def use_cuda_graphs(flag):
 
 
 def launch_count():
-    """Kernel-launching calls replayed so far (bench.py's gpu_launches)."""
-    return _STATE["launches"]
+    """Launches of this library's kernels so far, replayed graph nodes included (bench.py's gpu_launches)."""
+    from .elbo import LAUNCHES
+    return _STATE["launches"] + LAUNCHES["n"]
 
 
 class _Lease:
@@ -63,8 +64,7 @@ class _PlanFn(torch.autograd.Function):
         dev = plan.device
         outs = [torch.empty((plan.B,) + tuple(s), dtype=torch.float32, device=dev) for s in plan.out_shapes]
         plan.cur_outputs = outs
-        plan.run_forward(_STATE["cuda_graphs"])
-        _STATE["launches"] += plan.n_launch_fwd + len(plan.pre_fwd) + len(plan.post_fwd)
+        _STATE["launches"] += plan.run_forward(_STATE["cuda_graphs"])
         ctx.plan, ctx.n_in, ctx.n_args = plan, n_in, len(args)
         ctx.in_shapes = [tuple(a.shape) for a in args[:n_in]]
         ctx.in_needs = [bool(a.requires_grad) for a in args[:n_in]]
@@ -81,8 +81,7 @@ class _PlanFn(torch.autograd.Function):
         plan.cur_output_grads = [None if g is None else g.contiguous().float() for g in gouts]
         plan.cur_input_grads = [torch.zeros(s, dtype=torch.float32, device=dev) if need else None
                                 for s, need in zip(ctx.in_shapes, ctx.in_needs)]
-        plan.run_backward(_STATE["cuda_graphs"])
-        _STATE["launches"] += plan.n_launch_bwd + len(plan.pre_bwd) + len(plan.post_bwd)
+        _STATE["launches"] += plan.run_backward(_STATE["cuda_graphs"])
         flat = plan.flat_grad.clone()
         pgrads = []
         for p, off in zip(plan.params, plan._grad_off):

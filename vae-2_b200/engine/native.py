@@ -115,13 +115,17 @@ def check(status, what):
             what, h.vae2_status_string(status).decode(), h.vae2_last_cuda_error().decode()))
 
 
+COUNTERS = {"native_calls": 0}
+
+
 class _Caller:
-    """``call.vae2_bn_apply(...)`` = invoke + status check."""
+    """``call.vae2_bn_apply(...)`` = invoke + status check (+ a count of kernel-launching calls)."""
 
     def __getattr__(self, name):
         fn = getattr(lib(), name)
 
         def wrapped(*args):
+            COUNTERS["native_calls"] += 1
             check(fn(*args), name)
         wrapped.__name__ = name
         setattr(self, name, wrapped)
