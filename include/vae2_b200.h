@@ -82,6 +82,11 @@ int vae2_conv2d_wgrad(const void* x, const void* dy, float* dw_packed, int dtype
 int vae2_bias_grad(const void* dy, float* dbias, int dtype, int64_t npix, int C, int ld, int accumulate,
                    vae2_stream_t stream);
 int vae2_conv2d_tc_supported(const vae2_conv_geom* g);
+/* tensor-core weight gradient (bf16 act, stride 1): dw_packed is OVERWRITTEN; `workspace` holds the split-K
+ * partials, at least vae2_conv2d_wgrad_tc_workspace(g) floats (negative = shape unsupported, use engine 0) */
+long long vae2_conv2d_wgrad_tc_workspace(const vae2_conv_geom* g);
+int vae2_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, float* workspace, const vae2_conv_geom* g,
+                         vae2_stream_t stream);
 
 /* ---- batch norm: BatchNorm2d(momentum=0.01) / SyncBatchNorm, enc_hrnet.py:22-23, train.py:217 - */
 int vae2_bn_max_partials(void);

@@ -78,6 +78,24 @@ def test_conv_tc_fwd_dgrad(case):
     torch.cuda.synchronize()
     assert rel_err(from_act(dxa, "bf16", B, Cin, H, W, Cin_p), 2 * xr.grad) < 1e-2, "tc dgrad accumulate"
 
+    # weight gradient on tensor cores (split-K over pixels + workspace reduce)
+    need = N.lib().vae2_conv2d_wgrad_tc_workspace(C.byref(g))
+    if need > 0:
+        wr = w.clone().requires_grad_(True)
+        F.conv2d(x, wr, None, stride=1, padding=k // 2).backward(gy)
+        ws = torch.zeros(need, dtype=torch.float32, device=dev())
+        dwp = torch.full((k * k * Cin_p * Cout_p,), 7.0, dtype=torch.float32, device=dev())   # must be overwritten
+        N.call.vae2_conv2d_wgrad_tc(xa.data_ptr(), gya.data_ptr(), dwp.data_ptr(), ws.data_ptr(), C.byref(g), st())
+        dw = torch.zeros_like(w).to(dev())
+        d = (N.PackDesc * 1)()
+        d[0] = N.PackDesc(w=dw.data_ptr(), wp=dwp.data_ptr(), Cout=Cout, Cin=Cin, k=k, Cin_p=Cin_p, Cout_p=Cout_p)
+        t = table(d)
+        N.call.vae2_unpack_wgrad(t.data_ptr(), 1, 0, st())
+        torch.cuda.synchronize()
+        assert rel_err(dw.cpu(), wr.grad) < 6e-3, "tc wgrad rel err %.3e" % rel_err(dw.cpu(), wr.grad)
+    else:
+        assert Cout_p > 256, "wgrad_tc unexpectedly unsupported"
+
 
 def test_conv_tc_many_tiles_persistent():
     """More tiles than SMs (persistent loop, both TMEM accumulator stages, stage ring wrap-around)."""

@@ -80,6 +80,11 @@ int vae2_bias_grad(const void* dy, float* dbias, int dtype, int64_t npix, int C,
     return bias_grad(dy, dbias, dtype, npix, C, ld, accumulate, S(stream));
 }
 int vae2_conv2d_tc_supported(const vae2_conv_geom* g) { return conv_tc_supported(G(g)); }
+long long vae2_conv2d_wgrad_tc_workspace(const vae2_conv_geom* g) { return conv_wgrad_tc_workspace(G(g)); }
+int vae2_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, float* workspace, const vae2_conv_geom* g,
+                         vae2_stream_t stream) {
+    return conv_wgrad_tc(x, dy, dw_packed, workspace, G(g), S(stream));
+}
 
 int vae2_bn_max_partials(void) { return bn_stats_max_partials(); }
 int vae2_bn_stats(const void* y, float* partials, int* n_partials, int dtype, int64_t npix, int Cp, int ld,

@@ -303,6 +303,238 @@ static int next_pow2_cols(int n) {
     return c;
 }
 
+
+// =================================================================================================
+// Weight gradient on tcgen05:   dW[tap][ci][co] = sum_pixels  x[pixel + off(tap)][ci] * dy[pixel][co]
+//
+// GEMM with K = pixels.  Both operands are read exactly as they lie in memory (channels-last), i.e.
+// MN-major: a TMA box [atom channels][TW][TH] lands as KP = TW*TH rows (pixels) of `atom` channels,
+// which is the MN-major canonical layout (k rows of one swizzle span, 8-row groups SBO apart, the
+// next `atom` channels LBO = KP*row_bytes further on).  A 5-D tensor map (c_lo, w, h, b, c_hi)
+// fetches ALL channel atoms of one tap in a single TMA.
+//   A (M side) : rows m = tap*Cin_p + ci  -> the 9 tap-shifted x tiles stacked along M; one
+//                tcgen05.mma covers 128 consecutive rows ("group"), possibly spanning taps.
+//   B (N side) : dy tile, N = Cout_p, loaded once per pixel chunk and shared by all taps.
+//   D          : groups x [128 lanes x Cout_p columns] fp32 in TMEM (<= 512 columns per CTA; more
+//                groups -> several "sets" handled by different CTAs).
+// Split-K: CTA (set, range) walks pixel tiles range, range+nranges, ...; partial sums go to a
+// workspace slot per range and a second kernel adds the slots into dwp[tap][Cin_p][Cout_p].
+// =================================================================================================
+struct WParams {
+    int B, H, W;
+    int Cin_p, Cout_p, taps, ksz, pad;
+    int atomA, atomB;          // channels per swizzle atom on the M / N side (16, 32 or 64)
+    int TW, TH, KP;            // pixel patch per stage (KP = TW*TH, multiple of 16)
+    int tiles_w, tiles_h, total_ptiles;
+    int M_total;               // taps * Cin_p
+    int set_groups, nsets, nranges;
+    int a_atoms_stage;         // atoms reserved for A per stage
+    int stages;
+    int tmem_cols;
+    float* ws;                 // [nranges][M_total][Cout_p]
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+// MN-major descriptor: rows (k) of `row_bytes`, 8-row groups SBO = 8*row_bytes apart, atoms LBO apart
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t row_bytes, uint32_t lbo_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t rowA = p.atomA * 2, rowB = p.atomB * 2;
+    const uint32_t atomA_bytes = p.KP * rowA, atomB_bytes = p.KP * rowB;     // multiples of 1024 for KP = 32/64... (>= 512)
+    const uint32_t a_bytes = (uint32_t)p.a_atoms_stage * atomA_bytes;
+    const uint32_t b_bytes = (uint32_t)(p.Cout_p / p.atomB) * atomB_bytes;
+    const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kMaxStages;
+    uint64_t* acc_full = bars + 2 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int set = blockIdx.x % p.nsets, range = blockIdx.x / p.nsets;
+    const int g_lo = set * p.set_groups;
+    const int groups_total = (p.M_total + 127) / 128;
+    const int g_hi = min(groups_total, g_lo + p.set_groups);      // exclusive
+    const int m_lo = g_lo * 128, m_hi = min(p.M_total, g_hi * 128);
+    const int t0 = m_lo / p.Cin_p, t1 = (m_hi - 1) / p.Cin_p;      // taps this set touches
+    const int nchunkA = p.Cin_p / p.atomA;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int n_my_tiles = (p.total_ptiles - range + p.nranges - 1) / p.nranges;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(t1 - t0 + 1) * nchunkA * atomA_bytes + b_bytes;
+            for (int i = 0; i < n_my_tiles; ++i) {
+                const int pt = range + i * p.nranges;
+                const int b = pt / per_img;
+                const int r = pt - b * per_img;
+                const int h0 = (r / p.tiles_w) * p.TH, w0 = (r % p.tiles_w) * p.TW;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full[stage], tx_bytes);
+                for (int tap = t0; tap <= t1; ++tap) {
+                    const int ky = tap / p.ksz, kx = tap - ky * p.ksz;
+                    tma_load_5d(sa + (size_t)(tap - t0) * nchunkA * atomA_bytes, &map_x, &full[stage], 0, w0 + kx - p.pad,
+                                h0 + ky - p.pad, b, 0);
+                }
+                tma_load_5d(sa + a_bytes, &map_dy, &full[stage], 0, w0, h0, b, 0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = Cout_p, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.Cout_p >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_my_tiles; ++i) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                for (int g = g_lo; g < g_hi; ++g) {
+                    const uint32_t a_rel = (uint32_t)(g * 128 - t0 * p.Cin_p) / (uint32_t)p.atomA;   // first atom of this group
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_lo) * p.Cout_p);
+                    for (int k = 0; k < p.KP / 16; ++k) {
+                        umma_bf16(d_tmem, make_desc_mn(sa + a_rel * atomA_bytes + k * 16 * rowA, rowA, atomA_bytes),
+                                  make_desc_mn(sb + k * 16 * rowB, rowB, atomB_bytes), idesc, (i | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        float* ws = p.ws + (size_t)range * p.M_total * p.Cout_p;
+        for (int g = g_lo; g < g_hi; ++g) {
+            const int m = g * 128 + q * 32 + lane;
+            const uint32_t t0a = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_lo) * p.Cout_p);
+            for (int c0 = 0; c0 < p.Cout_p; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t0a + c0, v);
+                tmem_ld_wait();
+                if (m < p.M_total) {
+                    float4* dst = reinterpret_cast<float4*>(ws + (size_t)m * p.Cout_p + c0);
+                    if (n_my_tiles > 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                 __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// dwp[i] = sum over split-K slots
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long long n, int nslots) {
+    const long long n4 = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < nslots; ++s) {
+            const float4 v = reinterpret_cast<const float4*>(ws + (long long)s * n)[i];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4*>(dwp)[i] = a;
+    }
+}
+
+static int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+
+// Fills p (everything except ws) and returns the workspace size in floats; <0 if unsupported.
+static long long plan_wgrad(const ConvGeom& g, WParams& p) {
+    if (g.Cout_p > 256) return -1;
+    p.B = g.B; p.H = g.H; p.W = g.W;
+    p.Cin_p = g.Cin_p; p.Cout_p = g.Cout_p; p.ksz = g.k; p.taps = g.k * g.k; p.pad = g.k / 2;
+    p.atomA = pick_atom(g.Cin_p);
+    p.atomB = pick_atom(g.Cout_p);
+    int tw = 32;
+    while (tw > 8 && tw / 2 >= g.W) tw >>= 1;
+    p.TW = tw; p.TH = 32 / tw; p.KP = 32;
+    p.tiles_w = (g.W + p.TW - 1) / p.TW;
+    p.tiles_h = (g.H + p.TH - 1) / p.TH;
+    p.total_ptiles = g.B * p.tiles_w * p.tiles_h;
+    p.M_total = p.taps * g.Cin_p;
+    const int groups_total = (p.M_total + 127) / 128;
+    int sg = 512 / g.Cout_p;
+    if (sg > groups_total) sg = groups_total;
+    // keep the per-stage A footprint bounded: a set never needs more than (sg*128/Cin_p + 2) taps
+    p.set_groups = sg;
+    p.nsets = (groups_total + sg - 1) / sg;
+    p.tmem_cols = next_pow2_cols(sg * g.Cout_p);
+    // A atoms per stage: worst case over sets of (taps touched * chunks), and at least enough to cover whole groups
+    const int nchunkA = g.Cin_p / p.atomA;
+    int worst = 0;
+    for (int s = 0; s < p.nsets; ++s) {
+        const int m_lo = s * sg * 128;
+        int m_hi = (s + 1) * sg * 128;
+        const int m_hi_real = m_hi < p.M_total ? m_hi : p.M_total;
+        const int t0 = m_lo / g.Cin_p, t1 = (m_hi_real - 1) / g.Cin_p;
+        int atoms = (t1 - t0 + 1) * nchunkA;
+        const int need = (m_hi - t0 * g.Cin_p + p.atomA - 1) / p.atomA;   // group rows may overhang the loaded taps
+        if (need > atoms) atoms = need;
+        if (atoms > worst) worst = atoms;
+    }
+    p.a_atoms_stage = worst;
+    const long long a_bytes = (long long)worst * p.KP * p.atomA * 2;
+    const long long b_bytes = (long long)g.Cout_p * p.KP * 2;
+    const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    int stages = (int)(kSmemBudget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return -1;
+    p.stages = stages;
+    int nranges = kNumSMs / p.nsets;
+    if (nranges < 1) nranges = 1;
+    if (nranges > p.total_ptiles) nranges = p.total_ptiles;
+    const long long slot = (long long)p.M_total * g.Cout_p;
+    const long long cap = (64LL << 20) / 4 / slot;      // <= 64 MB of partials
+    if (nranges > cap) nranges = (int)(cap < 1 ? 1 : cap);
+    p.nranges = nranges;
+    return slot * nranges;
+}
+
 }  // namespace tc
 
 int conv_tc_supported(const ConvGeom& g) {
@@ -389,6 +621,54 @@ int conv_fwd_tc(const void* x, const void* wq, const float* bias, void* y, const
 int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st) {
     if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
     return launch_tc(dy, g.ldy, g.Cout_p, wqT, g.Cin_p, dx, g.ldx, nullptr, g.B, g.H, g.W, g.k, -1, accumulate, st);
+}
+
+}  // namespace vae2
+
+namespace vae2 {
+
+long long conv_wgrad_tc_workspace(const ConvGeom& g) {
+    if (!conv_tc_supported(g)) return -1;
+    tc::WParams p;
+    return tc::plan_wgrad(g, p);
+}
+
+static int make_map5(tc::EncodeTiledFn enc, CUtensorMap* m, const void* base, int atom, int C, int ld, int B, int H, int W, int TW, int TH) {
+    cuuint64_t dims[5] = {(cuuint64_t)atom, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / atom)};
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)atom * 2};
+    cuuint32_t box[5] = {(cuuint32_t)atom, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)(C / atom)};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swz(atom), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
+// dwp [tap][Cin_p][Cout_p] fp32 (overwritten); ws: at least conv_wgrad_tc_workspace(g) floats
+int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const ConvGeom& g, cudaStream_t st) {
+    using namespace tc;
+    if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
+    WParams p;
+    if (plan_wgrad(g, p) < 0) return VAE2_ERR_UNSUPPORTED;
+    p.ws = ws;
+    EncodeTiledFn enc = encode_fn();
+    CUtensorMap map_x, map_dy;
+    if (make_map5(enc, &map_x, x, p.atomA, g.Cin_p, g.ldx, g.B, g.H, g.W, p.TW, p.TH)) return VAE2_ERR_ARG;
+    if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, g.ldy, g.B, g.H, g.W, p.TW, p.TH)) return VAE2_ERR_ARG;
+    const long long a_bytes = (long long)p.a_atoms_stage * p.KP * p.atomA * 2;
+    const long long b_bytes = (long long)g.Cout_p * p.KP * 2;
+    const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return VAE2_ERR_CUDA;
+        attr_set = true;
+    }
+    wgrad_tc_kernel<<<p.nsets * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
+    if (int e = check_launch()) return e;
+    const long long n = (long long)p.M_total * g.Cout_p;
+    wgrad_reduce_kernel<<<stream_grid(n / 4, 256, 4), 256, 0, st>>>(ws, dwp, n, p.nranges);
+    return check_launch();
 }
 
 }  // namespace vae2

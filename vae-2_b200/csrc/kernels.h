@@ -113,6 +113,8 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
 int conv_fwd_tc(const void* x, const void* wq, const float* bias, void* y, const ConvGeom& g, float* stats_partials,
                 cudaStream_t st);
 int conv_tc_supported(const ConvGeom& g);
+long long conv_wgrad_tc_workspace(const ConvGeom& g);
+int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const ConvGeom& g, cudaStream_t st);
 int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st);
 
 }  // namespace vae2

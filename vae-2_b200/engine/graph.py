@@ -131,6 +131,7 @@ class Plan:
         self.keep = []                        # keep-alive for ctypes arrays / tensors
         self.busy = False
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
+        self.use_tc_wgrad = os.environ.get("VAE2_DISABLE_TC_WGRAD", "0") != "1"
         self.graph_fwd = self.graph_bwd = None
         self.n_launch_fwd = self.n_launch_bwd = 0
 
@@ -184,6 +185,18 @@ class Plan:
                 g = o._geom()
                 o.engine = 1 if N.lib().vae2_conv2d_tc_supported(C.byref(g)) else 0
         self.n_tc_convs = sum(o.engine for o in convs)
+        # shared split-K workspace of the tensor-core weight gradient (convs run one after another)
+        ws_floats = 0
+        if self.training:
+            for o in convs:
+                o.wgrad_tc = False
+                if o.engine == 1 and self.use_tc_wgrad:
+                    g = o._geom()
+                    need = N.lib().vae2_conv2d_wgrad_tc_workspace(C.byref(g))
+                    if need > 0:
+                        o.wgrad_tc = True
+                        ws_floats = max(ws_floats, need)
+        self.wgrad_ws = torch.zeros(ws_floats, dtype=torch.float32, device=dev) if ws_floats else None
         self.wp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev)
         self.wpT_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
         self.dwp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
@@ -449,7 +462,11 @@ class ConvOp:
         dy = y.grad()
         dyp, xp = dy.ptr, x.ptr
         dwp = plan.dwp_flat.data_ptr() + 4 * self.w_off
-        plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad(xp, dyp, dwp, pr.code, gp, 0, st))
+        if getattr(self, "wgrad_tc", False):
+            wsp = plan.wgrad_ws.data_ptr()
+            plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad_tc(xp, dyp, dwp, wsp, gp, st))
+        else:
+            plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad(xp, dyp, dwp, pr.code, gp, 0, st))
         if self.conv.bias is not None:
             db = plan.grad_ptr(self.conv.bias)
             npix, cb, ldy = y.npix, y.C, y.ld

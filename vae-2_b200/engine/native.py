@@ -57,6 +57,7 @@ _PROTOS = {
     "vae2_conv2d_dgrad": [vp, vp, vp, i32, C.POINTER(ConvGeom), i32, i32, vp],
     "vae2_conv2d_wgrad": [vp, vp, vp, i32, C.POINTER(ConvGeom), i32, vp],
     "vae2_bias_grad": [vp, vp, i32, i64, i32, i32, i32, vp],
+    "vae2_conv2d_wgrad_tc": [vp, vp, vp, vp, C.POINTER(ConvGeom), vp],
     "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)],
     "vae2_bn_stats": [vp, vp, ip, i32, i64, i32, i32, vp],
     "vae2_bn_merge": [vp, i32, i32, vp, vp],
@@ -78,7 +79,8 @@ _PROTOS = {
 _PLAIN_INT = {"vae2_abi_version": [], "vae2_bn_max_partials": [], "vae2_elbo_acc_floats": [],
               "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)]}
 
-EXPORTS = sorted(set(_PROTOS) | set(_PLAIN_INT) | {"vae2_status_string", "vae2_last_cuda_error"})
+EXPORTS = sorted(set(_PROTOS) | set(_PLAIN_INT) | {"vae2_status_string", "vae2_last_cuda_error",
+                                                     "vae2_conv2d_wgrad_tc_workspace"})
 
 _lib = None
 
@@ -100,6 +102,8 @@ def lib():
             fn = getattr(h, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        h.vae2_conv2d_wgrad_tc_workspace.argtypes = [C.POINTER(ConvGeom)]
+        h.vae2_conv2d_wgrad_tc_workspace.restype = C.c_longlong
         h.vae2_status_string.argtypes = [C.c_int]
         h.vae2_status_string.restype = C.c_char_p
         h.vae2_last_cuda_error.argtypes = []
