@@ -11,17 +11,21 @@ from test_gpu_kernels import dev, st, pad, to_act, from_act, table
 N = E.native
 pytestmark = pytest.mark.gpu
 
-TC_CASES = [  # (B, Cin, Cout, H, W, k, bias)
-    (1, 64, 64, 8, 128, 3, False),     # one full-width strip per tile, KC=64 (SWIZZLE_128B)
-    (1, 64, 64, 32, 64, 3, False),     # TW=64, TH=2
-    (2, 18, 18, 17, 23, 3, False),     # odd size, Cin_p=32 (SWIZZLE_64B), patches overhang the image
-    (1, 36, 36, 16, 32, 3, False),     # Cin_p=48 -> KC=16 (SWIZZLE_32B), 3 chunks per tap
-    (1, 64, 256, 9, 11, 1, False),     # 1x1, N=256
-    (1, 256, 64, 12, 40, 1, False),    # 1x1, K=256 (4 chunks)
-    (2, 270, 270, 16, 32, 1, True),    # head conv: Cp=272, two N tiles of 144, bias
-    (1, 144, 144, 8, 8, 3, False),     # low-res branch, TW=8 TH=16
-    (1, 72, 72, 33, 47, 3, False),
-    (3, 9, 64, 20, 36, 3, False),      # stem
+TC_CASES = [  # (B, Cin, Cout, H, W, k, bias, stride)
+    (1, 64, 64, 8, 128, 3, False, 1),     # one full-width strip per tile, KC=64 (SWIZZLE_128B)
+    (1, 64, 64, 32, 64, 3, False, 1),     # TW=64, TH=2
+    (2, 18, 18, 17, 23, 3, False, 1),     # odd size, Cin_p=32 (SWIZZLE_64B), patches overhang the image
+    (1, 36, 36, 16, 32, 3, False, 1),     # Cin_p=48 -> KC=16 (SWIZZLE_32B), 3 chunks per tap
+    (1, 64, 256, 9, 11, 1, False, 1),     # 1x1, N=256
+    (1, 256, 64, 12, 40, 1, False, 1),    # 1x1, K=256 (4 chunks)
+    (2, 270, 270, 16, 32, 1, True, 1),    # head conv: Cp=272, two N tiles of 144, bias
+    (1, 144, 144, 8, 8, 3, False, 1),     # low-res branch, TW=8 TH=16
+    (1, 72, 72, 33, 47, 3, False, 1),
+    (3, 9, 64, 20, 36, 3, False, 1),      # stem
+    (2, 18, 36, 16, 32, 3, False, 2),     # stride 2 (fuse-down / new-branch transitions), even size
+    (1, 36, 72, 33, 47, 3, False, 2),     # stride 2, odd size (Ho = ceil(H/2))
+    (1, 256, 36, 24, 40, 3, False, 2),    # transition1 new branch
+    (2, 72, 144, 9, 12, 3, False, 2),
 ]
 
 
@@ -41,22 +45,23 @@ def pack_bf16(w, Cin_p, Cout_p):
 
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_fwd_dgrad(case):
-    B, Cin, Cout, H, W, k, use_bias = case
+    B, Cin, Cout, H, W, k, use_bias, stride = case
+    Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
     tag = "tc%s" % (case,)
     x = O.det_normal(tag + "x", (B, Cin, H, W)).bfloat16().float()
     w = O.det_normal(tag + "w", (Cout, Cin, k, k), (2.0 / (Cin * k * k)) ** 0.5).bfloat16().float()
     bias = O.det_normal(tag + "b", (Cout,), 0.1) if use_bias else None
     xr = x.clone().requires_grad_(True)
-    yr = F.conv2d(xr, w, bias, stride=1, padding=k // 2)
+    yr = F.conv2d(xr, w, bias, stride=stride, padding=k // 2)
     gy = O.det_normal(tag + "gy", tuple(yr.shape)).bfloat16().float()
     yr.backward(gy)
 
     xa, Cin_p = to_act(x, "bf16", pad(Cin, 16))
     Cout_p = pad(Cout, 16)
     wq, wqT = pack_bf16(w, Cin_p, Cout_p)
-    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin_p, ldx=Cin_p, Ho=H, Wo=W, Cout_p=Cout_p, ldy=Cout_p, k=k, stride=1, pad=k // 2)
+    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin_p, ldx=Cin_p, Ho=Ho, Wo=Wo, Cout_p=Cout_p, ldy=Cout_p, k=k, stride=stride, pad=k // 2)
     assert N.lib().vae2_conv2d_tc_supported(C.byref(g)) == 1
-    ya = torch.zeros(B * H * W * Cout_p, dtype=torch.bfloat16, device=dev())
+    ya = torch.zeros(B * Ho * Wo * Cout_p, dtype=torch.bfloat16, device=dev())
     bp = None
     if bias is not None:
         bp = torch.zeros(Cout_p, dtype=torch.float32, device=dev())
@@ -64,7 +69,7 @@ def test_conv_tc_fwd_dgrad(case):
     N.call.vae2_conv2d_fwd(xa.data_ptr(), wq.data_ptr(), bp.data_ptr() if bp is not None else None, ya.data_ptr(), 1,
                            C.byref(g), 1, st())
     torch.cuda.synchronize()
-    y = from_act(ya, "bf16", B, Cout, H, W, Cout_p)
+    y = from_act(ya, "bf16", B, Cout, Ho, Wo, Cout_p)
     assert rel_err(y, yr.detach()) < 6e-3, "tc fwd rel err %.3e" % rel_err(y, yr.detach())
     assert float(ya.view(-1, Cout_p)[:, Cout:].float().abs().sum()) == 0.0
 
@@ -82,7 +87,7 @@ def test_conv_tc_fwd_dgrad(case):
     need = N.lib().vae2_conv2d_wgrad_tc_workspace(C.byref(g))
     if need > 0:
         wr = w.clone().requires_grad_(True)
-        F.conv2d(x, wr, None, stride=1, padding=k // 2).backward(gy)
+        F.conv2d(x, wr, None, stride=stride, padding=k // 2).backward(gy)
         ws = torch.zeros(need, dtype=torch.float32, device=dev())
         dwp = torch.full((k * k * Cin_p * Cout_p,), 7.0, dtype=torch.float32, device=dev())   # must be overwritten
         N.call.vae2_conv2d_wgrad_tc(xa.data_ptr(), gya.data_ptr(), dwp.data_ptr(), ws.data_ptr(), C.byref(g), st())
@@ -94,7 +99,7 @@ def test_conv_tc_fwd_dgrad(case):
         torch.cuda.synchronize()
         assert rel_err(dw.cpu(), wr.grad) < 6e-3, "tc wgrad rel err %.3e" % rel_err(dw.cpu(), wr.grad)
     else:
-        assert Cout_p > 256, "wgrad_tc unexpectedly unsupported"
+        raise AssertionError("wgrad_tc unexpectedly unsupported")
 
 
 def test_conv_tc_many_tiles_persistent():

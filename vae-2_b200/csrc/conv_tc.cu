@@ -35,11 +35,15 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
 
 struct Params {
-    int B, H, W;              // OUTPUT spatial extent (== input extent, stride 1)
+    int B;
+    int MH, MW;               // extent of the M grid (one GEMM row per grid point (i, j))
+    int OH, OW;               // spatial extent of the output tensor
+    int sO, oh_off, ow_off;   // output pixel of grid point (i, j) = (i*sO + oh_off, j*sO + ow_off)
+    int sA;                   // A box origin = (j0*sA + dw, i0*sA + dh); 2 for stride-2 forward (map has element stride 2)
     int Cn;                   // output channel lanes (N extent), multiple of 16
     int ldo;                  // output pixel pitch (elements)
-    int taps, ksz, pad;       // 9/3/1 or 1/1/0
-    int tap_sign;             // +1: input pixel = out + (k - pad)  (forward); -1: out - (k - pad) (dgrad)
+    int taps;                 // number of (dh, dw, weight-tap) entries
+    signed char tap_dh[9], tap_dw[9], tap_w[9];
     int kchunks;              // K chunks of KC channels per tap
     int KC;                   // 16 / 32 / 64 channels per stage
     int NT;                   // N tile (multiple of 16, <= 256)
@@ -175,14 +179,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int r = pt - b * per_img;
                 const int h0 = (r / p.tiles_w) * p.TH, w0 = (r % p.tiles_w) * p.TW;
                 for (int tap = 0; tap < p.taps; ++tap) {
-                    const int ky = tap / p.ksz, kx = tap - ky * p.ksz;
-                    const int dh = p.tap_sign * (ky - p.pad), dw = p.tap_sign * (kx - p.pad);
+                    const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], wt = p.tap_w[tap];
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full[stage], a_bytes + p.NT * row_bytes);
-                        tma_load_4d(sa, &map_a, &full[stage], kc * p.KC, w0 + dw, h0 + dh, b);
-                        tma_load_3d(sa + a_bytes, &map_w, &full[stage], kc * p.KC, nt * p.NT, tap);
+                        tma_load_4d(sa, &map_a, &full[stage], kc * p.KC, w0 * p.sA + dw, h0 * p.sA + dh, b);
+                        tma_load_3d(sa + a_bytes, &map_w, &full[stage], kc * p.KC, nt * p.NT, wt);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -230,12 +233,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int pt = tile / p.n_tiles;
             const int b = pt / per_img;
             const int r = pt - b * per_img;
-            const int h = (r / p.tiles_w) * p.TH + row / p.TW, w = (r % p.tiles_w) * p.TW + row % p.TW;
-            const bool in_img = h < p.H && w < p.W;
+            const int gi = (r / p.tiles_w) * p.TH + row / p.TW, gj = (r % p.tiles_w) * p.TW + row % p.TW;
+            const bool in_img = gi < p.MH && gj < p.MW;
+            const int h = gi * p.sO + p.oh_off, w = gj * p.sO + p.ow_off;
             mbar_wait(&acc_full[as], use & 1);
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.NT);
-            __nv_bfloat16* orow = p.out + (((long long)b * p.H + h) * p.W + w) * p.ldo;
+            __nv_bfloat16* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
             for (int c0 = 0; c0 < p.NT; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(t0 + c0, v);
@@ -328,6 +332,8 @@ struct WParams {
     int tiles_w, tiles_h, total_ptiles;
     int M_total;               // taps * Cin_p
     int set_groups, nsets, nranges;
+    int sA;                    // x box origin = (w0*sA + kx - pad, h0*sA + ky - pad); 2 for stride-2 convs
+    int NT, n_tiles;           // N tile (<= 256 output channels) and tile count
     int a_atoms_stage;         // atoms reserved for A per stage
     int stages;
     int tmem_cols;
@@ -358,7 +364,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t rowA = p.atomA * 2, rowB = p.atomB * 2;
     const uint32_t atomA_bytes = p.KP * rowA, atomB_bytes = p.KP * rowB;     // multiples of 1024 for KP = 32/64... (>= 512)
     const uint32_t a_bytes = (uint32_t)p.a_atoms_stage * atomA_bytes;
-    const uint32_t b_bytes = (uint32_t)(p.Cout_p / p.atomB) * atomB_bytes;
+    const uint32_t b_bytes = (uint32_t)(p.NT / p.atomB) * atomB_bytes;
     const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -368,7 +374,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int set = blockIdx.x % p.nsets, range = blockIdx.x / p.nsets;
+    const int set = blockIdx.x % p.nsets;
+    const int ntile = (blockIdx.x / p.nsets) % p.n_tiles;
+    const int range = blockIdx.x / (p.nsets * p.n_tiles);
+    const int n0 = ntile * p.NT;
     const int g_lo = set * p.set_groups;
     const int groups_total = (p.M_total + 127) / 128;
     const int g_hi = min(groups_total, g_lo + p.set_groups);      // exclusive
@@ -404,10 +413,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 mbar_expect_tx(&full[stage], tx_bytes);
                 for (int tap = t0; tap <= t1; ++tap) {
                     const int ky = tap / p.ksz, kx = tap - ky * p.ksz;
-                    tma_load_5d(sa + (size_t)(tap - t0) * nchunkA * atomA_bytes, &map_x, &full[stage], 0, w0 + kx - p.pad,
-                                h0 + ky - p.pad, b, 0);
+                    tma_load_5d(sa + (size_t)(tap - t0) * nchunkA * atomA_bytes, &map_x, &full[stage], 0,
+                                w0 * p.sA + kx - p.pad, h0 * p.sA + ky - p.pad, b, 0);
                 }
-                tma_load_5d(sa + a_bytes, &map_dy, &full[stage], 0, w0, h0, b, 0);
+                tma_load_5d(sa + a_bytes, &map_dy, &full[stage], 0, w0, h0, b, n0 / p.atomB);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -415,7 +424,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (lane == 0) {
             // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = Cout_p, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.Cout_p >> 3) << 17) | ((128u >> 4) << 24);
+                                   ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < n_my_tiles; ++i) {
@@ -425,7 +434,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const uint32_t sb = sa + a_bytes;
                 for (int g = g_lo; g < g_hi; ++g) {
                     const uint32_t a_rel = (uint32_t)(g * 128 - t0 * p.Cin_p) / (uint32_t)p.atomA;   // first atom of this group
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_lo) * p.Cout_p);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_lo) * p.NT);
                     for (int k = 0; k < p.KP / 16; ++k) {
                         umma_bf16(d_tmem, make_desc_mn(sa + a_rel * atomA_bytes + k * 16 * rowA, rowA, atomA_bytes),
                                   make_desc_mn(sb + k * 16 * rowB, rowB, atomB_bytes), idesc, (i | k) ? 1u : 0u);
@@ -443,13 +452,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         float* ws = p.ws + (size_t)range * p.M_total * p.Cout_p;
         for (int g = g_lo; g < g_hi; ++g) {
             const int m = g * 128 + q * 32 + lane;
-            const uint32_t t0a = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_lo) * p.Cout_p);
-            for (int c0 = 0; c0 < p.Cout_p; c0 += 16) {
+            const uint32_t t0a = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_lo) * p.NT);
+            for (int c0 = 0; c0 < p.NT; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(t0a + c0, v);
                 tmem_ld_wait();
-                if (m < p.M_total) {
-                    float4* dst = reinterpret_cast<float4*>(ws + (size_t)m * p.Cout_p + c0);
+                if (m < p.M_total && n0 + c0 < p.Cout_p) {
+                    float4* dst = reinterpret_cast<float4*>(ws + (size_t)m * p.Cout_p + n0 + c0);
                     if (n_my_tiles > 0) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
@@ -485,25 +494,27 @@ static int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16);
 
 // Fills p (everything except ws) and returns the workspace size in floats; <0 if unsupported.
 static long long plan_wgrad(const ConvGeom& g, WParams& p) {
-    if (g.Cout_p > 256) return -1;
-    p.B = g.B; p.H = g.H; p.W = g.W;
+    // K runs over OUTPUT pixels (Ho x Wo); x is sampled at stride g.stride
+    p.B = g.B; p.H = g.Ho; p.W = g.Wo; p.sA = g.stride;
+    p.n_tiles = (g.Cout_p + 255) / 256;
+    p.atomB = pick_atom(g.Cout_p);
+    p.NT = (((g.Cout_p + p.n_tiles - 1) / p.n_tiles) + p.atomB - 1) / p.atomB * p.atomB;
     p.Cin_p = g.Cin_p; p.Cout_p = g.Cout_p; p.ksz = g.k; p.taps = g.k * g.k; p.pad = g.k / 2;
     p.atomA = pick_atom(g.Cin_p);
-    p.atomB = pick_atom(g.Cout_p);
     int tw = 32;
-    while (tw > 8 && tw / 2 >= g.W) tw >>= 1;
+    while (tw > 8 && tw / 2 >= p.W) tw >>= 1;
     p.TW = tw; p.TH = 32 / tw; p.KP = 32;
-    p.tiles_w = (g.W + p.TW - 1) / p.TW;
-    p.tiles_h = (g.H + p.TH - 1) / p.TH;
+    p.tiles_w = (p.W + p.TW - 1) / p.TW;
+    p.tiles_h = (p.H + p.TH - 1) / p.TH;
     p.total_ptiles = g.B * p.tiles_w * p.tiles_h;
     p.M_total = p.taps * g.Cin_p;
     const int groups_total = (p.M_total + 127) / 128;
-    int sg = 512 / g.Cout_p;
+    int sg = 512 / p.NT;
     if (sg > groups_total) sg = groups_total;
     // keep the per-stage A footprint bounded: a set never needs more than (sg*128/Cin_p + 2) taps
     p.set_groups = sg;
     p.nsets = (groups_total + sg - 1) / sg;
-    p.tmem_cols = next_pow2_cols(sg * g.Cout_p);
+    p.tmem_cols = next_pow2_cols(sg * p.NT);
     // A atoms per stage: worst case over sets of (taps touched * chunks), and at least enough to cover whole groups
     const int nchunkA = g.Cin_p / p.atomA;
     int worst = 0;
@@ -519,13 +530,13 @@ static long long plan_wgrad(const ConvGeom& g, WParams& p) {
     }
     p.a_atoms_stage = worst;
     const long long a_bytes = (long long)worst * p.KP * p.atomA * 2;
-    const long long b_bytes = (long long)g.Cout_p * p.KP * 2;
+    const long long b_bytes = (long long)p.NT * p.KP * 2;
     const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     int stages = (int)(kSmemBudget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -1;
     p.stages = stages;
-    int nranges = kNumSMs / p.nsets;
+    int nranges = kNumSMs / (p.nsets * p.n_tiles);
     if (nranges < 1) nranges = 1;
     if (nranges > p.total_ptiles) nranges = p.total_ptiles;
     const long long slot = (long long)p.M_total * g.Cout_p;
@@ -538,34 +549,47 @@ static long long plan_wgrad(const ConvGeom& g, WParams& p) {
 }  // namespace tc
 
 int conv_tc_supported(const ConvGeom& g) {
-    if (g.stride != 1) return 0;
+    if (!(g.stride == 1 || (g.stride == 2 && g.k == 3))) return 0;
     if (!(g.k == 1 || g.k == 3)) return 0;
     if (g.Cin_p % 16 || g.Cout_p % 16 || g.ldx % 8 || g.ldy % 8) return 0;
-    if (g.H != g.Ho || g.W != g.Wo) return 0;
+    if (g.stride == 1 && (g.H != g.Ho || g.W != g.Wo)) return 0;
+    if (g.stride == 2 && (g.Ho != (g.H + 1) / 2 || g.Wo != (g.W + 1) / 2)) return 0;
     return tc::encode_fn() != nullptr ? 1 : 0;
 }
 
-// Generic launcher: `a` is the gathered tensor [B][H][W][lda] with Ck lanes on the K axis, `wq` the
-// packed bf16 weights [taps][Cn][Ck] (K contiguous), `out` [B][H][W][ldo] with Cn lanes.
-static int launch_tc(const void* a, int lda, int Ck, const void* wq, int Cn, void* out, int ldo, const float* bias, int B,
-                     int H, int W, int ksz, int tap_sign, int accumulate, cudaStream_t st) {
+namespace tc {
+struct Launch {
+    const void* a; int lda, Ck, AH, AW, a_estride;   // gathered tensor [B][AH][AW][lda], Ck lanes, TMA element stride
+    const void* wq; int Cn, wtaps;                    // packed bf16 weights [wtaps][Cn][Ck]
+    void* out; int ldo, OH, OW;
+    const float* bias;
+    int B, MH, MW, sO, oh_off, ow_off, sA;
+    int ntaps; signed char dh[9], dw[9], wt[9];
+    int accumulate;
+};
+}  // namespace tc
+
+static int launch_tc(const tc::Launch& L, cudaStream_t st) {
     using namespace tc;
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) return VAE2_ERR_UNSUPPORTED;
+    if (L.MH <= 0 || L.MW <= 0) return VAE2_OK;
     Params p;
-    p.B = B; p.H = H; p.W = W; p.Cn = Cn; p.ldo = ldo;
-    p.ksz = ksz; p.taps = ksz * ksz; p.pad = ksz / 2; p.tap_sign = tap_sign;
-    p.KC = pick_kc(Ck);
-    p.kchunks = Ck / p.KC;
-    p.n_tiles = (Cn + 255) / 256;
-    p.NT = (((Cn + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
-    // pixel patch: widest power-of-two strip that does not overshoot the row by more than 2x
+    p.B = L.B; p.MH = L.MH; p.MW = L.MW; p.OH = L.OH; p.OW = L.OW;
+    p.sO = L.sO; p.oh_off = L.oh_off; p.ow_off = L.ow_off; p.sA = L.sA;
+    p.Cn = L.Cn; p.ldo = L.ldo;
+    p.taps = L.ntaps;
+    for (int i = 0; i < 9; ++i) { p.tap_dh[i] = L.dh[i]; p.tap_dw[i] = L.dw[i]; p.tap_w[i] = L.wt[i]; }
+    p.KC = pick_kc(L.Ck);
+    p.kchunks = L.Ck / p.KC;
+    p.n_tiles = (L.Cn + 255) / 256;
+    p.NT = (((L.Cn + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
     int tw = 128;
-    while (tw > 8 && tw / 2 >= W) tw >>= 1;
+    while (tw > 8 && tw / 2 >= L.MW) tw >>= 1;
     p.TW = tw; p.TH = 128 / tw;
-    p.tiles_w = (W + p.TW - 1) / p.TW;
-    p.tiles_h = (H + p.TH - 1) / p.TH;
-    p.total_tiles = B * p.tiles_w * p.tiles_h * p.n_tiles;
+    p.tiles_w = (L.MW + p.TW - 1) / p.TW;
+    p.tiles_h = (L.MH + p.TH - 1) / p.TH;
+    p.total_tiles = L.B * p.tiles_w * p.tiles_h * p.n_tiles;
     const int row_bytes = p.KC * 2;
     const int a_bytes = 128 * row_bytes;
     const int b_bytes = ((p.NT * row_bytes + 1023) / 1024) * 1024;
@@ -575,27 +599,28 @@ static int launch_tc(const void* a, int lda, int Ck, const void* wq, int Cn, voi
     p.stages = stages;
     p.acc_stages = (2 * p.NT <= 512) ? 2 : 1;
     p.tmem_cols = next_pow2_cols(p.acc_stages * p.NT);
-    p.accumulate = accumulate;
-    p.bias = bias;
-    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.accumulate = L.accumulate;
+    p.bias = L.bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(L.out);
 
     CUtensorMap map_a, map_w;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)Ck, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)W * lda * 2, (cuuint64_t)H * W * lda * 2};
-        cuuint32_t box[4] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
-        if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a), dims, strides, box, es,
+        const cuuint32_t es_ = (cuuint32_t)L.a_estride;
+        cuuint64_t dims[4] = {(cuuint64_t)L.Ck, (cuuint64_t)L.AW, (cuuint64_t)L.AH, (cuuint64_t)L.B};
+        cuuint64_t strides[3] = {(cuuint64_t)L.lda * 2, (cuuint64_t)L.AW * L.lda * 2, (cuuint64_t)L.AH * L.AW * L.lda * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW * es_, (cuuint32_t)p.TH * es_, 1};
+        cuuint32_t es[4] = {1, es_, es_, 1};
+        if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(L.a), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return VAE2_ERR_ARG;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Ck, (cuuint64_t)Cn, (cuuint64_t)p.taps};
-        cuuint64_t strides[2] = {(cuuint64_t)Ck * 2, (cuuint64_t)Cn * Ck * 2};
+        cuuint64_t dims[3] = {(cuuint64_t)L.Ck, (cuuint64_t)L.Cn, (cuuint64_t)L.wtaps};
+        cuuint64_t strides[2] = {(cuuint64_t)L.Ck * 2, (cuuint64_t)L.Cn * L.Ck * 2};
         cuuint32_t box[3] = {(cuuint32_t)p.KC, (cuuint32_t)p.NT, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wq), dims, strides, box, es,
+        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(L.wq), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return VAE2_ERR_ARG;
@@ -614,13 +639,52 @@ static int launch_tc(const void* a, int lda, int Ck, const void* wq, int Cn, voi
 
 int conv_fwd_tc(const void* x, const void* wq, const float* bias, void* y, const ConvGeom& g, float*, cudaStream_t st) {
     if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
-    return launch_tc(x, g.ldx, g.Cin_p, wq, g.Cout_p, y, g.ldy, bias, g.B, g.H, g.W, g.k, +1, 0, st);
+    tc::Launch L{};
+    L.a = x; L.lda = g.ldx; L.Ck = g.Cin_p; L.AH = g.H; L.AW = g.W; L.a_estride = g.stride;
+    L.wq = wq; L.Cn = g.Cout_p; L.wtaps = g.k * g.k;
+    L.out = y; L.ldo = g.ldy; L.OH = g.Ho; L.OW = g.Wo; L.bias = bias;
+    L.B = g.B; L.MH = g.Ho; L.MW = g.Wo; L.sO = 1; L.oh_off = 0; L.ow_off = 0; L.sA = g.stride;
+    L.ntaps = g.k * g.k;
+    for (int t = 0; t < L.ntaps; ++t) { L.dh[t] = (signed char)(t / g.k - g.pad); L.dw[t] = (signed char)(t % g.k - g.pad); L.wt[t] = (signed char)t; }
+    L.accumulate = 0;
+    return launch_tc(L, st);
 }
 
-// dx (=|+=) conv_transpose(dy): same kernel, A = dy, weights = wqT [tap][Cin_p][Cout_p], mirrored taps
+// dx (=|+=) conv_transpose(dy): A = dy, weights = wqT [tap][Cin_p][Cout_p].
+// stride 1: one launch with mirrored tap offsets.  stride 2: dx pixels split into the four parity
+// classes (h%2, w%2); class (ph, pw) only sees taps with ky = ph+1 (mod 2), kx = pw+1 (mod 2) and is a
+// small stride-1 conv over dy whose results land on the class's strided pixel grid.
 int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st) {
     if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
-    return launch_tc(dy, g.ldy, g.Cout_p, wqT, g.Cin_p, dx, g.ldx, nullptr, g.B, g.H, g.W, g.k, -1, accumulate, st);
+    tc::Launch L{};
+    L.a = dy; L.lda = g.ldy; L.Ck = g.Cout_p; L.AH = g.Ho; L.AW = g.Wo; L.a_estride = 1;
+    L.wq = wqT; L.Cn = g.Cin_p; L.wtaps = g.k * g.k;
+    L.out = dx; L.ldo = g.ldx; L.OH = g.H; L.OW = g.W; L.bias = nullptr;
+    L.B = g.B; L.sA = 1; L.accumulate = accumulate;
+    if (g.stride == 1) {
+        L.MH = g.H; L.MW = g.W; L.sO = 1; L.oh_off = 0; L.ow_off = 0;
+        L.ntaps = g.k * g.k;
+        for (int t = 0; t < L.ntaps; ++t) { L.dh[t] = (signed char)(g.pad - t / g.k); L.dw[t] = (signed char)(g.pad - t % g.k); L.wt[t] = (signed char)t; }
+        return launch_tc(L, st);
+    }
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            L.MH = (g.H - ph + 1) / 2; L.MW = (g.W - pw + 1) / 2;
+            L.sO = 2; L.oh_off = ph; L.ow_off = pw;
+            int n = 0;
+            for (int ky = 0; ky < 3; ++ky) {
+                if (((ph + 1 - ky) & 1) != 0) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    if (((pw + 1 - kx) & 1) != 0) continue;
+                    L.dh[n] = (signed char)((ph + 1 - ky) / 2); L.dw[n] = (signed char)((pw + 1 - kx) / 2);
+                    L.wt[n] = (signed char)(ky * 3 + kx);
+                    ++n;
+                }
+            }
+            L.ntaps = n;
+            if (int e = launch_tc(L, st)) return e;
+        }
+    return VAE2_OK;
 }
 
 }  // namespace vae2
@@ -633,11 +697,13 @@ long long conv_wgrad_tc_workspace(const ConvGeom& g) {
     return tc::plan_wgrad(g, p);
 }
 
-static int make_map5(tc::EncodeTiledFn enc, CUtensorMap* m, const void* base, int atom, int C, int ld, int B, int H, int W, int TW, int TH) {
+static int make_map5(tc::EncodeTiledFn enc, CUtensorMap* m, const void* base, int atom, int C, int boxC, int ld, int B, int H,
+                     int W, int TW, int TH, int estride) {
+    const cuuint32_t e = (cuuint32_t)estride;
     cuuint64_t dims[5] = {(cuuint64_t)atom, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / atom)};
     cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)atom * 2};
-    cuuint32_t box[5] = {(cuuint32_t)atom, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)(C / atom)};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)atom, (cuuint32_t)TW * e, (cuuint32_t)TH * e, 1, (cuuint32_t)(boxC / atom)};
+    cuuint32_t es[5] = {1, e, e, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, tc::swz(atom), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
@@ -652,10 +718,10 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
     p.ws = ws;
     EncodeTiledFn enc = encode_fn();
     CUtensorMap map_x, map_dy;
-    if (make_map5(enc, &map_x, x, p.atomA, g.Cin_p, g.ldx, g.B, g.H, g.W, p.TW, p.TH)) return VAE2_ERR_ARG;
-    if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, g.ldy, g.B, g.H, g.W, p.TW, p.TH)) return VAE2_ERR_ARG;
+    if (make_map5(enc, &map_x, x, p.atomA, g.Cin_p, g.Cin_p, g.ldx, g.B, g.H, g.W, p.TW, p.TH, g.stride)) return VAE2_ERR_ARG;
+    if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, p.TW, p.TH, 1)) return VAE2_ERR_ARG;
     const long long a_bytes = (long long)p.a_atoms_stage * p.KP * p.atomA * 2;
-    const long long b_bytes = (long long)g.Cout_p * p.KP * 2;
+    const long long b_bytes = (long long)p.NT * p.KP * 2;
     const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
     static bool attr_set = false;
@@ -664,7 +730,7 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
             return VAE2_ERR_CUDA;
         attr_set = true;
     }
-    wgrad_tc_kernel<<<p.nsets * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
+    wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
     if (int e = check_launch()) return e;
     const long long n = (long long)p.M_total * g.Cout_p;
     wgrad_reduce_kernel<<<stream_grid(n / 4, 256, 4), 256, 0, st>>>(ws, dwp, n, p.nranges);
