@@ -323,6 +323,7 @@ def main():
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": 3 * B * 9 * H * W * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
+            "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": tf / tf_burst,
                          "traffic": None, "kernel": desc, "ms_per_launch": kms, "peak_source": src + " (burst, kernel timed alone)"},

@@ -18,7 +18,7 @@
 namespace vae2 {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_MAX_PARTS = kNumSMs * 4;
+constexpr int BN_MAX_PARTS = kNumSMs * 2;   // <= 2 CTAs per SM: few, fat partials keep the merges short
 
 int bn_stats_max_partials() { return BN_MAX_PARTS; }
 
@@ -39,15 +39,28 @@ bn_stats_kernel(const T* __restrict__ y, float* __restrict__ partials, long long
     for (int i = 0; i < V; ++i) { mean[i] = 0.f; m2[i] = 0.f; }
     float n = 0.f;
     if (active) {
-        for (long long p = (long long)blockIdx.x * R + r; p < P; p += (long long)gridDim.x * R) {
-            const Vec<T> x = Vec<T>::load(y + p * ld + lane * V);
-            n += 1.f;
-            const float inv = 1.f / n;
+        // 4 independent 16-byte loads in flight per thread before the (serial) Welford updates
+        const long long stride = (long long)gridDim.x * R;
+        for (long long p = (long long)blockIdx.x * R + r; p < P; p += 4 * stride) {
+            Vec<T> x[4];
+            bool ok[4];
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float d = x.v[i] - mean[i];
-                mean[i] += d * inv;
-                m2[i] = fmaf(d, x.v[i] - mean[i], m2[i]);
+            for (int u = 0; u < 4; ++u) {
+                const long long q = p + u * stride;
+                ok[u] = q < P;
+                if (ok[u]) x[u] = Vec<T>::load(y + q * ld + lane * V);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                n += 1.f;
+                const float inv = 1.f / n;
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float d = x[u].v[i] - mean[i];
+                    mean[i] += d * inv;
+                    m2[i] = fmaf(d, x[u].v[i] - mean[i], m2[i]);
+                }
             }
         }
     }
@@ -101,9 +114,14 @@ __device__ __forceinline__ void warp_merge_parts(const float* __restrict__ parts
                                                  float& n, float& mean, float& m2) {
     const int lane = threadIdx.x & 31;
     n = 0.f; mean = 0.f; m2 = 0.f;
-    for (int k = lane; k < n_parts; k += 32) {
+    for (int k = lane; k < n_parts; k += 64) {   // two independent partials in flight per step
         const float* p = parts + (long long)k * 3 * Cp;
-        chan_merge(n, mean, m2, p[c], p[Cp + c], p[2 * Cp + c]);
+        const bool has2 = k + 32 < n_parts;
+        const float* q = parts + (long long)(has2 ? k + 32 : k) * 3 * Cp;
+        const float a0 = p[c], a1 = p[Cp + c], a2 = p[2 * Cp + c];
+        const float b0 = q[c], b1 = q[Cp + c], b2 = q[2 * Cp + c];
+        chan_merge(n, mean, m2, a0, a1, a2);
+        if (has2) chan_merge(n, mean, m2, b0, b1, b2);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -223,18 +241,29 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* 
     if (active) {
 #pragma unroll
         for (int i = 0; i < V; ++i) { mu[i] = mean[lane * V + i]; is[i] = invstd[lane * V + i]; }
-        for (long long p = (long long)blockIdx.x * R + r; p < P; p += (long long)gridDim.x * R) {
-            Vec<T> gv = Vec<T>::load(g + p * ld_g + lane * V);
-            const Vec<T> yv = Vec<T>::load(y + p * ld_y + lane * V);
-            if (relu) {
-                const Vec<T> av = Vec<T>::load(a + p * ld_a + lane * V);
+        const long long stride = (long long)gridDim.x * R;
+        for (long long p = (long long)blockIdx.x * R + r; p < P; p += 2 * stride) {
+            Vec<T> gv[2], yv[2], av[2];
+            bool ok[2];
 #pragma unroll
-                for (int i = 0; i < V; ++i) gv.v[i] = av.v[i] > 0.f ? gv.v[i] : 0.f;
+            for (int u = 0; u < 2; ++u) {     // 2 pixels x 3 tensors = 6 independent loads in flight
+                const long long q = p + u * stride;
+                ok[u] = q < P;
+                if (ok[u]) {
+                    gv[u] = Vec<T>::load(g + q * ld_g + lane * V);
+                    yv[u] = Vec<T>::load(y + q * ld_y + lane * V);
+                    if (relu) av[u] = Vec<T>::load(a + q * ld_a + lane * V);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                s1[i] += gv.v[i];
-                s2[i] = fmaf(gv.v[i], (yv.v[i] - mu[i]) * is[i], s2[i]);
+            for (int u = 0; u < 2; ++u) {
+                if (!ok[u]) continue;
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float gg = (relu && !(av[u].v[i] > 0.f)) ? 0.f : gv[u].v[i];
+                    s1[i] += gg;
+                    s2[i] = fmaf(gg, (yv[u].v[i] - mu[i]) * is[i], s2[i]);
+                }
             }
         }
     }
@@ -336,7 +365,7 @@ static inline int vec_of(int dtype) { return dtype == VAE2_DT_F32 ? 4 : 8; }
 static int reduce_grid(long long P, int Cp, int V) {
     const int lanes = Cp / V;
     const int R = BN_THREADS / lanes;
-    long long need = (P + (long long)R * 8 - 1) / ((long long)R * 8);  // >= 8 pixels per thread
+    long long need = (P + (long long)R * 2 - 1) / ((long long)R * 2);   // 2 pixels per thread until the CTA cap, then more
     if (need < 1) need = 1;
     if (need > BN_MAX_PARTS) need = BN_MAX_PARTS;
     return (int)need;

@@ -511,6 +511,11 @@ static long long plan_wgrad(const ConvGeom& g, WParams& p) {
     const int groups_total = (p.M_total + 127) / 128;
     int sg = 512 / p.NT;
     if (sg > groups_total) sg = groups_total;
+    // shared-memory cap: a set of sg groups stages ~(sg*128 + 2*Cin_p) rows of KP*2 bytes of x per stage; keep
+    // that near 60 KB so that >= 3 pipeline stages fit (wide Cin, e.g. the 256-channel transition convs)
+    int sg_cap = (60 * 1024 - 128 * g.Cin_p) / 8192;
+    if (sg_cap < 1) sg_cap = 1;
+    if (sg > sg_cap) sg = sg_cap;
     // keep the per-stage A footprint bounded: a set never needs more than (sg*128/Cin_p + 2) taps
     p.set_groups = sg;
     p.nsets = (groups_total + sg - 1) / sg;

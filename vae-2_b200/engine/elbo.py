@@ -23,15 +23,16 @@ def _table(structs, dev):
 def check_finite(block=False):
     """Raise AssertionError (as the reference's _anomoly_detection does) if an earlier launch saw
     inf/nan in z or in a prediction.  Flags of launches that have already completed cost no stall."""
-    keep = []
+    keep, failed = [], None
     for names, flags, ev in _pending_flags:
         if block or ev.query():
-            bad = flags.tolist()
-            for n, b in zip(names, bad):
-                assert b == 0, "{} got nan or inf".format(n)
+            for n, b in zip(names, flags.tolist()):
+                if b != 0 and failed is None:
+                    failed = n
         else:
             keep.append((names, flags, ev))
-    _pending_flags[:] = keep
+    _pending_flags[:] = keep        # a reported launch is consumed even when it raises
+    assert failed is None, "{} got nan or inf".format(failed)
 
 
 class _Terms(torch.autograd.Function):
