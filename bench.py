@@ -335,9 +335,13 @@ def main():
                                                 "peak = sustained bf16 (" + src + ")"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(cfg, H, W)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroying a process group whose collectives live inside captured
+        # CUDA graphs was seen to hang at exit; every rank has passed the final barrier by now
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
