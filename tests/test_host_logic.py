@@ -1,0 +1,148 @@
+"""CPU: the C-ABI library's export surface, the drop-in module surface, plan recording, config,
+and the multi-rank host logic (world_size-2 gloo)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import E, O, M, ROOT, build_product, cfg_of, golden
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vae2_b200.h")).read()
+    declared = set(re.findall(r"\b(vae2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 30
+    h = E.native.lib()                       # loads libvae2_b200.so (no GPU needed to dlopen)
+    missing = [n for n in sorted(declared) if not hasattr(h, n)]
+    assert not missing, missing
+    assert h.vae2_abi_version() == 1
+    assert set(E.native.EXPORTS) <= declared
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(E.native, "_lib", None)
+    monkeypatch.setattr(E.native, "LIB_PATH", "/nonexistent/libvae2_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        E.native.lib()
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    cfg = cfg_of("vae2_hrnet_tiny_32x64.yaml")
+    net = M.get_encz_model(cfg)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 18, 32, 64))
+    import core.criterion as Cr
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Cr.L1Loss()(predict=torch.zeros(1, 3), target=torch.zeros(1, 3))
+
+
+@pytest.mark.parametrize("name", ["tiny_b2_32x64", "w18_b1_32x64"])
+def test_parameter_names_match_the_reference(name):
+    gold = golden(name)
+    g, d = build_product(cfg_of(str(gold["cfg"])))
+    assert sorted(k for k, _ in g.named_parameters()) == sorted(gold["g_grad_names"].tolist())
+    assert sorted(k for k, _ in d.named_parameters()) == sorted(gold["d_grad_names"].tolist())
+    assert g.encz_model.hd_z and g.encz_model.z_dim == 8 and g.D_model_sequence.clip_length == 3
+
+
+def test_plan_recording_covers_every_parameter():
+    from vae2_b200_engine.graph import Plan, Recorder
+    cfg = cfg_of("vae2_hrnet_w18_small_v2_256x512.yaml")
+    net = M.get_encdec_model(cfg)
+    plan = Plan(torch.device("cpu"), 1, "bf16", True, True)
+    sizes = O.branch_sizes(64, 128)
+    shapes = ((1, 9, 64, 128),) + tuple((1, 8, h, w) for h, w in sizes) + ((1, 8, 1, 1),)
+    outs = net._record(Recorder(plan), shapes, (False, True, True, True, True, False), "")
+    plan.finalize()
+    assert outs == [(9, 64, 128)] * 3
+    assert len(plan.params) == len(list(net.parameters()))
+    kinds = [type(o).__name__ for o in plan.ops]
+    assert kinds.count("ConvOp") == 462 and kinds.count("BnOp") == 453      # 462 convs / 453 BNs
+    # concat lane maps: transition3_e sees [code 8 | z 8 | features C] in padded segments
+    conv = next(o for o in plan.ops if type(o).__name__ == "ConvOp" and o.conv is net.transition3_e[0][0])
+    assert conv.x.cin_map[:16] == list(range(16)) and conv.x.cin_map[16] == 16 and conv.x.Cp % 16 == 0
+
+
+def test_config_surface(tmp_path):
+    from config import get_cfg_defaults, update_config
+    cfg = get_cfg_defaults()
+
+    class A:
+        cfg = os.path.join(ROOT, "experiments", "vae2", "vae2_hrnet_w18_small_v2_256x512.yaml")
+        opts = ["TRAIN.LR", "0.001", "MODEL.EXTRA.Z_DIM", "8"]
+    update_config(cfg, A)
+    assert cfg.TRAIN.LR == 0.001 and cfg.MODEL.EXTRA["STAGE4"]["NUM_CHANNELS"] == [18, 36, 72, 144]
+    assert cfg.MODEL.EXTRA.STAGE2.NUM_BRANCHES == 2 and cfg.DATASET.NUM_CLASSES == 3
+    with pytest.raises(AttributeError):
+        cfg.TRAIN.LR = 1.0                   # frozen
+    with pytest.raises(KeyError):
+        get_cfg_defaults().merge_from_list(["TRAIN.NO_SUCH_KEY", "1"])
+
+
+# ---- world_size-2 gloo: the SyncBN message algebra and the data-parallel gradient semantics ----------
+def _chan_merge(parts):
+    """Python restatement of csrc/bn.cu chan_merge over a list of (count, mean, M2) rows."""
+    n, mean, m2 = 0.0, 0.0, 0.0
+    for nb, mb, m2b in parts:
+        if nb <= 0:
+            continue
+        nn = n + nb
+        d = mb - mean
+        mean = mean + d * nb / nn
+        m2 = m2 + m2b + d * d * n * nb / nn
+        n = nn
+    return n, mean, m2
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    C_, per = 5, 7 * 11
+    full = torch.randn(world * per, C_, dtype=torch.float64) * 3 + 1.5      # the global batch, identical on all ranks
+    mine = full[rank * per:(rank + 1) * per]
+    # forward message: [3][C] = (count, mean, M2) per rank, all-gathered (graph.py BnOp.sync)
+    msg = torch.stack([torch.full((C_,), float(per), dtype=torch.float64), mine.mean(0),
+                       ((mine - mine.mean(0)) ** 2).sum(0)]).reshape(-1)
+    gathered = torch.zeros(world * 3 * C_, dtype=torch.float64)
+    dist.all_gather_into_tensor(gathered, msg)
+    parts = gathered.view(world, 3, C_)
+    merged = [_chan_merge([(float(parts[r, 0, c]), float(parts[r, 1, c]), float(parts[r, 2, c])) for r in range(world)])
+              for c in range(C_)]
+    mean = torch.tensor([m[1] for m in merged], dtype=torch.float64)
+    var = torch.tensor([m[2] / m[0] for m in merged], dtype=torch.float64)
+    ok_fwd = torch.allclose(mean, full.mean(0), atol=1e-12) and torch.allclose(var, full.var(0, unbiased=False), atol=1e-12)
+    # backward message: all-reduce of (sum dy, sum dy*xhat); dx uses the GLOBAL sums over the GLOBAL count
+    dy_full = torch.randn(world * per, C_, dtype=torch.float64)
+    xhat_full = (full - full.mean(0)) / torch.sqrt(full.var(0, unbiased=False) + 1e-5)
+    dy, xhat = dy_full[rank * per:(rank + 1) * per], xhat_full[rank * per:(rank + 1) * per]
+    sums = torch.stack([dy.sum(0), (dy * xhat).sum(0)])
+    local = sums.clone()
+    dist.all_reduce(sums)
+    ok_bwd = torch.allclose(sums[0], dy_full.sum(0)) and torch.allclose(sums[1], (dy_full * xhat_full).sum(0))
+    # parameter gradients stay LOCAL sums (DDP averages them afterwards): mean over ranks == global / world
+    g = local[1].clone()
+    dist.all_reduce(g)
+    ok_ddp = torch.allclose(g / world, (dy_full * xhat_full).sum(0) / world)
+    # bench.py's timing reduction: MAX over ranks
+    t = torch.tensor([10.0 + rank])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, bool(ok_fwd), bool(ok_bwd), bool(ok_ddp), float(t)))
+    dist.destroy_process_group()
+
+
+def test_syncbn_message_algebra_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=60) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, True, True, 11.0), (1, True, True, True, 11.0)]
