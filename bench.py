@@ -28,7 +28,7 @@ import torch.distributed as dist  # noqa: E402
 
 WORKLOADS = {
     # name: (yaml, H, W, per-GPU batch, algorithmic conv FLOP per sample for a full iteration)
-    "w18_256x512": ("vae2_hrnet_w18_small_v2_256x512.yaml", 256, 512, 1, 7.60e12),
+    "w18_256x512": ("vae2_hrnet_w18_small_v2_256x512.yaml", 256, 512, {"fp32": 2, "bf16": 4}, 7.60e12),
     "w18_1024x2048": ("vae2_hrnet_w18_small_v2_1024x2048.yaml", 1024, 2048, 1, 121.6e12),
     "tiny_32x64": ("vae2_hrnet_tiny_32x64.yaml", 32, 64, 2, None),
 }
@@ -238,6 +238,8 @@ def main():
 
     from config import load_config
     yaml_name, H, W, B, flop_per_sample = WORKLOADS[args.workload]
+    if isinstance(B, dict):      # largest per-GPU batch that fits 180 GB with this precision's activation footprint
+        B = B[args.precision]
     B = args.batch or B
     cfg = load_config(os.path.join(ROOT, "experiments", "vae2", yaml_name))
     if args.impl == "reference":

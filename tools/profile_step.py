@@ -11,6 +11,10 @@ prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 workload = sys.argv[2] if len(sys.argv) > 2 else "w18_256x512"
 E = engine(); E.set_precision(prec); E.use_cuda_graphs(False)
 yaml_name, H, W, B, _ = bench.WORKLOADS[workload]
+if isinstance(B, dict):
+    B = B[prec]
+if len(sys.argv) > 3:
+    B = int(sys.argv[3])
 cfg = load_config(os.path.join(ROOT, "experiments", "vae2", yaml_name))
 dev = torch.device("cuda:0")
 g, d, og, od = bench.build_models(cfg, dev, 1, 0)

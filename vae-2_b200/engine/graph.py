@@ -43,6 +43,27 @@ def conv_out(n, k, s):
     return (n + 2 * p - k) // s + 1
 
 
+class GradArena:
+    """One gradient arena per (device, dtype), shared by ALL plans: activation gradients only live inside
+    a plan's run_backward (written from the upstream gradient in pre_bwd, consumed by post_bwd), and
+    backward passes run one at a time, so every plan can alias the same memory.  This halves the
+    resident footprint of a training step (the D nets alone are 12 plan instances per iteration)."""
+    _arenas = {}
+
+    @classmethod
+    def get(cls, device, tdtype, numel):
+        key = (str(device), tdtype)
+        cur = cls._arenas.get(key)
+        if cur is None or cur.numel() < numel:
+            cur = torch.zeros(numel, dtype=tdtype, device=device)   # older plans keep their (smaller) arena alive
+            cls._arenas[key] = cur
+        return cur
+
+    @classmethod
+    def reset(cls):
+        cls._arenas.clear()
+
+
 class Act:
     """A channels-last activation [B][H][W][ld] (possibly a channel slice of a wider root)."""
 
@@ -54,6 +75,7 @@ class Act:
             self.Cp = pad_to(C_, pr.tot_align) if Cp is None else Cp
             self.buf = torch.zeros(self.B * H * W * self.Cp, dtype=pr.tdtype, device=plan.device)
             self.ld, self.c_off, self.parent = self.Cp, 0, None
+            plan.all_acts.append(self)
         else:
             self.Cp = Cp
             self.buf, self.ld, self.c_off, self.parent = root.buf, root.ld, root.c_off + c_off, root
@@ -83,7 +105,7 @@ class Act:
             if self.parent is None:
                 g = Act.__new__(Act)
                 g.__dict__.update(self.__dict__)
-                g.buf = torch.zeros_like(self.buf)
+                g.buf = self.plan.grad_alloc(self.buf.numel())
                 g._grad, g.parent = None, None
                 self._grad = g
             else:
@@ -130,6 +152,8 @@ class Plan:
         self.inputs, self.outputs = [], []
         self.keep = []                        # keep-alive for ctypes arrays / tensors
         self.busy = False
+        self._garena, self._goff = None, 0
+        self.all_acts = []
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
         self.use_tc_wgrad = os.environ.get("VAE2_DISABLE_TC_WGRAD", "0") != "1"
         self.graph_fwd = self.graph_bwd = None
@@ -145,6 +169,16 @@ class Plan:
 
     def new_act(self, C_, H, W, name=""):
         return Act(self, C_, H, W, name=name)
+
+    def grad_alloc(self, numel):
+        """Bump-allocate an activation-gradient buffer from the shared arena (128-element aligned)."""
+        if self._garena is None:      # finalize() sizes the arena; a stray early request gets private memory
+            return torch.zeros(numel, dtype=self.prec.tdtype, device=self.device)
+        n = pad_to(numel, 128)
+        assert self._goff + n <= self._garena.numel(), "gradient arena under-sized"
+        t = self._garena[self._goff:self._goff + numel]
+        self._goff += n
+        return t
 
     def concat(self, Cs, H, W, name="cat"):
         """A buffer made of padded channel segments; returns (root, [slice acts])."""
@@ -235,6 +269,9 @@ class Plan:
             o.emit_fwd(self)
         # backward program (reverse order; accumulate flags resolved statically)
         if self.training:
+            if os.environ.get("VAE2_PRIVATE_GRADS", "0") != "1":
+                need = sum(pad_to(a.buf.numel(), 128) for a in self.all_acts)
+                self._garena, self._goff = GradArena.get(dev, self.prec.tdtype, need), 0
             nbytes = self.dwp_flat.numel() * 4
             dptr = self.dwp_flat
             self.bwd.append(lambda st: dptr.zero_())
