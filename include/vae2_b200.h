@@ -99,6 +99,12 @@ int vae2_bn_merge(const float* partials, int n_partials, int Cp, float* merged, 
 int vae2_bn_finalize(const float* partials, int n_partials, int C, int Cp, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                      float eps, float* mean, float* invstd, float* scale, float* shift, vae2_stream_t stream);
+/* same, with the partial sets `part_stride` floats apart: several BNs of one SyncBN group share ONE all-gather
+ * message, so rank r's partial of this BN sits at partials + r*part_stride */
+int vae2_bn_finalize_strided(const float* partials, int n_partials, int64_t part_stride, int C, int Cp,
+                             const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             int64_t* num_batches_tracked, float momentum, float eps, float* mean, float* invstd,
+                             float* scale, float* shift, vae2_stream_t stream);
 int vae2_bn_eval_coeffs(int C, int Cp, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, vae2_stream_t stream);
 /* out = [relu](scale*y + shift [+ res])   (BasicBlock/Bottleneck tails, enc_hrnet.py:46-62, 83-103) */

@@ -61,7 +61,10 @@ def test_plan_recording_covers_every_parameter():
     assert outs == [(9, 64, 128)] * 3
     assert len(plan.params) == len(list(net.parameters()))
     kinds = [type(o).__name__ for o in plan.ops]
-    assert kinds.count("ConvOp") == 462 and kinds.count("BnOp") == 453      # 462 convs / 453 BNs
+    n_bn = kinds.count("BnOp") + sum(len(o.members) for o in plan.ops if type(o).__name__ == "BnGroupOp")
+    assert kinds.count("ConvOp") == 462 and n_bn == 453      # 462 convs / 453 BNs
+    # BNs at the same depth of sibling branches share one group (= one SyncBN collective)
+    assert kinds.count("BnOp") + kinds.count("BnGroupOp") < 0.6 * n_bn
     # concat lane maps: transition3_e sees [code 8 | z 8 | features C] in padded segments
     conv = next(o for o in plan.ops if type(o).__name__ == "ConvOp" and o.conv is net.transition3_e[0][0])
     assert conv.x.cin_map[:16] == list(range(16)) and conv.x.cin_map[16] == 16 and conv.x.Cp % 16 == 0

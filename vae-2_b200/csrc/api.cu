@@ -100,6 +100,12 @@ int vae2_bn_finalize(const float* partials, int n_partials, int C, int Cp, const
     return bn_finalize(partials, n_partials, C, Cp, gamma, beta, running_mean, running_var,
                        reinterpret_cast<long long*>(nbt), momentum, eps, mean, invstd, scale, shift, S(stream));
 }
+int vae2_bn_finalize_strided(const float* partials, int n_partials, int64_t part_stride, int C, int Cp, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
+                             float eps, float* mean, float* invstd, float* scale, float* shift, vae2_stream_t stream) {
+    return bn_finalize(partials, n_partials, C, Cp, gamma, beta, running_mean, running_var,
+                       reinterpret_cast<long long*>(nbt), momentum, eps, mean, invstd, scale, shift, S(stream), part_stride);
+}
 int vae2_bn_eval_coeffs(int C, int Cp, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, vae2_stream_t stream) {
     return bn_eval_coeffs(C, Cp, gamma, beta, running_mean, running_var, eps, scale, shift, S(stream));

@@ -111,13 +111,14 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
 // One WARP per channel: lanes fold partials lane, lane+32, ... then a 5-step shuffle tree of Chan
 // merges (the merge is associative), so the latency is ~n_parts/32 dependent loads, not n_parts.
 __device__ __forceinline__ void warp_merge_parts(const float* __restrict__ parts, int n_parts, int Cp, int c,
-                                                 float& n, float& mean, float& m2) {
+                                                 float& n, float& mean, float& m2, long long part_stride = 0) {
+    if (part_stride == 0) part_stride = 3LL * Cp;
     const int lane = threadIdx.x & 31;
     n = 0.f; mean = 0.f; m2 = 0.f;
     for (int k = lane; k < n_parts; k += 64) {   // two independent partials in flight per step
-        const float* p = parts + (long long)k * 3 * Cp;
+        const float* p = parts + (long long)k * part_stride;
         const bool has2 = k + 32 < n_parts;
-        const float* q = parts + (long long)(has2 ? k + 32 : k) * 3 * Cp;
+        const float* q = parts + (long long)(has2 ? k + 32 : k) * part_stride;
         const float a0 = p[c], a1 = p[Cp + c], a2 = p[2 * Cp + c];
         const float b0 = q[c], b1 = q[Cp + c], b2 = q[2 * Cp + c];
         chan_merge(n, mean, m2, a0, a1, a2);
@@ -155,7 +156,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ parts, int n_parts,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ mean_o, float* __restrict__ invstd_o,
-                                   float* __restrict__ scale_o, float* __restrict__ shift_o) {
+                                   float* __restrict__ scale_o, float* __restrict__ shift_o, long long part_stride) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = gt >> 5;
     if (gt == 0 && nbt != nullptr) *nbt += 1;
@@ -166,7 +167,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ parts, int n_parts,
         return;
     }
     float n, mean, m2;
-    warp_merge_parts(parts, n_parts, Cp, c, n, mean, m2);
+    warp_merge_parts(parts, n_parts, Cp, c, n, mean, m2, part_stride);
     if (!lead) return;
     const float var = m2 / n;
     const float invstd = rsqrtf(var + eps);
@@ -391,9 +392,10 @@ int bn_merge(const float* partials, int n_partials, int Cp, float* merged, cudaS
 
 int bn_finalize(const float* parts, int n_parts, int C, int Cp, const float* gamma, const float* beta,
                 float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
-                float* mean, float* invstd, float* scale, float* shift, cudaStream_t st) {
+                float* mean, float* invstd, float* scale, float* shift, cudaStream_t st, long long part_stride) {
     bn_finalize_kernel<<<(Cp * 32 + 127) / 128, 128, 0, st>>>(parts, n_parts, C, Cp, gamma, beta, running_mean, running_var,
-                                                        num_batches_tracked, momentum, eps, mean, invstd, scale, shift);
+                                                        num_batches_tracked, momentum, eps, mean, invstd, scale, shift,
+                                                        part_stride);
     return check_launch();
 }
 

@@ -47,7 +47,7 @@ int bn_stats_max_partials();
 int bn_merge(const float* partials, int n_partials, int Cp, float* merged, cudaStream_t st);
 int bn_finalize(const float* parts, int n_parts, int C, int Cp, const float* gamma, const float* beta,
                 float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
-                float* mean, float* invstd, float* scale, float* shift, cudaStream_t st);
+                float* mean, float* invstd, float* scale, float* shift, cudaStream_t st, long long part_stride = 0);
 int bn_eval_coeffs(int C, int Cp, const float* gamma, const float* beta, const float* running_mean,
                    const float* running_var, float eps, float* scale, float* shift, cudaStream_t st);
 int bn_apply(const void* y, const void* res, void* out, int dtype, long long P, int Cp, int ld_y, int ld_res, int ld_out,

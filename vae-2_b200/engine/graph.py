@@ -152,6 +152,7 @@ class Plan:
         self.inputs, self.outputs = [], []
         self.keep = []                        # keep-alive for ctypes arrays / tensors
         self.busy = False
+        self.n_collectives_fwd = self.n_collectives_bwd = 0
         self._garena, self._goff = None, 0
         self.all_acts = []
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
@@ -517,7 +518,11 @@ class ConvOp:
 
 
 class BnOp:
-    """BatchNorm2d (+residual)(+ReLU) on a raw conv output; training or eval statistics."""
+    """BatchNorm2d (+residual)(+ReLU) on a raw conv output; training or eval statistics.
+
+    Emission is split into sub-steps so that a BnGroupOp can run the members of a SyncBN group through
+    ONE collective: stats(+rank-local merge) | all-gather | finalize+apply, and in backward
+    reduce | all-reduce | coeffs+elemt."""
 
     def __init__(self, plan, y, bn, relu, residual=None, out=None):
         self.y, self.bn, self.relu, self.res = y, bn, relu, residual
@@ -527,46 +532,52 @@ class BnOp:
         plan.param(bn.bias)
         self.sync = isinstance(bn, torch.nn.SyncBatchNorm) and plan.world_size > 1
 
-    def emit_fwd(self, plan):
-        pr, dev = plan.prec, plan.device
-        y, out, bn, res = self.y, self.out, self.bn, self.res
+    # ---- forward sub-steps ---------------------------------------------------------------------
+    def _fwd_setup(self, plan):
+        y = self.y
+        f32 = dict(dtype=torch.float32, device=plan.device)
+        self.mean, self.invstd = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
+        self.scale, self.shift = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
+        self.batch_stats = plan.bn_batch_stats or not self.bn.track_running_stats
+        if self.batch_stats:
+            self.partials = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * y.Cp, **f32)
+            self.npart = C.c_int(0)
+
+    def _emit_stats(self, plan, merged_ptr=None):
+        """Per-CTA partials (and, for SyncBN, the rank-local merge into the group message)."""
+        pr, y = plan.prec, self.y
+        pp, yp, npart, Cp, npix, ld = self.partials.data_ptr(), y.ptr, self.npart, y.Cp, y.npix, y.ld
+        plan.fwd.append(lambda st: N.call.vae2_bn_stats(yp, pp, C.byref(npart), pr.code, npix, Cp, ld, st))
+        if merged_ptr is not None:
+            plan.fwd.append(lambda st: N.call.vae2_bn_merge(pp, npart.value, Cp, merged_ptr, st))
+
+    def _emit_finalize(self, plan, parts_ptr=None, n_parts=None, stride=0):
+        bn, y = self.bn, self.y
         Cp, C_ = y.Cp, y.C
-        f32 = dict(dtype=torch.float32, device=dev)
-        self.mean, self.invstd = torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
-        self.scale, self.shift = torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
         eps = float(bn.eps)
         mom = 0.0 if bn.momentum is None else float(bn.momentum)
-        lanes = min(Cp, out.Cp)
-        if plan.bn_batch_stats or not bn.track_running_stats:
-            maxp = N.lib().vae2_bn_max_partials()
-            self.partials = torch.zeros(maxp * 3 * Cp, **f32)
-            npart = C.c_int(0)
-            plan.keep.append(npart)
-            pp, yp = self.partials.data_ptr(), y.ptr
-            npix, ld = y.npix, y.ld
-            plan.fwd.append(lambda st: N.call.vae2_bn_stats(yp, pp, C.byref(npart), pr.code, npix, Cp, ld, st))
+        gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
+        if self.batch_stats:
             rm = bn.running_mean.data_ptr() if bn.running_mean is not None else None
             rv = bn.running_var.data_ptr() if bn.running_var is not None else None
             nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
-            gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
             outs = (self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr())
-            if self.sync:
-                merged = torch.zeros(3 * Cp, **f32)
-                gathered = torch.zeros(plan.world_size * 3 * Cp, **f32)
-                plan.keep += [merged, gathered]
-                mp, gtp, ws, grp = merged.data_ptr(), gathered.data_ptr(), plan.world_size, plan.group
-                plan.fwd.append(lambda st: N.call.vae2_bn_merge(pp, npart.value, Cp, mp, st))
-                plan.fwd.append(lambda st: dist.all_gather_into_tensor(gathered, merged, group=grp))
-                plan.fwd.append(lambda st: N.call.vae2_bn_finalize(gtp, ws, C_, Cp, gp, bp, rm, rv, nbt, mom, eps,
-                                                                   *outs, st))
-            else:
+            if parts_ptr is None:
+                pp, npart = self.partials.data_ptr(), self.npart
                 plan.fwd.append(lambda st: N.call.vae2_bn_finalize(pp, npart.value, C_, Cp, gp, bp, rm, rv, nbt, mom,
                                                                    eps, *outs, st))
+            else:
+                plan.fwd.append(lambda st: N.call.vae2_bn_finalize_strided(parts_ptr, n_parts, stride, C_, Cp, gp, bp,
+                                                                           rm, rv, nbt, mom, eps, *outs, st))
         else:
-            gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
             rm, rv = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             sp, hp = self.scale.data_ptr(), self.shift.data_ptr()
             plan.fwd.append(lambda st: N.call.vae2_bn_eval_coeffs(C_, Cp, gp, bp, rm, rv, eps, sp, hp, st))
+
+    def _emit_apply(self, plan):
+        pr = plan.prec
+        y, out, res = self.y, self.out, self.res
+        lanes = min(y.Cp, out.Cp)
         yp, op_, rp = y.ptr, out.ptr, (res.ptr if res is not None else None)
         ldr = res.ld if res is not None else 0
         sp, hp, relu = self.scale.data_ptr(), self.shift.data_ptr(), 1 if self.relu else 0
@@ -574,51 +585,121 @@ class BnOp:
         plan.fwd.append(lambda st: N.call.vae2_bn_apply(yp, rp, op_, pr.code, npix, lanes, ldy, ldr, ldo, sp, hp,
                                                         relu, st))
 
-    def emit_bwd(self, plan):
-        pr, dev = plan.prec, plan.device
-        y, out, bn, res = self.y, self.out, self.bn, self.res
-        Cp, C_ = y.Cp, y.C
-        f32 = dict(dtype=torch.float32, device=dev)
-        g = out.grad()
-        maxp = N.lib().vae2_bn_max_partials()
-        parts = torch.zeros(maxp * 2 * Cp, **f32)
-        sums, c1, c2 = torch.zeros(2 * Cp, **f32), torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
-        plan.keep += [parts, sums, c1, c2]
-        npart = C.c_int(0)
-        plan.keep.append(npart)
-        lanes = min(Cp, out.Cp)
-        gp_, ap, yp = g.ptr, out.ptr, y.ptr
-        npix = y.npix
-        relu = 1 if self.relu else 0
-        mp, ip = self.mean.data_ptr(), self.invstd.data_ptr()
-        pp, sp = parts.data_ptr(), sums.data_ptr()
+    def emit_fwd(self, plan):
+        """Stand-alone BN (its own collective under SyncBN)."""
+        BnGroupOp(plan, [self]).emit_fwd(plan)
+
+    # ---- backward sub-steps --------------------------------------------------------------------
+    def _bwd_setup(self, plan):
+        y = self.y
+        f32 = dict(dtype=torch.float32, device=plan.device)
+        self.bparts = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * y.Cp, **f32)
+        self.sums, self.c1, self.c2 = torch.zeros(2 * y.Cp, **f32), torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
+        self.bnpart = C.c_int(0)
+        self.lanes = min(y.Cp, self.out.Cp)
+        self.g = self.out.grad()
+
+    def _emit_bwd_reduce(self, plan):
+        pr = plan.prec
+        y, out, g = self.y, self.out, self.g
+        gp_, ap, yp, pp, sp = g.ptr, out.ptr, y.ptr, self.bparts.data_ptr(), self.sums.data_ptr()
+        npart, npix, lanes, C_ = self.bnpart, y.npix, self.lanes, y.C
+        mp, ip, relu = self.mean.data_ptr(), self.invstd.data_ptr(), 1 if self.relu else 0
+        gld, old, yld = g.ld, out.ld, y.ld
         plan.bwd.append(lambda st: N.call.vae2_bn_bwd_reduce(gp_, ap, yp, pp, C.byref(npart), pr.code, npix, lanes,
-                                                             g.ld, out.ld, y.ld, mp, ip, relu, st))
+                                                             gld, old, yld, mp, ip, relu, st))
         plan.bwd.append(lambda st: N.call.vae2_bn_bwd_finalize(pp, npart.value, C_, lanes, sp, st))
+
+    def _emit_bwd_apply(self, plan, gsum_ptr=None):
+        """coefficients (from the global sums) + elementwise pass; parameter grads from the LOCAL sums."""
+        pr = plan.prec
+        y, out, bn, res, g = self.y, self.out, self.bn, self.res, self.g
+        npix, lanes, C_ = y.npix, self.lanes, y.C
+        sp = self.sums.data_ptr()
         dgam, dbet = plan.grad_ptr(bn.weight), plan.grad_ptr(bn.bias)
-        c1p, c2p = c1.data_ptr(), c2.data_ptr()
-        count = npix * (plan.world_size if self.sync else 1)
-        if self.sync:
-            gsum = torch.zeros(2 * Cp, **f32)
-            plan.keep.append(gsum)
-            gsp, grp = gsum.data_ptr(), plan.group
-            plan.bwd.append(lambda st: gsum.copy_(sums))
-            plan.bwd.append(lambda st: dist.all_reduce(gsum, group=grp))
-            plan.bwd.append(lambda st: N.call.vae2_bn_bwd_coeffs(gsp, C_, lanes, 1.0 / count, dgam, dbet, 0, sp, c1p,
-                                                                 c2p, st))
-        else:
-            plan.bwd.append(lambda st: N.call.vae2_bn_bwd_coeffs(sp, C_, lanes, 1.0 / count, dgam, dbet, 0, sp, c1p,
-                                                                 c2p, st))
+        c1p, c2p = self.c1.data_ptr(), self.c2.data_ptr()
+        count = npix * (plan.world_size if gsum_ptr is not None else 1)
+        gs = gsum_ptr if gsum_ptr is not None else sp
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_coeffs(gs, C_, lanes, 1.0 / count, dgam, dbet, 0, sp, c1p, c2p, st))
         dy = y.grad()
         acc_dy = y.take_acc_flag()
         dres_p, ld_dres, acc_res = None, 0, 0
         if res is not None and res.needs_grad:
             acc_res = res.take_acc_flag()
             dres_p, ld_dres = res.grad().ptr, res.ld
-        dyp, scp = dy.ptr, self.scale.data_ptr()
-        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_elemt(gp_, ap, yp, dyp, dres_p, pr.code, npix, lanes, g.ld,
-                                                            out.ld, y.ld, dy.ld, ld_dres, mp, ip, scp, c1p, c2p, relu,
-                                                            acc_dy, acc_res, st))
+        gp_, ap, yp, dyp = g.ptr, out.ptr, y.ptr, dy.ptr
+        mp, ip, scp, relu = self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), 1 if self.relu else 0
+        gld, old, yld, dld = g.ld, out.ld, y.ld, dy.ld
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_elemt(gp_, ap, yp, dyp, dres_p, pr.code, npix, lanes, gld, old,
+                                                            yld, dld, ld_dres, mp, ip, scp, c1p, c2p, relu, acc_dy,
+                                                            acc_res, st))
+
+    def emit_bwd(self, plan):
+        BnGroupOp(plan, [self]).emit_bwd(plan)
+
+
+class BnGroupOp:
+    """BNs at the same depth of independent branches.  Single rank: the members simply run one after the
+    other.  SyncBN: their (count, mean, M2) messages are concatenated and travel in ONE all-gather, their
+    backward sums in ONE all-reduce -- the reference's per-BN collectives (1177 + 1160 per iteration,
+    SURVEY.md §2.2) shrink by the branch count."""
+
+    def __init__(self, plan, members):
+        self.members = members
+        self.sync = bool(members) and members[0].sync
+
+    def emit_fwd(self, plan):
+        ms = self.members
+        for m in ms:
+            m._fwd_setup(plan)
+        if not (self.sync and ms[0].batch_stats):
+            for m in ms:
+                if m.batch_stats:
+                    m._emit_stats(plan)
+                m._emit_finalize(plan)
+                m._emit_apply(plan)
+            return
+        f32 = dict(dtype=torch.float32, device=plan.device)
+        offs, total = [], 0
+        for m in ms:
+            offs.append(total)
+            total += 3 * m.y.Cp
+        msg, gathered = torch.zeros(total, **f32), torch.zeros(plan.world_size * total, **f32)
+        plan.keep += [msg, gathered]
+        for m, off in zip(ms, offs):
+            m._emit_stats(plan, merged_ptr=msg.data_ptr() + 4 * off)
+        grp = plan.group
+        plan.fwd.append(lambda st: dist.all_gather_into_tensor(gathered, msg, group=grp))
+        plan.n_collectives_fwd += 1
+        for m, off in zip(ms, offs):
+            m._emit_finalize(plan, parts_ptr=gathered.data_ptr() + 4 * off, n_parts=plan.world_size, stride=total)
+            m._emit_apply(plan)
+
+    def emit_bwd(self, plan):
+        ms = list(reversed(self.members))
+        for m in ms:
+            m._bwd_setup(plan)
+        if not (self.sync and ms[0].batch_stats):
+            for m in ms:
+                m._emit_bwd_reduce(plan)
+                m._emit_bwd_apply(plan)
+            return
+        f32 = dict(dtype=torch.float32, device=plan.device)
+        offs, total = [], 0
+        for m in ms:
+            offs.append(total)
+            total += 2 * m.y.Cp
+        gsum = torch.zeros(total, **f32)
+        plan.keep.append(gsum)
+        for m, off in zip(ms, offs):
+            m._emit_bwd_reduce(plan)
+            dst, src, n = gsum[off:off + 2 * m.lanes], m.sums, 2 * m.lanes
+            plan.bwd.append(lambda st, dst=dst, src=src, n=n: dst.copy_(src[:n]))
+        grp = plan.group
+        plan.bwd.append(lambda st: dist.all_reduce(gsum, group=grp))
+        plan.n_collectives_bwd += 1
+        for m, off in zip(ms, offs):
+            m._emit_bwd_apply(plan, gsum_ptr=gsum.data_ptr() + 4 * off)
 
 
 class FuseOp:
@@ -737,6 +818,18 @@ class Recorder:
 
     def conv_bn(self, x, conv, bn, relu=False, residual=None, out=None):
         return self.bn(self.conv(x, conv), bn, relu, residual, out)
+
+    def conv_bn_multi(self, items):
+        """items: dicts {x, conv, bn, relu?, residual?, out?} for INDEPENDENT conv+BN pairs (same depth of
+        different branches).  All convs are recorded first, then the BNs as one group (one SyncBN collective)."""
+        if len(items) == 1:
+            it = items[0]
+            return [self.conv_bn(it["x"], it["conv"], it["bn"], it.get("relu", False), it.get("residual"), it.get("out"))]
+        ys = [self.conv(it["x"], it["conv"]) for it in items]
+        ops = [BnOp(self.plan, y, it["bn"], it.get("relu", False), it.get("residual"), it.get("out"))
+               for y, it in zip(ys, items)]
+        self.plan.add(BnGroupOp(self.plan, ops))
+        return [op.out for op in ops]
 
     def fuse(self, srcs, H, W, relu=True, out=None):
         return self.plan.add(FuseOp(self.plan, srcs, H, W, relu, out)).out

@@ -62,6 +62,7 @@ _PROTOS = {
     "vae2_bn_stats": [vp, vp, ip, i32, i64, i32, i32, vp],
     "vae2_bn_merge": [vp, i32, i32, vp, vp],
     "vae2_bn_finalize": [vp, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp],
+    "vae2_bn_finalize_strided": [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp],
     "vae2_bn_eval_coeffs": [i32, i32, vp, vp, vp, vp, f32, vp, vp, vp],
     "vae2_bn_apply": [vp, vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp],
     "vae2_bn_bwd_reduce": [vp, vp, vp, vp, ip, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp],

@@ -69,9 +69,17 @@ class BasicBlock(_Single):
         self.downsample, self.stride = downsample, stride
 
     def emit(self, rec, x, out=None):
-        h = rec.conv_bn(x, self.conv1, self.bn1, relu=True)
-        res = x if self.downsample is None else rec.conv_bn(x, self.downsample[0], self.downsample[1])
-        return rec.conv_bn(h, self.conv2, self.bn2, relu=True, residual=res, out=out)
+        return self.emit_multi(rec, [self], [x], [out])[0]
+
+    @staticmethod
+    def emit_multi(rec, blocks, xs, outs):
+        """The same block position of several independent branches, in lock-step: conv1 of every branch,
+        ONE BN group, conv2 of every branch, ONE BN group (so SyncBN needs one collective per depth)."""
+        hs = rec.conv_bn_multi([dict(x=x, conv=b.conv1, bn=b.bn1, relu=True) for b, x in zip(blocks, xs)])
+        ress = [x if b.downsample is None else rec.conv_bn(x, b.downsample[0], b.downsample[1])
+                for b, x in zip(blocks, xs)]
+        return rec.conv_bn_multi([dict(x=h, conv=b.conv2, bn=b.bn2, relu=True, residual=r, out=o)
+                                  for b, h, r, o in zip(blocks, hs, ress, outs)])
 
 
 class Bottleneck(_Single):
@@ -111,6 +119,20 @@ def _emit_stack(rec, stack, x, out=None):
     for i, blk in enumerate(stack):
         x = blk.emit(rec, x, out=out if i == n - 1 else None)
     return x
+
+
+def _emit_stacks_lockstep(rec, stacks, xs, outs=None):
+    """Independent block stacks (the branches of one HR module) advanced block by block."""
+    if not all(isinstance(b, BasicBlock) for st in stacks for b in st):
+        return [_emit_stack(rec, st, x, outs[i] if outs else None) for i, (st, x) in enumerate(zip(stacks, xs))]
+    cur = list(xs)
+    for k in range(max(len(st) for st in stacks)):
+        act = [b for b in range(len(stacks)) if k < len(stacks[b])]
+        o = [outs[b] if (outs and k == len(stacks[b]) - 1) else None for b in act]
+        res = BasicBlock.emit_multi(rec, [stacks[b][k] for b in act], [cur[b] for b in act], o)
+        for b, r in zip(act, res):
+            cur[b] = r
+    return cur
 
 
 class HighResolutionModule(EngineModule):
@@ -163,23 +185,41 @@ class HighResolutionModule(EngineModule):
         nb = self.num_branches
         if nb == 1:
             return [_emit_stack(rec, self.branches[0], xs[0], out=outs[0] if outs else None)]
-        xs = [_emit_stack(rec, self.branches[b], xs[b]) for b in range(nb)]
-        fused = []
-        for i in range(len(self.fuse_layers)):
-            terms = []
+        xs = _emit_stacks_lockstep(rec, list(self.branches), xs)
+        # fuse convs level by level: level 0 = every 1x1 (j > i) and the first stride-2 step of every
+        # down chain (j < i), level 1 = second steps, ... -- each level is one BN group
+        n_out = len(self.fuse_layers)
+        terms = [[None] * nb for _ in range(n_out)]
+        cur = {}
+        for i in range(n_out):
             for j in range(nb):
                 if j == i:
-                    terms.append(xs[j])
-                elif j > i:
-                    terms.append(rec.conv_bn(xs[j], self.fuse_layers[i][j][0], self.fuse_layers[i][j][1]))
+                    terms[i][j] = xs[j]
+                elif j < i:
+                    cur[(i, j)] = xs[j]
+        level = 0
+        while True:
+            items, keys = [], []
+            for i in range(n_out):
+                for j in range(nb):
+                    if j > i and level == 0:
+                        fl = self.fuse_layers[i][j]
+                        items.append(dict(x=xs[j], conv=fl[0], bn=fl[1], relu=False))
+                        keys.append((i, j, True))
+                    elif j < i and level < len(self.fuse_layers[i][j]):
+                        step = self.fuse_layers[i][j][level]
+                        items.append(dict(x=cur[(i, j)], conv=step[0], bn=step[1], relu=len(step) == 3))
+                        keys.append((i, j, level == len(self.fuse_layers[i][j]) - 1))
+            if not items:
+                break
+            for (i, j, last), t in zip(keys, rec.conv_bn_multi(items)):
+                if last:
+                    terms[i][j] = t
                 else:
-                    t = xs[j]
-                    for step in self.fuse_layers[i][j]:
-                        t = rec.conv_bn(t, step[0], step[1], relu=len(step) == 3)
-                    terms.append(t)
-            # reference sums j = 0..nb-1 in order; fp32 addition order is kept (terms[0] first)
-            fused.append(rec.fuse(terms, xs[i].H, xs[i].W, relu=True, out=outs[i] if outs else None))
-        return fused
+                    cur[(i, j)] = t
+            level += 1
+        # reference sums j = 0..nb-1 in order; fp32 addition order is kept (terms[i][0] first)
+        return [rec.fuse(terms[i], xs[i].H, xs[i].W, relu=True, out=outs[i] if outs else None) for i in range(n_out)]
 
     def _record(self, rec, shapes, needs, tag):
         xs = [rec.input(s[1], s[2], s[3], n) for s, n in zip(shapes, needs)]
@@ -208,19 +248,37 @@ def _transition(pre, cur):
 def _emit_transition(rec, layers, prev, n_pre, outs=None):
     """Existing branches pass through (or get a 3x3 conv when widths differ); new branches are
     stride-2 chains fed from the LAST previous branch (reference forward :796-817)."""
-    res = []
+    res = [None] * len(layers)
+    items, idx, chains = [], [], {}
     for i, layer in enumerate(layers):
         out = outs[i] if outs else None
         if i < n_pre:
             if layer is None:
-                res.append(prev[i] if out is None else rec.copy(prev[i], out))
+                res[i] = prev[i] if out is None else rec.copy(prev[i], out)
             else:
-                res.append(rec.conv_bn(prev[i], layer[0], layer[1], relu=True, out=out))
+                items.append(dict(x=prev[i], conv=layer[0], bn=layer[1], relu=True, out=out))
+                idx.append(i)
         else:
-            t = prev[-1]
-            for j, step in enumerate(layer):
-                t = rec.conv_bn(t, step[0], step[1], relu=True, out=out if j == len(layer) - 1 else None)
-            res.append(t)
+            chains[i] = prev[-1]
+    level = 0
+    while True:      # new branches: stride-2 chains from the last previous branch, advanced level by level
+        for i, t in chains.items():
+            layer = layers[i]
+            if level < len(layer):
+                last = level == len(layer) - 1
+                items.append(dict(x=t, conv=layer[level][0], bn=layer[level][1], relu=True,
+                                  out=(outs[i] if outs else None) if last else None))
+                idx.append(i)
+        if not items:
+            break
+        for i, t in zip(idx, rec.conv_bn_multi(items)):
+            if i < n_pre:
+                res[i] = t
+            else:
+                chains[i] = t
+                res[i] = t
+        items, idx = [], []
+        level += 1
     return res
 
 
@@ -423,8 +481,10 @@ class HighResolutionNetED(HighResolutionNet):
             for b, sl in pending.items():
                 z_dsts[b].append(sl)
             root, sl = rec.concat([3, 3, 3], H, W, name=p + "pred")
+            heads = [getattr(self, "%slast_layer_%d" % (p, h + 1)) for h in range(3)]
+            mids = rec.conv_bn_multi([dict(x=cat, conv=hd[0], bn=hd[1], relu=True) for hd in heads])
             for h in range(3):
-                self._emit_head(rec, getattr(self, "%slast_layer_%d" % (p, h + 1)), cat, out=sl[h])
+                rec.conv(mids[h], heads[h][3], y=sl[h])
             preds.append((root, sl))
         # z inputs fan out into the three nets' concat buffers (enc_hrnet.py:825-826, 885, 943)
         for b in range(4 if coded else 0):
