@@ -71,7 +71,9 @@ typedef struct {
     int32_t Ho, Wo, Cout_p, ldy;
     int32_t k, stride, pad;
 } vae2_conv_geom;
-/* engine: 0 = CUDA-core fp32 FMA (exact fp32), 1 = tcgen05/TMEM/TMA (bf16 operands, dtype must be 1) */
+/* engine: 0 = CUDA-core fp32 FMA (exact fp32), 1 = tcgen05/TMEM/TMA (bf16 operands, dtype must be 1),
+ *         2 = tcgen05 with an exact 3-way bf16 split of every fp32 operand and 6 accumulated products (fp32
+ *             tensors, fp32-level accuracy; forward and dgrad only; w_packed from vae2_pack_weights_tf32) */
 int vae2_conv2d_fwd(const void* x, const void* w_packed, const float* bias, void* y, int dtype,
                     const vae2_conv_geom* g, int engine, vae2_stream_t stream);
 int vae2_conv2d_dgrad(const void* dy, const void* w_packed_t, void* dx, int dtype, const vae2_conv_geom* g,
@@ -82,6 +84,18 @@ int vae2_conv2d_wgrad(const void* x, const void* dy, float* dw_packed, int dtype
 int vae2_bias_grad(const void* dy, float* dbias, int dtype, int64_t npix, int C, int ld, int accumulate,
                    vae2_stream_t stream);
 int vae2_conv2d_tc_supported(const vae2_conv_geom* g);
+/* engine-2 weights: three bf16 planes, [3][tap][Nf][Kf] (forward) and [3][tap][NfT][KfT] (data gradient),
+ * zero-initialised by the caller; dims from vae2_conv2d_tf32_dims */
+typedef struct {
+    const float* w;
+    const int32_t* cin_map;
+    void* fwd;
+    void* bwd;
+    int32_t Cout, Cin, k, Nf, Kf, NfT, KfT, reserved;
+} vae2_tf32_pack_desc;   /* DEVICE array */
+int vae2_conv2d_tf32_supported(const vae2_conv_geom* g);
+void vae2_conv2d_tf32_dims(const vae2_conv_geom* g, int* Nf, int* Kf, int* NfT, int* KfT);
+int vae2_pack_weights_tf32(const vae2_tf32_pack_desc* descs_dev, int n, vae2_stream_t stream);
 /* tensor-core weight gradient (bf16 act, stride 1): dw_packed is OVERWRITTEN; `workspace` holds the split-K
  * partials, at least vae2_conv2d_wgrad_tc_workspace(g) floats (negative = shape unsupported, use engine 0) */
 long long vae2_conv2d_wgrad_tc_workspace(const vae2_conv_geom* g);

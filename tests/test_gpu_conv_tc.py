@@ -115,3 +115,56 @@ def test_conv_tc_many_tiles_persistent():
     N.call.vae2_conv2d_fwd(xa.data_ptr(), wq.data_ptr(), None, ya.data_ptr(), 1, C.byref(g), 1, st())
     torch.cuda.synchronize()
     assert rel_err(from_act(ya, "bf16", B, Cout, H, W, 64), yr) < 6e-3
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_f32x3_fwd_dgrad(case):
+    """The opt-in tensor-core convolution of the fp32 path (engine 2: exact 3-way bf16 split, 6 products) against a
+    float64 convolution.  Operands and products are exact; what remains is the tensor core's TRUNCATING fp32
+    accumulation, one truncation per tcgen05.mma (12 per 32-channel chunk and tap), measured at 1e-6 .. 1.5e-5 per
+    conv -- 100x better than a TF32 pass (~1e-3), 5-70x worse than an fp32 FMA loop (2e-7).  That is why the default
+    fp32 path keeps its convolutions on CUDA cores."""
+    B, Cin, Cout, H, W, k, use_bias, stride = case
+    tag = "t32%s" % (case,)
+    x = O.det_normal(tag + "x", (B, Cin, H, W))
+    w = O.det_normal(tag + "w", (Cout, Cin, k, k), (2.0 / (Cin * k * k)) ** 0.5)
+    bias = O.det_normal(tag + "b", (Cout,), 0.1) if use_bias else None
+    xr = x.double().requires_grad_(True)
+    yr = F.conv2d(xr, w.double(), bias.double() if bias is not None else None, stride=stride, padding=k // 2)
+    gy = O.det_normal(tag + "gy", tuple(yr.shape))
+    yr.backward(gy.double())
+    y32 = F.conv2d(x, w, bias, stride=stride, padding=k // 2)
+    Ho, Wo = yr.shape[-2:]
+    xa, Cin_p = to_act(x, "fp32")
+    Cout_p = pad(Cout, 4)
+    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin_p, ldx=Cin_p, Ho=Ho, Wo=Wo, Cout_p=Cout_p, ldy=Cout_p, k=k, stride=stride, pad=k // 2)
+    assert N.lib().vae2_conv2d_tf32_supported(C.byref(g)) == 1
+    Nf, Kf, NfT, KfT = N.tf32_dims(g)
+    wd = w.contiguous().to(dev())
+    wf = torch.zeros(3 * k * k * Nf * Kf, dtype=torch.bfloat16, device=dev())
+    wb = torch.zeros(3 * k * k * NfT * KfT, dtype=torch.bfloat16, device=dev())
+    d = (N.Tf32PackDesc * 1)()
+    d[0] = N.Tf32PackDesc(w=wd.data_ptr(), fwd=wf.data_ptr(), bwd=wb.data_ptr(), Cout=Cout, Cin=Cin, k=k, Nf=Nf, Kf=Kf, NfT=NfT, KfT=KfT)
+    t = table(d)
+    N.call.vae2_pack_weights_tf32(t.data_ptr(), 1, st())
+    ya = torch.zeros(B * Ho * Wo * Cout_p, dtype=torch.float32, device=dev())
+    bp = None
+    if bias is not None:
+        bp = torch.zeros(Cout_p, dtype=torch.float32, device=dev())
+        bp[:Cout] = bias.to(dev())
+    N.call.vae2_conv2d_fwd(xa.data_ptr(), wf.data_ptr(), bp.data_ptr() if bp is not None else None, ya.data_ptr(), 0,
+                           C.byref(g), 2, st())
+    torch.cuda.synchronize()
+    y = from_act(ya, "fp32", B, Cout, Ho, Wo, Cout_p)
+    e_mine, e_ref = rel_err(y, yr.detach()), rel_err(y32, yr.detach())
+    assert e_mine < 3e-5, "f32x3 fwd err %.2e vs torch-fp32 err %.2e" % (e_mine, e_ref)
+    assert float(ya.view(-1, Cout_p)[:, Cout:].abs().sum()) == 0.0
+    gya, _ = to_act(gy, "fp32", Cout_p)
+    dxa = torch.zeros_like(xa)
+    N.call.vae2_conv2d_dgrad(gya.data_ptr(), wb.data_ptr(), dxa.data_ptr(), 0, C.byref(g), 0, 2, st())
+    torch.cuda.synchronize()
+    dx = from_act(dxa, "fp32", B, Cin, H, W, Cin_p)
+    assert rel_err(dx, xr.grad) < 3e-5, "f32x3 dgrad err %.2e" % rel_err(dx, xr.grad)
+    N.call.vae2_conv2d_dgrad(gya.data_ptr(), wb.data_ptr(), dxa.data_ptr(), 0, C.byref(g), 1, 2, st())
+    torch.cuda.synchronize()
+    assert rel_err(from_act(dxa, "fp32", B, Cin, H, W, Cin_p), 2 * xr.grad) < 3e-5, "f32x3 dgrad accumulate"

@@ -11,6 +11,7 @@ static_assert(sizeof(vae2_fuse_src) == sizeof(FuseSrc), "fuse src ABI");
 static_assert(sizeof(vae2_fuse_dst) == sizeof(FuseDst), "fuse dst ABI");
 static_assert(sizeof(vae2_elbo_seg) == sizeof(ElboSeg), "elbo seg ABI");
 static_assert(sizeof(vae2_elbo_bwd_seg) == sizeof(ElboBwdSeg), "elbo bwd seg ABI");
+static_assert(sizeof(vae2_tf32_pack_desc) == sizeof(Tf32PackDesc), "tf32 pack desc ABI");
 
 static inline cudaStream_t S(vae2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline const ConvGeom& G(const vae2_conv_geom* g) { return *reinterpret_cast<const ConvGeom*>(g); }
@@ -60,6 +61,10 @@ int vae2_conv2d_fwd(const void* x, const void* w_packed, const float* bias, void
         if (dtype != VAE2_DT_BF16) return VAE2_ERR_ARG;
         return conv_fwd_tc(x, w_packed, bias, y, G(g), nullptr, S(stream));
     }
+    if (engine == 2) {
+        if (dtype != VAE2_DT_F32) return VAE2_ERR_ARG;
+        return conv_fwd_tf32(x, w_packed, bias, y, G(g), S(stream));
+    }
     return conv_fwd_simt(x, reinterpret_cast<const float*>(w_packed), bias, y, dtype, G(g), S(stream));
 }
 int vae2_conv2d_dgrad(const void* dy, const void* w_packed_t, void* dx, int dtype, const vae2_conv_geom* g, int accumulate,
@@ -67,6 +72,10 @@ int vae2_conv2d_dgrad(const void* dy, const void* w_packed_t, void* dx, int dtyp
     if (engine == 1) {
         if (dtype != VAE2_DT_BF16) return VAE2_ERR_ARG;
         return conv_dgrad_tc(dy, w_packed_t, dx, G(g), accumulate, S(stream));
+    }
+    if (engine == 2) {
+        if (dtype != VAE2_DT_F32) return VAE2_ERR_ARG;
+        return conv_dgrad_tf32(dy, w_packed_t, dx, G(g), accumulate, S(stream));
     }
     return conv_dgrad_simt(dy, reinterpret_cast<const float*>(w_packed_t), dx, dtype, G(g), accumulate, S(stream));
 }
@@ -80,6 +89,11 @@ int vae2_bias_grad(const void* dy, float* dbias, int dtype, int64_t npix, int C,
     return bias_grad(dy, dbias, dtype, npix, C, ld, accumulate, S(stream));
 }
 int vae2_conv2d_tc_supported(const vae2_conv_geom* g) { return conv_tc_supported(G(g)); }
+int vae2_conv2d_tf32_supported(const vae2_conv_geom* g) { return conv_tf32_supported(G(g)); }
+void vae2_conv2d_tf32_dims(const vae2_conv_geom* g, int* Nf, int* Kf, int* NfT, int* KfT) { conv_tf32_dims(G(g), Nf, Kf, NfT, KfT); }
+int vae2_pack_weights_tf32(const vae2_tf32_pack_desc* d, int n, vae2_stream_t stream) {
+    return pack_weights_tf32(reinterpret_cast<const Tf32PackDesc*>(d), n, S(stream));
+}
 long long vae2_conv2d_wgrad_tc_workspace(const vae2_conv_geom* g) { return conv_wgrad_tc_workspace(G(g)); }
 int vae2_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, float* workspace, const vae2_conv_geom* g,
                          vae2_stream_t stream) {

@@ -1,0 +1,457 @@
+// fp32-accurate convolution on tcgen05 tensor cores: three-way bf16 split ("bf16x3") with fp32 accumulation.
+//
+// The fp32 configuration (BASELINE configs[1]) must stay within 1e-4 of the reference.  A single TF32 pass
+// (~1e-3 per product) cannot do that, and a 2-term TF32 split only represents 22 of the 24 significand bits
+// (measured 4e-6 per conv, 20x the error of an fp32 FMA loop).  Every fp32 operand is therefore split EXACTLY
+// into three bf16 terms,  x = x1 + x2 + x3  (8 + 8 + 8 significand bits), and the product is accumulated as
+//     x1*w1 + x1*w2 + x2*w1 + x2*w2 + x1*w3 + x3*w1          (dropped terms <= 2^-24 relative)
+// in the fp32 TMEM accumulator; bf16 x bf16 products are exact in fp32.  Six bf16 MMAs with K=16 cost the same
+// number of tcgen05.mma instructions as three TF32 MMAs with K=8.  Same implicit GEMM as conv_tc.cu (M tile =
+// TH x TW pixel patch, taps x 32-channel chunks on K, N tile <= 256), different operand plumbing:
+//   * activations stay plain fp32 in HBM; four PRODUCER warps (one pixel row per thread) gather the shifted
+//     pixel's 32 channels with 16-byte loads (bounds / padding by predicate, stride-2 by address), split them
+//     and write three bf16 tiles into shared memory in the 64-byte-swizzled K-major layout the tensor core
+//     reads (fence.proxy.async before the mbarrier arrive);
+//   * weights are split once per step by the pack kernel into three bf16 planes [3][tap][N][K], one TMA per stage;
+//   * one thread issues 6 x 2 tcgen05.mma.kind::f16 (M=128, N=NT, K=16) per stage; epilogue warps read TMEM and
+//     store fp32 (+bias, optional accumulate for the data gradient).
+// Forward and data gradient (stride 1 and 2, 3x3 and 1x1) share the kernel through a tap table, exactly like the
+// bf16 kernel; the weight gradient of the fp32 path stays on conv_simt.cu.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace vae2 {
+namespace t32 {
+
+using namespace tc;
+
+constexpr int kThreads = 320;       // warps 0-3 A producers | 4 MMA issuer | 5 weight TMA | 6-9 epilogue
+constexpr int kMaxStages = 6;
+constexpr int kSmemBudget = 200 * 1024;
+constexpr int KC = 32;              // channels per stage: 32 bf16 = one 64-byte swizzled row
+constexpr int kABytes = 128 * 64;   // one A tile (128 pixel rows x 64 bytes)
+
+struct Params {
+    int B, MH, MW, OH, OW, sO, oh_off, ow_off, sA;
+    int AH, AW, lda, Ck;
+    int Cn, ldo;
+    int taps;
+    signed char tap_dh[9], tap_dw[9], tap_w[9];
+    int kchunks;
+    int NT, n_tiles, TW, TH, tiles_w, tiles_h, total_tiles, stages, tmem_cols, acc_stages, accumulate;
+    const float* a;
+    const float* bias;
+    float* out;
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// x = b1 + b2 + b3 exactly (each residual is exactly representable in fp32)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16& b2, __nv_bfloat16& b3) {
+    b1 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b1);
+    b2 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b2);
+    b3 = __float2bfloat16_rn(r2);
+}
+
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t b_bytes = ((uint32_t)(p.NT * 64) + 1023u) & ~1023u;   // one weight plane tile (NT rows x 64 B)
+    const uint32_t w_tx = 3u * (uint32_t)(p.NT * 64);                    // bytes one weight TMA delivers
+    const uint32_t stage_bytes = 3 * kABytes + ((3u * (uint32_t)(p.NT * 64) + 1023u) & ~1023u);   // [A1][A2][A3][W1 W2 W3]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                       // [stages]  4 producer warps + 1 expect_tx arrive
+    uint64_t* empty = bars + kMaxStages;         // [stages]  tcgen05.commit
+    uint64_t* acc_full = bars + 2 * kMaxStages;  // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int total = p.total_tiles, gstride = gridDim.x, n_tiles = p.n_tiles, nstage = p.stages;
+    const int ntaps = p.taps, kchunks = p.kchunks;
+
+    if (warp < 4) {
+        // ================= A producers: gather + split + swizzled store =================
+        const int row = threadIdx.x;                       // tile row = pixel of the patch
+        const int ri = row / p.TW, rj = row % p.TW;
+        const uint32_t swz = (uint32_t)((row >> 1) & 3);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gstride) {
+            const int pt = tile / n_tiles;
+            const int b = pt / per_img;
+            const int r = pt - b * per_img;
+            const int gi = (r / p.tiles_w) * p.TH + ri, gj = (r % p.tiles_w) * p.TW + rj;
+            const bool in_grid = gi < p.MH && gj < p.MW;
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const int ih = gi * p.sA + p.tap_dh[tap], iw = gj * p.sA + p.tap_dw[tap];
+                const bool ok = in_grid && ih >= 0 && ih < p.AH && iw >= 0 && iw < p.AW;
+                const float* src = p.a + (((long long)b * p.AH + (ok ? ih : 0)) * p.AW + (ok ? iw : 0)) * p.lda;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = kc * KC + j * 4;
+                        v[j] = (ok && c < p.Ck) ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* a1 = smem + (size_t)stage * stage_bytes + (size_t)row * 64;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {          // 16-byte chunk j of the 64-byte row = channels 8j .. 8j+7
+                        const float xs[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w,
+                                             v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+                        uint4 o1, o2, o3;
+                        __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(&o1);
+                        __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(&o2);
+                        __nv_bfloat16* h3 = reinterpret_cast<__nv_bfloat16*>(&o3);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) split3(xs[e], h1[e], h2[e], h3[e]);
+                        const uint32_t off = ((uint32_t)j ^ swz) << 4;     // 64-byte swizzle: chunk ^ ((row >> 1) & 3)
+                        *reinterpret_cast<uint4*>(a1 + off) = o1;
+                        *reinterpret_cast<uint4*>(a1 + kABytes + off) = o2;
+                        *reinterpret_cast<uint4*>(a1 + 2 * kABytes + off) = o3;
+                    }
+                    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[stage]);
+                    if (++stage == nstage) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================= weight TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gstride) {
+                const int nt = tile % n_tiles;
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    const int wt = p.tap_w[tap];
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sb = smem + (size_t)stage * stage_bytes + 3 * kABytes;
+                        mbar_expect_tx(&full[stage], w_tx);
+                        tma_load_4d(sb, &map_w, &full[stage], kc * KC, nt * p.NT, wt, 0);     // box [32 ch][NT][1 tap][3 planes]
+                        if (++stage == nstage) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // D = f32, A = B = bf16, K-major both, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t hi = desc_hi_word(64);
+            const uint32_t lo_flags = 1u << 16;
+            const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | lo_flags;
+            const uint32_t stage_step = stage_bytes >> 4, a_step = kABytes >> 4, w_off = (3 * kABytes) >> 4;
+            const uint32_t w_step = (uint32_t)(p.NT * 64) >> 4;          // planes are packed back to back by the TMA box
+            const int nks = ntaps * kchunks, two_acc = p.acc_stages == 2, NT = p.NT;
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
+                const int as = two_acc ? (it & 1) : 0;
+                const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(&acc_empty[as], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NT);
+                uint32_t accum = 0;
+                for (int ks = 0; ks < nks; ++ks) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a1 = a_lo0 + (uint32_t)stage * stage_step, a2 = a1 + a_step, a3 = a2 + a_step;
+                    const uint32_t w1 = a1 + w_off, w2 = w1 + w_step, w3 = w2 + w_step;
+                    // smallest terms first, x1*w1 last (keeps the tiny products from being absorbed early)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) { umma_bf16_lohi(d_tmem, a3 + 2 * k, hi, w1 + 2 * k, hi, idesc, accum); accum = 1; }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a1 + 2 * k, hi, w3 + 2 * k, hi, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a2 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a2 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a1 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a1 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
+                    umma_commit(&empty[stage]);
+                    if (++stage == nstage) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        // ================= epilogue warps 6..9 (TMEM -> registers -> fp32 global) =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ri = row / p.TW, rj = row % p.TW;
+        const int two_acc = p.acc_stages == 2, NT = p.NT, Cn = p.Cn, accumulate = p.accumulate;
+        const float* bias = p.bias;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
+            const int as = two_acc ? (it & 1) : 0;
+            const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
+            const int nt = tile % n_tiles;
+            const int pt = tile / n_tiles;
+            const int b = pt / per_img;
+            const int r = pt - b * per_img;
+            const int gi = (r / p.tiles_w) * p.TH + ri, gj = (r % p.tiles_w) * p.TW + rj;
+            const bool in_img = gi < p.MH && gj < p.MW;
+            const int h = gi * p.sO + p.oh_off, w = gj * p.sO + p.ow_off;
+            mbar_wait(&acc_full[as], use & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * NT);
+            float* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t0 + c0, v);
+                tmem_ld_wait();
+                const int n = nt * NT + c0;
+                if (in_img) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int nn = n + 4 * i;
+                        if (nn < Cn) {                      // Cn is a multiple of 4
+                            float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                            if (bias != nullptr) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + nn));
+                                f.x += bb.x; f.y += bb.y; f.z += bb.z; f.w += bb.w;
+                            }
+                            float4* dst = reinterpret_cast<float4*>(orow + nn);
+                            if (accumulate) { const float4 o = *dst; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
+                            *dst = f;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- weight split/pack: OIHW fp32 -> three bf16 planes [3][tap][Nf][Kf] (K contiguous, zero padded) -----------
+__global__ void pack_weights_f32x3_kernel(const Tf32PackDesc* __restrict__ descs) {
+    const Tf32PackDesc d = descs[blockIdx.y];
+    const int kk = d.k * d.k;
+    const int total = d.Cout * d.Cin * kk;
+    const long long plane = (long long)kk * d.Nf * d.Kf, planeT = (long long)kk * d.NfT * d.KfT;
+    __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(d.fwd);
+    __nv_bfloat16* bwd = reinterpret_cast<__nv_bfloat16*>(d.bwd);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % kk;
+        const int ci = (i / kk) % d.Cin;
+        const int co = i / (kk * d.Cin);
+        __nv_bfloat16 w1, w2, w3;
+        split3(d.w[i], w1, w2, w3);
+        const int pc = d.cin_map ? d.cin_map[ci] : ci;
+        if (fwd) {        // forward operand: N = output channel, K = physical input lane
+            const long long o = ((long long)tap * d.Nf + co) * d.Kf + pc;
+            fwd[o] = w1; fwd[plane + o] = w2; fwd[2 * plane + o] = w3;
+        }
+        if (bwd) {        // data-gradient operand: N = physical input lane, K = output channel
+            const long long o = ((long long)tap * d.NfT + pc) * d.KfT + co;
+            bwd[o] = w1; bwd[planeT + o] = w2; bwd[2 * planeT + o] = w3;
+        }
+    }
+}
+
+struct Launch {
+    const float* a; int lda, Ck, AH, AW;
+    const void* w; int Nf, Kf, wtaps;           // three bf16 planes [3][wtaps][Nf][Kf]
+    float* out; int ldo, OH, OW, Cn;
+    const float* bias;
+    int B, MH, MW, sO, oh_off, ow_off, sA;
+    int ntaps; signed char dh[9], dw[9], wt[9];
+    int accumulate;
+};
+
+}  // namespace t32
+
+// N tiling shared by the packer (buffer sizes) and the launcher
+static void t32_ntile(int Cn, int* n_tiles, int* NT) {
+    const int npad = (Cn + 15) / 16 * 16;
+    *n_tiles = (npad + 255) / 256;
+    *NT = (((npad + *n_tiles - 1) / *n_tiles) + 15) / 16 * 16;
+}
+
+void conv_tf32_dims(const ConvGeom& g, int* Nf, int* Kf, int* NfT, int* KfT) {
+    int nt, NT;
+    t32_ntile(g.Cout_p, &nt, &NT);
+    *Nf = nt * NT; *Kf = (g.Cin_p + 31) / 32 * 32;
+    t32_ntile(g.Cin_p, &nt, &NT);
+    *NfT = nt * NT; *KfT = (g.Cout_p + 31) / 32 * 32;
+}
+
+int conv_tf32_supported(const ConvGeom& g) {
+    if (!(g.stride == 1 || (g.stride == 2 && g.k == 3))) return 0;
+    if (!(g.k == 1 || g.k == 3)) return 0;
+    if (g.Cin_p % 4 || g.Cout_p % 4 || g.ldx % 4 || g.ldy % 4) return 0;
+    if (g.stride == 1 && (g.H != g.Ho || g.W != g.Wo)) return 0;
+    if (g.stride == 2 && (g.Ho != (g.H + 1) / 2 || g.Wo != (g.W + 1) / 2)) return 0;
+    return 1;
+}
+
+int pack_weights_tf32(const Tf32PackDesc* descs_dev, int n, cudaStream_t st) {
+    if (n <= 0) return VAE2_OK;
+    dim3 grid(8, n);
+    t32::pack_weights_f32x3_kernel<<<grid, 256, 0, st>>>(descs_dev);
+    return check_launch();
+}
+
+typedef CUresult (*EncodeTiledFn32)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn32 enc32() {
+    static EncodeTiledFn32 fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn32>(sym);
+    }
+    return fn;
+}
+
+static int launch_t32(const t32::Launch& L, cudaStream_t st) {
+    using namespace t32;
+    EncodeTiledFn32 enc = enc32();
+    if (enc == nullptr) return VAE2_ERR_UNSUPPORTED;
+    if (L.MH <= 0 || L.MW <= 0) return VAE2_OK;
+    Params p;
+    p.B = L.B; p.MH = L.MH; p.MW = L.MW; p.OH = L.OH; p.OW = L.OW;
+    p.sO = L.sO; p.oh_off = L.oh_off; p.ow_off = L.ow_off; p.sA = L.sA;
+    p.AH = L.AH; p.AW = L.AW; p.lda = L.lda; p.Ck = L.Ck;
+    p.Cn = L.Cn; p.ldo = L.ldo;
+    p.taps = L.ntaps;
+    for (int i = 0; i < 9; ++i) { p.tap_dh[i] = L.dh[i]; p.tap_dw[i] = L.dw[i]; p.tap_w[i] = L.wt[i]; }
+    p.kchunks = L.Kf / KC;
+    t32_ntile(L.Cn, &p.n_tiles, &p.NT);
+    if (p.n_tiles * p.NT != L.Nf) return VAE2_ERR_ARG;
+    int tw = 128;
+    while (tw > 8 && tw / 2 >= L.MW) tw >>= 1;
+    p.TW = tw; p.TH = 128 / tw;
+    p.tiles_w = (L.MW + p.TW - 1) / p.TW;
+    p.tiles_h = (L.MH + p.TH - 1) / p.TH;
+    p.total_tiles = L.B * p.tiles_w * p.tiles_h * p.n_tiles;
+    const int stage_bytes = 3 * kABytes + (3 * p.NT * 64 + 1023) / 1024 * 1024;
+    int stages = kSmemBudget / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return VAE2_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.acc_stages = (2 * p.NT <= 512) ? 2 : 1;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.acc_stages * p.NT) p.tmem_cols <<= 1;
+    p.accumulate = L.accumulate;
+    p.a = L.a; p.bias = L.bias; p.out = L.out;
+
+    CUtensorMap map_w;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)L.Kf, (cuuint64_t)L.Nf, (cuuint64_t)L.wtaps, 3};
+        cuuint64_t strides[3] = {(cuuint64_t)L.Kf * 2, (cuuint64_t)L.Nf * L.Kf * 2, (cuuint64_t)L.wtaps * L.Nf * L.Kf * 2};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)p.NT, 1, 3};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(L.w), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return VAE2_ERR_ARG;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_f32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return VAE2_ERR_CUDA;
+        attr_set = true;
+    }
+    int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    conv_f32x3_kernel<<<grid, kThreads, smem, st>>>(map_w, p);
+    return check_launch();
+}
+
+// w_fwd: bf16 planes [3][tap][Nf][Kf] as produced by pack_weights_tf32 (fwd operand)
+int conv_fwd_tf32(const void* x, const void* w_fwd, const float* bias, void* y, const ConvGeom& g, cudaStream_t st) {
+    if (!conv_tf32_supported(g)) return VAE2_ERR_UNSUPPORTED;
+    int Nf, Kf, NfT, KfT;
+    conv_tf32_dims(g, &Nf, &Kf, &NfT, &KfT);
+    t32::Launch L{};
+    L.a = (const float*)x; L.lda = g.ldx; L.Ck = g.Cin_p; L.AH = g.H; L.AW = g.W;
+    L.w = w_fwd; L.Nf = Nf; L.Kf = Kf; L.wtaps = g.k * g.k;
+    L.out = (float*)y; L.ldo = g.ldy; L.OH = g.Ho; L.OW = g.Wo; L.Cn = g.Cout_p; L.bias = bias;
+    L.B = g.B; L.MH = g.Ho; L.MW = g.Wo; L.sO = 1; L.oh_off = 0; L.ow_off = 0; L.sA = g.stride;
+    L.ntaps = g.k * g.k;
+    for (int t = 0; t < L.ntaps; ++t) { L.dh[t] = (signed char)(t / g.k - g.pad); L.dw[t] = (signed char)(t % g.k - g.pad); L.wt[t] = (signed char)t; }
+    L.accumulate = 0;
+    return launch_t32(L, st);
+}
+
+// w_bwd: bf16 planes [3][tap][NfT][KfT] (data-gradient operand).  Stride 2 -> four output parity classes (see conv_tc.cu).
+int conv_dgrad_tf32(const void* dy, const void* w_bwd, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st) {
+    if (!conv_tf32_supported(g)) return VAE2_ERR_UNSUPPORTED;
+    int Nf, Kf, NfT, KfT;
+    conv_tf32_dims(g, &Nf, &Kf, &NfT, &KfT);
+    t32::Launch L{};
+    L.a = (const float*)dy; L.lda = g.ldy; L.Ck = g.Cout_p; L.AH = g.Ho; L.AW = g.Wo;
+    L.w = w_bwd; L.Nf = NfT; L.Kf = KfT; L.wtaps = g.k * g.k;
+    L.out = (float*)dx; L.ldo = g.ldx; L.OH = g.H; L.OW = g.W; L.Cn = g.Cin_p; L.bias = nullptr;
+    L.B = g.B; L.sA = 1; L.accumulate = accumulate;
+    if (g.stride == 1) {
+        L.MH = g.H; L.MW = g.W; L.sO = 1; L.oh_off = 0; L.ow_off = 0;
+        L.ntaps = g.k * g.k;
+        for (int t = 0; t < L.ntaps; ++t) { L.dh[t] = (signed char)(g.pad - t / g.k); L.dw[t] = (signed char)(g.pad - t % g.k); L.wt[t] = (signed char)t; }
+        return launch_t32(L, st);
+    }
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            L.MH = (g.H - ph + 1) / 2; L.MW = (g.W - pw + 1) / 2;
+            L.sO = 2; L.oh_off = ph; L.ow_off = pw;
+            int n = 0;
+            for (int ky = 0; ky < 3; ++ky) {
+                if (((ph + 1 - ky) & 1) != 0) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    if (((pw + 1 - kx) & 1) != 0) continue;
+                    L.dh[n] = (signed char)((ph + 1 - ky) / 2); L.dw[n] = (signed char)((pw + 1 - kx) / 2);
+                    L.wt[n] = (signed char)(ky * 3 + kx);
+                    ++n;
+                }
+            }
+            L.ntaps = n;
+            if (int e = launch_t32(L, st)) return e;
+        }
+    return VAE2_OK;
+}
+
+}  // namespace vae2

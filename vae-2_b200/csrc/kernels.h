@@ -117,4 +117,18 @@ long long conv_wgrad_tc_workspace(const ConvGeom& g);
 int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const ConvGeom& g, cudaStream_t st);
 int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st);
 
+// conv_f32x3.cu (fp32-accurate tcgen05 convolution by an exact 3-way bf16 split: forward and data gradient of the fp32 path)
+struct Tf32PackDesc {
+    const float* w;        // OIHW fp32 parameter
+    const int* cin_map;    // logical input channel -> physical lane, null = identity
+    void* fwd;             // bf16 planes [3][tap][Nf][Kf], or null
+    void* bwd;             // bf16 planes [3][tap][NfT][KfT], or null
+    int Cout, Cin, k, Nf, Kf, NfT, KfT, _pad;
+};
+int conv_tf32_supported(const ConvGeom& g);
+void conv_tf32_dims(const ConvGeom& g, int* Nf, int* Kf, int* NfT, int* KfT);
+int pack_weights_tf32(const Tf32PackDesc* descs_dev, int n, cudaStream_t st);
+int conv_fwd_tf32(const void* x, const void* w_fwd, const float* bias, void* y, const ConvGeom& g, cudaStream_t st);
+int conv_dgrad_tf32(const void* dy, const void* w_bwd, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st);
+
 }  // namespace vae2

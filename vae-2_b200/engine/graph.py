@@ -156,6 +156,7 @@ class Plan:
         self._garena, self._goff = None, 0
         self.all_acts = []
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
+        self.fp32_tc = os.environ.get("VAE2_FP32_TC", "0") == "1"
         self.use_tc_wgrad = os.environ.get("VAE2_DISABLE_TC_WGRAD", "0") != "1"
         self.graph_fwd = self.graph_bwd = None
         self.n_launch_fwd = self.n_launch_bwd = 0
@@ -214,11 +215,41 @@ class Plan:
         for o in convs:
             o.w_off = tot
             tot += pad_to(o.taps * o.x.root_cp() * o.y.Cp, 4)
-        # tensor-core eligibility (bf16 path, stride-1 convs): decided once per conv at plan build
+        # tensor-core eligibility: decided once per conv at plan build
         if self.prec.code == 1 and dev.type == "cuda" and self.use_tc:
             for o in convs:
                 g = o._geom()
                 o.engine = 1 if N.lib().vae2_conv2d_tc_supported(C.byref(g)) else 0
+        # fp32 storage with the fwd/dgrad GEMMs on tensor cores through the exact 3-way bf16 split (opt-in:
+        # its truncating fp32 accumulation is ~1e-6..1e-5 per conv)
+        x3 = [o for o in convs if self.prec.code == 0 and self.fp32_tc and dev.type == "cuda"
+              and N.lib().vae2_conv2d_tf32_supported(C.byref(o._geom()))]
+        tot3f = tot3b = 0
+        for o in x3:
+            o.engine = 2
+            o.x3dims = N.tf32_dims(o._geom())
+            Nf, Kf, NfT, KfT = o.x3dims
+            o.x3_foff, o.x3_boff = tot3f, tot3b
+            tot3f += pad_to(3 * o.taps * Nf * Kf, 8)
+            tot3b += pad_to(3 * o.taps * NfT * KfT, 8)
+        self.w3f_flat = torch.zeros(max(tot3f, 8), dtype=torch.bfloat16, device=dev) if x3 else None
+        self.w3b_flat = torch.zeros(max(tot3b, 8), dtype=torch.bfloat16, device=dev) if (x3 and self.training) else None
+        if x3:
+            t3 = (N.Tf32PackDesc * len(x3))()
+            for i, o in enumerate(x3):
+                w = o.conv.weight
+                cm = None
+                if o.x.cin_map is not None:
+                    t = torch.tensor(o.x.cin_map, dtype=torch.int32, device=dev)
+                    self.keep.append(t)
+                    cm = t.data_ptr()
+                Nf, Kf, NfT, KfT = o.x3dims
+                t3[i] = N.Tf32PackDesc(w=w.data_ptr(), cin_map=cm, fwd=self.w3f_flat.data_ptr() + 2 * o.x3_foff,
+                                       bwd=(self.w3b_flat.data_ptr() + 2 * o.x3_boff) if self.training else None,
+                                       Cout=w.shape[0], Cin=w.shape[1], k=w.shape[2], Nf=Nf, Kf=Kf, NfT=NfT, KfT=KfT)
+            self.t3_dev = torch.frombuffer(bytearray(bytes(t3)), dtype=torch.uint8).to(dev)
+            n3 = len(x3)
+            self.fwd.append(lambda st: N.call.vae2_pack_weights_tf32(self.t3_dev.data_ptr(), n3, st))
         self.n_tc_convs = sum(o.engine for o in convs)
         # shared split-K workspace of the tensor-core weight gradient (convs run one after another)
         ws_floats = 0
@@ -478,6 +509,8 @@ class ConvOp:
         plan.keep.append(g)
         x, y = self.x, self.y
         wp = (plan.wq_flat.data_ptr() + 2 * self.w_off) if self.engine == 1 else (plan.wp_flat.data_ptr() + 4 * self.w_off)
+        if self.engine == 2:
+            wp = plan.w3f_flat.data_ptr() + 2 * self.x3_foff
         bias = None
         if self.conv.bias is not None:
             # bias padded to Cout_p lanes (pad = 0); refreshed from the parameter every forward
@@ -512,6 +545,8 @@ class ConvOp:
         if x.needs_grad:
             eng = self.engine
             wpT = (plan.wqT_flat.data_ptr() + 2 * self.w_off) if eng == 1 else (plan.wpT_flat.data_ptr() + 4 * self.w_off)
+            if eng == 2:
+                wpT = plan.w3b_flat.data_ptr() + 2 * self.x3_boff
             acc = x.take_acc_flag()
             dxp = x.grad().ptr
             plan.bwd.append(lambda st: N.call.vae2_conv2d_dgrad(dyp, wpT, dxp, pr.code, gp, acc, eng, st))

@@ -25,6 +25,12 @@ class PackDesc(C.Structure):
                 ("Cout_p", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Tf32PackDesc(C.Structure):
+    _fields_ = [("w", vp), ("cin_map", vp), ("fwd", vp), ("bwd", vp),
+                ("Cout", C.c_int32), ("Cin", C.c_int32), ("k", C.c_int32), ("Nf", C.c_int32), ("Kf", C.c_int32),
+                ("NfT", C.c_int32), ("KfT", C.c_int32), ("reserved", C.c_int32)]
+
+
 class FuseSrc(C.Structure):
     _fields_ = [("ptr", vp), ("H", C.c_int32), ("W", C.c_int32), ("ld", C.c_int32)]
 
@@ -53,6 +59,7 @@ _PROTOS = {
     "vae2_code_broadcast": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "vae2_pack_weights": [vp, i32, vp],
     "vae2_unpack_wgrad": [vp, i32, i32, vp],
+    "vae2_pack_weights_tf32": [vp, i32, vp],
     "vae2_conv2d_fwd": [vp, vp, vp, vp, i32, C.POINTER(ConvGeom), i32, vp],
     "vae2_conv2d_dgrad": [vp, vp, vp, i32, C.POINTER(ConvGeom), i32, i32, vp],
     "vae2_conv2d_wgrad": [vp, vp, vp, i32, C.POINTER(ConvGeom), i32, vp],
@@ -78,10 +85,10 @@ _PROTOS = {
     "vae2_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, f32, vp],
 }
 _PLAIN_INT = {"vae2_abi_version": [], "vae2_bn_max_partials": [], "vae2_elbo_acc_floats": [],
-              "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)]}
+              "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)], "vae2_conv2d_tf32_supported": [C.POINTER(ConvGeom)]}
 
 EXPORTS = sorted(set(_PROTOS) | set(_PLAIN_INT) | {"vae2_status_string", "vae2_last_cuda_error",
-                                                     "vae2_conv2d_wgrad_tc_workspace"})
+                                                     "vae2_conv2d_wgrad_tc_workspace", "vae2_conv2d_tf32_dims"})
 
 _lib = None
 
@@ -105,12 +112,21 @@ def lib():
             fn.restype = C.c_int
         h.vae2_conv2d_wgrad_tc_workspace.argtypes = [C.POINTER(ConvGeom)]
         h.vae2_conv2d_wgrad_tc_workspace.restype = C.c_longlong
+        h.vae2_conv2d_tf32_dims.argtypes = [C.POINTER(ConvGeom), ip, ip, ip, ip]
+        h.vae2_conv2d_tf32_dims.restype = None
         h.vae2_status_string.argtypes = [C.c_int]
         h.vae2_status_string.restype = C.c_char_p
         h.vae2_last_cuda_error.argtypes = []
         h.vae2_last_cuda_error.restype = C.c_char_p
         _lib = h
     return _lib
+
+
+def tf32_dims(geom):
+    """(Nf, Kf, NfT, KfT): padded operand extents of the 3xTF32 weight planes for this conv."""
+    a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    lib().vae2_conv2d_tf32_dims(C.byref(geom), C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    return a.value, b.value, c.value, d.value
 
 
 def check(status, what):
