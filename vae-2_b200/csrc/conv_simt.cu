@@ -102,10 +102,13 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
         const int IW = (MODE == MODE_FWD) ? g.W : g.Wo;
         const int lda = (MODE == MODE_FWD) ? g.ldx : g.ldy;
 
-        for (int tap = 0; tap < taps; ++tap) {
+        // Software pipeline: the global loads of chunk i+1 are issued (into registers) before the FMAs of chunk i,
+        // so their latency overlaps the math; shared memory is single-buffered (store after the compute barrier).
+        const TA* a_ptr[A_PER_T];
+        float4 ar[A_PER_T];
+        float4 br;
+        auto resolve_tap = [&](int tap) {
             const int ky = tap / g.k, kx = tap - ky * g.k;
-            // resolve the gathered pixel for each of this thread's rows under this tap
-            const TA* a_ptr[A_PER_T];
 #pragma unroll
             for (int j = 0; j < A_PER_T; ++j) {
                 int ih, iw;
@@ -122,44 +125,65 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
                 ok = ok && ih >= 0 && ih < IH && iw >= 0 && iw < IW;
                 a_ptr[j] = ok ? Asrc + (((long long)a_n[j] * IH + ih) * IW + iw) * lda : nullptr;
             }
-            for (int kc = 0; kc < Cch; kc += BK) {
-                float4 ar[A_PER_T];
+        };
+        auto gload = [&](int tap, int kc) {
 #pragma unroll
-                for (int j = 0; j < A_PER_T; ++j) {
-                    const int c = kc + a_kq;
-                    ar[j] = (a_ptr[j] != nullptr && c < Cch) ? load4<TA>(a_ptr[j] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float4 br = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b_active && kc + b_row < Cch && n0 + b_col < N)
-                    br = *reinterpret_cast<const float4*>(Bw + ((long long)tap * Cch + kc + b_row) * ldb + n0 + b_col);
-                __syncthreads();
+            for (int j = 0; j < A_PER_T; ++j) {
+                const int c = kc + a_kq;
+                ar[j] = (a_ptr[j] != nullptr && c < Cch) ? load4<TA>(a_ptr[j] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            br = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b_active && kc + b_row < Cch && n0 + b_col < N)
+                br = *reinterpret_cast<const float4*>(Bw + ((long long)tap * Cch + kc + b_row) * ldb + n0 + b_col);
+        };
+        auto sstore = [&]() {
 #pragma unroll
-                for (int j = 0; j < A_PER_T; ++j) {
-                    const int r = (tid + j * NTHREADS) / 4;
-                    As[a_kq + 0][r] = ar[j].x; As[a_kq + 1][r] = ar[j].y;
-                    As[a_kq + 2][r] = ar[j].z; As[a_kq + 3][r] = ar[j].w;
-                }
-                if (b_active) *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = br;
-                __syncthreads();
-                // only the channels that exist in this chunk (Cch is a multiple of 4): an 18->20-lane
-                // tensor costs 20 k-steps per tap, not 32
-                const int kmax = (Cch - kc) < BK ? (Cch - kc) : BK;
-                for (int k4 = 0; k4 < kmax; k4 += 4) {
+            for (int j = 0; j < A_PER_T; ++j) {
+                const int r = (tid + j * NTHREADS) / 4;
+                As[a_kq + 0][r] = ar[j].x; As[a_kq + 1][r] = ar[j].y;
+                As[a_kq + 2][r] = ar[j].z; As[a_kq + 3][r] = ar[j].w;
+            }
+            if (b_active) *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = br;
+        };
+        const int nkc = (Cch + BK - 1) / BK;
+        const int n_iter = taps * nkc;
+        int tap = 0, kc = 0;
+        resolve_tap(0);
+        gload(0, 0);
+        sstore();
+        __syncthreads();
+        for (int it = 0; it < n_iter; ++it) {
+            int ntap = tap, nkcv = kc + BK;
+            if (nkcv >= Cch) { nkcv = 0; ntap = tap + 1; }
+            const bool has_next = it + 1 < n_iter;
+            if (has_next) {
+                if (ntap != tap) resolve_tap(ntap);
+                gload(ntap, nkcv);
+            }
+            // only the channels that exist in this chunk (Cch is a multiple of 4): an 18->20-lane
+            // tensor costs 20 k-steps per tap, not 32
+            const int kmax = (Cch - kc) < BK ? (Cch - kc) : BK;
+            for (int k4 = 0; k4 < kmax; k4 += 4) {
 #pragma unroll
-                    for (int kq = 0; kq < 4; ++kq) {
-                        const int kk = k4 + kq;
-                        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
-                        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
-                        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
-                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        const float bv[4] = {b.x, b.y, b.z, b.w};
+                for (int kq = 0; kq < 4; ++kq) {
+                    const int kk = k4 + kq;
+                    const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
+                    const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                        for (int i = 0; i < TM; ++i)
+                    for (int i = 0; i < TM; ++i)
 #pragma unroll
-                            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-                    }
+                        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
                 }
             }
+            __syncthreads();
+            if (has_next) {
+                sstore();
+                __syncthreads();
+            }
+            tap = ntap; kc = nkcv;
         }
         // ---- epilogue: rows are output pixels ----
         TA* out = reinterpret_cast<TA*>(Cdst);
@@ -205,8 +229,9 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
             a_tap_ky[j] = tap / g.k;
             a_tap_kx[j] = tap - a_tap_ky[j] * g.k;
         }
-        for (long long k0 = k_begin; k0 < k_end; k0 += BK) {
-            float4 ar[A_PER_T];
+        float4 ar[A_PER_T];
+        float4 br;
+        auto gload = [&](long long k0) {
 #pragma unroll
             for (int j = 0; j < A_PER_T; ++j) {
                 const long long p = k0 + a_kk[j];
@@ -222,15 +247,24 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
                         ar[j] = load4<TA>(Asrc + (((long long)nb * g.H + ih) * g.W + iw) * g.ldx + a_ci[j]);
                 }
             }
-            float4 br = make_float4(0.f, 0.f, 0.f, 0.f);
+            br = make_float4(0.f, 0.f, 0.f, 0.f);
             if (b_active && k0 + b_row < k_end && n0 + b_col < N)
                 br = load4<TA>(Bd + (k0 + b_row) * g.ldy + n0 + b_col);
-            __syncthreads();
+        };
+        auto sstore = [&]() {
 #pragma unroll
             for (int j = 0; j < A_PER_T; ++j)
                 *reinterpret_cast<float4*>(&As[a_kk[j]][a_mq[j] * 4]) = ar[j];
             if (b_active) *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = br;
-            __syncthreads();
+        };
+        if (k_begin < k_end) {
+            gload(k_begin);
+            sstore();
+        }
+        __syncthreads();
+        for (long long k0 = k_begin; k0 < k_end; k0 += BK) {
+            const bool has_next = k0 + BK < k_end;
+            if (has_next) gload(k0 + BK);       // in flight during the FMAs below
 #pragma unroll
             for (int kk = 0; kk < BK; ++kk) {
                 const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
@@ -242,6 +276,11 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
                     for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+            if (has_next) {
+                sstore();
+                __syncthreads();
             }
         }
         float* out = reinterpret_cast<float*>(Cdst);  // dwp [M][N]
