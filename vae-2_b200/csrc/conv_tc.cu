@@ -21,6 +21,7 @@
 //     (tcgen05.ld 32 lanes x 16 columns -> +bias -> bf16 -> 32-byte global stores, one pixel row
 //     per thread).  Persistent CTAs (one per SM) walk the tile list.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -60,7 +61,7 @@ struct Params {
     __nv_bfloat16* out;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 4)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][A tile | B tile] (1024-aligned), then barriers
@@ -522,11 +523,19 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
     const int row_bytes = p.KC * 2;
     const int a_bytes = 128 * row_bytes;
     const int b_bytes = ((p.NT * row_bytes + 1023) / 1024) * 1024;
-    int stages = kSmemBudget / (a_bytes + b_bytes);
+    // Two co-resident CTAs per SM (each with half the shared memory and <= 256 TMEM columns) when the tiles are
+    // small: tcgen05.mma issue costs the issuing thread ~110 cycles regardless of N, so narrow-N convs are
+    // issue-bound and a second, independent issuer per SM doubles their throughput.
+    int ctas = 1;
+    if (p.NT <= 32 && 4 * (a_bytes + b_bytes) + 2048 <= kSmemBudget / 4) ctas = 4;
+    else if (p.NT <= 128 && 4 * (a_bytes + b_bytes) + 2048 <= kSmemBudget / 2) ctas = 2;
+    if (const char* e = getenv("VAE2_TC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < ctas) ctas = v; }
+    const int budget = kSmemBudget / ctas;
+    int stages = budget / (a_bytes + b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return VAE2_ERR_UNSUPPORTED;
     p.stages = stages;
-    p.acc_stages = (2 * p.NT <= 512) ? 2 : 1;
+    p.acc_stages = (2 * p.NT <= 512 / ctas) ? 2 : 1;
     p.tmem_cols = next_pow2_cols(p.acc_stages * p.NT);
     p.accumulate = L.accumulate;
     p.bias = L.bias;
@@ -561,7 +570,7 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
             return VAE2_ERR_CUDA;
         attr_set = true;
     }
-    int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    int grid = p.total_tiles < ctas * kNumSMs ? p.total_tiles : ctas * kNumSMs;
     conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_w, p);
     return check_launch();
 }
