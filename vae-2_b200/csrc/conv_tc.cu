@@ -224,7 +224,18 @@ static CUtensorMapSwizzle swz(int kc) {
     return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-static int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+// K chunk (channels per pipeline stage).  A stage costs the single issuing thread ~300 cycles of barrier
+// wait / fence / commit plus ~110 cycles per tcgen05.mma (measured), so fewer, fatter stages win even when
+// the last chunk is partly empty: TMA zero-fills the channels beyond the tensor's extent for free.
+static int pick_kc(int c) {
+    int best = 16, best_cost = 1 << 30;
+    for (int kc = 16; kc <= 64; kc *= 2) {
+        if (kc > 16 && c <= kc / 2) break;
+        const int cost = ((c + kc - 1) / kc) * (300 + (kc / 16) * 110);
+        if (cost < best_cost) { best_cost = cost; best = kc; }
+    }
+    return best;
+}
 
 static int next_pow2_cols(int n) {
     int c = 32;
@@ -511,7 +522,7 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
     p.taps = L.ntaps;
     for (int i = 0; i < 9; ++i) { p.tap_dh[i] = L.dh[i]; p.tap_dw[i] = L.dw[i]; p.tap_w[i] = L.wt[i]; }
     p.KC = pick_kc(L.Ck);
-    p.kchunks = L.Ck / p.KC;
+    p.kchunks = (L.Ck + p.KC - 1) / p.KC;
     p.n_tiles = (L.Cn + 255) / 256;
     p.NT = (((L.Cn + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
     int tw = 128;
