@@ -429,7 +429,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 static int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
 // Fills p (everything except ws) and returns the workspace size in floats; <0 if unsupported.
+static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages);
+
+// 64 pixels per stage when that still leaves a 3-deep pipeline, else 32
 static long long plan_wgrad(const ConvGeom& g, WParams& p) {
+    int first = 64;
+    if (const char* e = getenv("VAE2_WGRAD_KP")) { const int v = atoi(e); if (v == 32) first = 32; }
+    if (first == 64) {
+        const long long r = plan_wgrad_kp(g, p, 64, 3);
+        if (r >= 0) return r;
+    }
+    return plan_wgrad_kp(g, p, 32, 2);
+}
+
+static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages) {
     // K runs over OUTPUT pixels (Ho x Wo); x is sampled at stride g.stride
     p.B = g.B; p.H = g.Ho; p.W = g.Wo; p.sA = g.stride;
     p.n_tiles = (g.Cout_p + 255) / 256;
@@ -437,45 +450,45 @@ static long long plan_wgrad(const ConvGeom& g, WParams& p) {
     p.NT = (((g.Cout_p + p.n_tiles - 1) / p.n_tiles) + p.atomB - 1) / p.atomB * p.atomB;
     p.Cin_p = g.Cin_p; p.Cout_p = g.Cout_p; p.ksz = g.k; p.taps = g.k * g.k; p.pad = g.k / 2;
     p.atomA = pick_atom(g.Cin_p);
-    int tw = 32;
+    // pixels per stage: 64 halves the number of stages (each costs the issuing thread ~300 cycles of barrier
+    // traffic on top of its MMAs); 32 when the operands are too wide for two 64-pixel stages in shared memory
+    int tw = kp;
     while (tw > 8 && tw / 2 >= p.W) tw >>= 1;
-    p.TW = tw; p.TH = 32 / tw; p.KP = 32;
+    p.TW = tw; p.TH = kp / tw; p.KP = kp;
     p.tiles_w = (p.W + p.TW - 1) / p.TW;
     p.tiles_h = (p.H + p.TH - 1) / p.TH;
     p.total_ptiles = g.B * p.tiles_w * p.tiles_h;
     p.M_total = p.taps * g.Cin_p;
     const int groups_total = (p.M_total + 127) / 128;
-    int sg = 512 / p.NT;
-    if (sg > groups_total) sg = groups_total;
-    // shared-memory cap: a set of sg groups stages ~(sg*128 + 2*Cin_p) rows of KP*2 bytes of x per stage; keep
-    // that near 60 KB so that >= 3 pipeline stages fit (wide Cin, e.g. the 256-channel transition convs)
-    int sg_cap = (60 * 1024 - 128 * g.Cin_p) / 8192;
-    if (sg_cap < 1) sg_cap = 1;
-    if (sg > sg_cap) sg = sg_cap;
-    // keep the per-stage A footprint bounded: a set never needs more than (sg*128/Cin_p + 2) taps
+    // groups per CTA ("set"): as many as TMEM holds (512 columns), shrunk until the stage ring is deep enough
+    const int nchunkA = g.Cin_p / p.atomA;
+    int sg_max = 512 / p.NT;
+    if (sg_max > groups_total) sg_max = groups_total;
+    int sg = 0, stages = 0, worst = 0;
+    for (int cand = sg_max; cand >= 1; --cand) {
+        const int nsets = (groups_total + cand - 1) / cand;
+        int w = 0;                      // A atoms per stage: worst case over the sets (whole taps, whole groups)
+        for (int s_ = 0; s_ < nsets; ++s_) {
+            const int m_lo = s_ * cand * 128;
+            const int m_hi = (s_ + 1) * cand * 128;
+            const int m_hi_real = m_hi < p.M_total ? m_hi : p.M_total;
+            const int t0 = m_lo / g.Cin_p, t1 = (m_hi_real - 1) / g.Cin_p;
+            int atoms = (t1 - t0 + 1) * nchunkA;
+            const int need = (m_hi - t0 * g.Cin_p + p.atomA - 1) / p.atomA;   // group rows may overhang the loaded taps
+            if (need > atoms) atoms = need;
+            if (atoms > w) w = atoms;
+        }
+        const long long a_b = (long long)w * p.KP * p.atomA * 2, b_b = (long long)p.NT * p.KP * 2;
+        const long long sb = ((a_b + b_b + 1023) / 1024) * 1024;
+        int st_ = (int)(kSmemBudget / sb);
+        if (st_ > kMaxStages) st_ = kMaxStages;
+        if (st_ >= min_stages) { sg = cand; stages = st_; worst = w; break; }
+    }
+    if (sg == 0) return -1;
     p.set_groups = sg;
     p.nsets = (groups_total + sg - 1) / sg;
     p.tmem_cols = next_pow2_cols(sg * p.NT);
-    // A atoms per stage: worst case over sets of (taps touched * chunks), and at least enough to cover whole groups
-    const int nchunkA = g.Cin_p / p.atomA;
-    int worst = 0;
-    for (int s = 0; s < p.nsets; ++s) {
-        const int m_lo = s * sg * 128;
-        int m_hi = (s + 1) * sg * 128;
-        const int m_hi_real = m_hi < p.M_total ? m_hi : p.M_total;
-        const int t0 = m_lo / g.Cin_p, t1 = (m_hi_real - 1) / g.Cin_p;
-        int atoms = (t1 - t0 + 1) * nchunkA;
-        const int need = (m_hi - t0 * g.Cin_p + p.atomA - 1) / p.atomA;   // group rows may overhang the loaded taps
-        if (need > atoms) atoms = need;
-        if (atoms > worst) worst = atoms;
-    }
     p.a_atoms_stage = worst;
-    const long long a_bytes = (long long)worst * p.KP * p.atomA * 2;
-    const long long b_bytes = (long long)p.NT * p.KP * 2;
-    const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
-    int stages = (int)(kSmemBudget / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return -1;
     p.stages = stages;
     int nranges = kNumSMs / (p.nsets * p.n_tiles);
     if (nranges < 1) nranges = 1;
