@@ -134,6 +134,21 @@ int vae2_bn_bwd_elemt(const void* g, const void* a, const void* y, void* dy, voi
                       int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
                       const float* invstd, const float* scale, const float* c1, const float* c2, int relu,
                       int acc_dy, int acc_dres, vae2_stream_t stream);
+/* Single-rank training BN in ONE cooperative launch per direction (statistics | grid barrier | finalize |
+ * grid barrier | elementwise).  Same results as stats+finalize+apply resp. bwd_reduce+bwd_finalize+bwd_coeffs+
+ * bwd_elemt above; `partials` is scratch of vae2_bn_max_partials()*3*Cp floats.  SyncBN keeps the split entry
+ * points because its collective sits between the phases.  bwd `relu`: 0 none, 1 mask read from the stored
+ * activation `a`, 2 mask recomputed as fma(y, scale, shift) > 0 (BN+ReLU without a residual: `a` is not read). */
+int vae2_bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int dtype, int64_t npix, int C,
+                      int Cp, int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                      float eps, float* mean, float* invstd, float* scale, float* shift, int relu,
+                      vae2_stream_t stream);
+int vae2_bn_bwd_fused(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                      int64_t npix, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres,
+                      const float* mean, const float* invstd, const float* scale, const float* shift, float* dgamma,
+                      float* dbeta, int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres,
+                      vae2_stream_t stream);
 
 /* ---- branch fusion / upsampling: HighResolutionModule.forward enc_hrnet.py:233-248, :833-839 -- */
 typedef struct { const void* ptr; int32_t H, W, ld; } vae2_fuse_src;        /* HOST array */

@@ -175,10 +175,12 @@ def test_conv_concat_channel_map():
     assert rel_err(from_act(ya, "fp32", B, 18, H, W, Cout_p), yr) < 2e-5
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["split", "fused"])
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape,relu,with_res", [((2, 18, 17, 23), True, True), ((1, 64, 32, 64), True, False),
-                                                   ((3, 270, 5, 7), False, False), ((2, 8, 64, 64), True, True)])
-def test_batchnorm_train_fwd_bwd(shape, relu, with_res, prec):
+                                                   ((3, 270, 5, 7), False, False), ((2, 8, 64, 64), True, True),
+                                                   ((4, 36, 96, 160), True, True), ((1, 20, 3, 5), False, False)])
+def test_batchnorm_train_fwd_bwd(shape, relu, with_res, prec, fused):
     code, tdt, al, tol = DT[prec]
     B, C_, H, W = shape
     tag = "bn%s" % (shape,)
@@ -209,16 +211,22 @@ def test_batchnorm_train_fwd_bwd(shape, relu, with_res, prec):
     f32 = dict(dtype=torch.float32, device=dev())
     parts = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * Cp, **f32)
     npart = C.c_int(0)
-    N.call.vae2_bn_stats(ya.data_ptr(), parts.data_ptr(), C.byref(npart), code, P, Cp, Cp, st())
     gd, bd, rmd, rvd = gam.to(dev()), bet.to(dev()), rm.to(dev()), rv.to(dev())
     nbt = torch.zeros(1, dtype=torch.int64, device=dev())
     mean, invstd, scale, shift = (torch.zeros(Cp, **f32) for _ in range(4))
-    N.call.vae2_bn_finalize(parts.data_ptr(), npart.value, C_, Cp, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(),
-                            rvd.data_ptr(), nbt.data_ptr(), 0.01, 1e-5, mean.data_ptr(), invstd.data_ptr(),
-                            scale.data_ptr(), shift.data_ptr(), st())
     oa = torch.zeros_like(ya)
-    N.call.vae2_bn_apply(ya.data_ptr(), ra.data_ptr() if ra is not None else None, oa.data_ptr(), code, P, Cp, Cp, Cp, Cp,
-                         scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, st())
+    if fused:
+        N.call.vae2_bn_fwd_fused(ya.data_ptr(), ra.data_ptr() if ra is not None else None, oa.data_ptr(), parts.data_ptr(),
+                                 code, P, C_, Cp, Cp, Cp, Cp, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(), rvd.data_ptr(),
+                                 nbt.data_ptr(), 0.01, 1e-5, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+                                 shift.data_ptr(), 1 if relu else 0, st())
+    else:
+        N.call.vae2_bn_stats(ya.data_ptr(), parts.data_ptr(), C.byref(npart), code, P, Cp, Cp, st())
+        N.call.vae2_bn_finalize(parts.data_ptr(), npart.value, C_, Cp, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(),
+                                rvd.data_ptr(), nbt.data_ptr(), 0.01, 1e-5, mean.data_ptr(), invstd.data_ptr(),
+                                scale.data_ptr(), shift.data_ptr(), st())
+        N.call.vae2_bn_apply(ya.data_ptr(), ra.data_ptr() if ra is not None else None, oa.data_ptr(), code, P, Cp, Cp, Cp,
+                             Cp, scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, st())
     assert rel_err(from_act(oa, prec, B, C_, H, W, Cp), o.detach()) < tol, "apply"
     assert rel_err(rmd.cpu(), rm_r) < 1e-5 and rel_err(rvd.cpu(), rv_r) < 1e-5, "running stats"
     assert int(nbt) == 1
@@ -226,24 +234,34 @@ def test_batchnorm_train_fwd_bwd(shape, relu, with_res, prec):
 
     ga, _ = to_act(go, prec)
     parts2 = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * Cp, **f32)
-    N.call.vae2_bn_bwd_reduce(ga.data_ptr(), oa.data_ptr(), ya.data_ptr(), parts2.data_ptr(), C.byref(npart), code, P, Cp,
-                              Cp, Cp, Cp, mean.data_ptr(), invstd.data_ptr(), 1 if relu else 0, st())
     sums, c1, c2 = torch.zeros(2 * Cp, **f32), torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
-    N.call.vae2_bn_bwd_finalize(parts2.data_ptr(), npart.value, C_, Cp, sums.data_ptr(), st())
     dg, db = torch.zeros(C_, **f32), torch.zeros(C_, **f32)
-    N.call.vae2_bn_bwd_coeffs(sums.data_ptr(), C_, Cp, 1.0 / P, dg.data_ptr(), db.data_ptr(), 0, sums.data_ptr(),
-                              c1.data_ptr(), c2.data_ptr(), st())
-    dya = torch.zeros_like(ya)
-    dra = torch.zeros_like(ya) if ra is not None else None
-    N.call.vae2_bn_bwd_elemt(ga.data_ptr(), oa.data_ptr(), ya.data_ptr(), dya.data_ptr(),
-                             dra.data_ptr() if dra is not None else None, code, P, Cp, Cp, Cp, Cp, Cp, Cp,
-                             mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), c1.data_ptr(), c2.data_ptr(),
-                             1 if relu else 0, 0, 0, st())
+    # the dx / dres buffers start non-zero and are accumulated into: the plan's "second writer" case
+    dy0 = O.det_normal(tag + "dy0", shape)
+    dya, _ = to_act(dy0, prec)
+    dy0 = from_act(dya, prec, B, C_, H, W, Cp)
+    dra = dya.clone() if ra is not None else None
+    if fused:
+        N.call.vae2_bn_bwd_fused(ga.data_ptr(), oa.data_ptr(), ya.data_ptr(), dya.data_ptr(),
+                                 dra.data_ptr() if dra is not None else None, parts2.data_ptr(), code, P, C_, Cp, Cp, Cp,
+                                 Cp, Cp, Cp, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                 dg.data_ptr(), db.data_ptr(), 0, c1.data_ptr(), c2.data_ptr(),
+                                 0 if not relu else (1 if with_res else 2), 1, 1, st())
+    else:
+        N.call.vae2_bn_bwd_reduce(ga.data_ptr(), oa.data_ptr(), ya.data_ptr(), parts2.data_ptr(), C.byref(npart), code, P,
+                                  Cp, Cp, Cp, Cp, mean.data_ptr(), invstd.data_ptr(), 1 if relu else 0, st())
+        N.call.vae2_bn_bwd_finalize(parts2.data_ptr(), npart.value, C_, Cp, sums.data_ptr(), st())
+        N.call.vae2_bn_bwd_coeffs(sums.data_ptr(), C_, Cp, 1.0 / P, dg.data_ptr(), db.data_ptr(), 0, sums.data_ptr(),
+                                  c1.data_ptr(), c2.data_ptr(), st())
+        N.call.vae2_bn_bwd_elemt(ga.data_ptr(), oa.data_ptr(), ya.data_ptr(), dya.data_ptr(),
+                                 dra.data_ptr() if dra is not None else None, code, P, Cp, Cp, Cp, Cp, Cp, Cp,
+                                 mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), c1.data_ptr(), c2.data_ptr(),
+                                 1 if relu else 0, 1, 1, st())
     btol = tol * 5
-    assert rel_err(from_act(dya, prec, B, C_, H, W, Cp), yr.grad) < btol, "dx"
+    assert rel_err(from_act(dya, prec, B, C_, H, W, Cp) - dy0, yr.grad) < btol, "dx"
     assert rel_err(dg.cpu(), gr.grad) < btol and rel_err(db.cpu(), br.grad) < btol, "dgamma/dbeta"
     if dra is not None:
-        assert rel_err(from_act(dra, prec, B, C_, H, W, Cp), rr.grad) < btol, "dres"
+        assert rel_err(from_act(dra, prec, B, C_, H, W, Cp) - dy0, rr.grad) < btol, "dres"
 
 
 def test_batchnorm_eval_coeffs():

@@ -12,13 +12,40 @@
 // consecutive channels (16-byte vectors); a 256-thread CTA covers R = 256 / lanes pixels per
 // step and strides over the image, so every global access is a full 16-byte vector and
 // consecutive threads touch consecutive addresses.
+//
+// Single-rank training BNs run as ONE cooperative launch per direction (bn_fwd_fused / bn_bwd_fused):
+// statistics -> grid barrier -> per-channel finalize spread over the grid's warps -> grid barrier ->
+// elementwise pass.  The stand-alone kernels stay for SyncBN (a collective sits between the phases)
+// and for eval-mode statistics.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace vae2 {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_MAX_PARTS = kNumSMs * 2;   // <= 2 CTAs per SM: few, fat partials keep the merges short
+constexpr int BN_SPLIT_PARTS = kNumSMs * 2;  // stand-alone reductions: few, fat partials keep the merge kernels short
+constexpr int BN_MAX_PARTS = kNumSMs * 4;    // fused kernels: up to 4 co-resident CTAs per SM
+
+// Thread layout shared by every pass: `lanes` threads cover one pixel's Cp channels (V each), the CTA
+// covers R pixels per step; a thread keeps its channel group for the whole kernel, so per-channel
+// coefficients live in registers.
+template <typename T>
+struct Lay {
+    static constexpr int V = Vec<T>::N;
+    int lanes, R, lane, r;
+    bool active;
+    __device__ __forceinline__ explicit Lay(int Cp) {
+        lanes = Cp / V;
+        R = blockDim.x / lanes;
+        lane = threadIdx.x % lanes;
+        r = threadIdx.x / lanes;
+        active = r < R;
+    }
+};
 
 int bn_stats_max_partials() { return BN_MAX_PARTS; }
 
@@ -26,54 +53,56 @@ int bn_stats_max_partials() { return BN_MAX_PARTS; }
 // statistics: per-CTA (count, mean, M2) per channel  -> partials[cta][3][Cp]
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS)
-bn_stats_kernel(const T* __restrict__ y, float* __restrict__ partials, long long P, int Cp, int ld) {
+__device__ __forceinline__ void stats_pass(const T* __restrict__ y, long long P, int ld, const Lay<T>& L,
+                                           float (&mean)[Vec<T>::N], float (&m2)[Vec<T>::N], float& n) {
     constexpr int V = Vec<T>::N;
-    const int lanes = Cp / V;
-    const int R = BN_THREADS / lanes;
-    const int lane = threadIdx.x % lanes, r = threadIdx.x / lanes;
-    const bool active = r < R;
-
-    float mean[V], m2[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { mean[i] = 0.f; m2[i] = 0.f; }
-    float n = 0.f;
-    if (active) {
-        // 4 independent 16-byte loads in flight per thread before the (serial) Welford updates
-        const long long stride = (long long)gridDim.x * R;
-        for (long long p = (long long)blockIdx.x * R + r; p < P; p += 4 * stride) {
-            Vec<T> x[4];
-            bool ok[4];
+    n = 0.f;
+    if (!L.active) return;
+    // 4 independent 16-byte loads in flight per thread before the (serial) Welford updates
+    const long long stride = (long long)gridDim.x * L.R;
+    for (long long p = (long long)blockIdx.x * L.R + L.r; p < P; p += 4 * stride) {
+        uint4 x[4];
+        bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long q = p + u * stride;
-                ok[u] = q < P;
-                if (ok[u]) x[u] = Vec<T>::load(y + q * ld + lane * V);
-            }
+        for (int u = 0; u < 4; ++u) {
+            const long long q = p + u * stride;
+            ok[u] = q < P;
+            if (ok[u]) x[u] = ld16<T>(y + q * ld + L.lane * V);
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!ok[u]) continue;
-                n += 1.f;
-                const float inv = 1.f / n;
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            n += 1.f;
+            const float inv = 1.f / n;
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    const float d = x[u].v[i] - mean[i];
-                    mean[i] += d * inv;
-                    m2[i] = fmaf(d, x[u].v[i] - mean[i], m2[i]);
-                }
+            for (int i = 0; i < V; ++i) {
+                const float xv = elem<T>(x[u], i);
+                const float d = xv - mean[i];
+                mean[i] += d * inv;
+                m2[i] = fmaf(d, xv - mean[i], m2[i]);
             }
         }
     }
-    // CTA merge (Chan): thread rows r = 0..R-1 for each lane, folded by row 0
-    extern __shared__ float sm[];          // [BN_THREADS][2*V + 1]
+}
+
+// CTA merge (Chan) over the thread rows r = 0..R-1 of each lane: a log2(R)-step tree in shared memory
+// (sm: [blockDim][2V+1]); the result is valid in the r == 0 threads.
+template <int V>
+__device__ __forceinline__ void cta_merge_welford(float* sm, int lanes, int R, int lane, int r, bool active,
+                                                  float (&mean)[V], float (&m2)[V], float& n) {
     float* mine = sm + threadIdx.x * (2 * V + 1);
 #pragma unroll
     for (int i = 0; i < V; ++i) { mine[i] = mean[i]; mine[V + i] = m2[i]; }
     mine[2 * V] = n;
-    __syncthreads();
-    if (active && r == 0) {
-        for (int rr = 1; rr < R; ++rr) {
-            const float* o = sm + (rr * lanes + lane) * (2 * V + 1);
+    int h = 1;
+    while (h < R) h <<= 1;
+    int rows = R;
+    for (h >>= 1; h >= 1; h >>= 1) {
+        __syncthreads();
+        if (active && r < h && r + h < rows) {
+            const float* o = sm + ((r + h) * lanes + lane) * (2 * V + 1);
             const float nb = o[2 * V];
             if (nb > 0.f) {
                 const float nn = n + nb;
@@ -85,17 +114,43 @@ bn_stats_kernel(const T* __restrict__ y, float* __restrict__ partials, long long
                     m2[i] += o[V + i] + d * d * n * f;
                 }
                 n = nn;
+#pragma unroll
+                for (int i = 0; i < V; ++i) { mine[i] = mean[i]; mine[V + i] = m2[i]; }
+                mine[2 * V] = n;
             }
         }
+        rows = rows < h ? rows : h;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void stats_to_partials(const T* __restrict__ y, float* __restrict__ partials, long long P,
+                                                  int Cp, int ld, float* sm) {
+    constexpr int V = Vec<T>::N;
+    const Lay<T> L(Cp);
+    float mean[V], m2[V], n;
+    stats_pass<T>(y, P, ld, L, mean, m2, n);
+    cta_merge_welford<V>(sm, L.lanes, L.R, L.lane, L.r, L.active, mean, m2, n);
+    if (L.active && L.r == 0) {
         float* out = partials + (long long)blockIdx.x * 3 * Cp;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c = lane * V + i;
+            const int c = L.lane * V + i;
             out[c] = n;
             out[Cp + c] = mean[i];
             out[2 * Cp + c] = m2[i];
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// statistics: per-CTA (count, mean, M2) per channel  -> partials[cta][3][Cp]
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_kernel(const T* __restrict__ y, float* __restrict__ partials, long long P, int Cp, int ld) {
+    extern __shared__ float sm[];          // [BN_THREADS][2*V + 1]
+    stats_to_partials<T>(y, partials, P, Cp, ld, sm);
 }
 
 __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
@@ -115,14 +170,19 @@ __device__ __forceinline__ void warp_merge_parts(const float* __restrict__ parts
     if (part_stride == 0) part_stride = 3LL * Cp;
     const int lane = threadIdx.x & 31;
     n = 0.f; mean = 0.f; m2 = 0.f;
-    for (int k = lane; k < n_parts; k += 64) {   // two independent partials in flight per step
-        const float* p = parts + (long long)k * part_stride;
-        const bool has2 = k + 32 < n_parts;
-        const float* q = parts + (long long)(has2 ? k + 32 : k) * part_stride;
-        const float a0 = p[c], a1 = p[Cp + c], a2 = p[2 * Cp + c];
-        const float b0 = q[c], b1 = q[Cp + c], b2 = q[2 * Cp + c];
-        chan_merge(n, mean, m2, a0, a1, a2);
-        if (has2) chan_merge(n, mean, m2, b0, b1, b2);
+    for (int k0 = lane; k0 < n_parts; k0 += 256) {   // 8 independent partials in flight per step
+        float a[8][3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + 32 * j;
+            const bool valid = k < n_parts;
+            const float* p = parts + (long long)(valid ? k : k0) * part_stride;
+            a[j][0] = valid ? p[c] : 0.f;          // count 0: skipped by the merge
+            a[j][1] = p[Cp + c];
+            a[j][2] = p[2 * Cp + c];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) chan_merge(n, mean, m2, a[j][0], a[j][1], a[j][2]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -150,7 +210,36 @@ __global__ void bn_merge_kernel(const float* __restrict__ parts, int n_parts, in
     if ((threadIdx.x & 31) == 0) { merged[c] = n; merged[Cp + c] = mean; merged[2 * Cp + c] = m2; }
 }
 
-// merge + produce normalisation coefficients + running-stat update
+// merge + produce normalisation coefficients + running-stat update for channel c (called by a full warp)
+__device__ __forceinline__ void finalize_channel(int c, const float* __restrict__ parts, int n_parts, int C, int Cp,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                 float momentum, float eps, float* __restrict__ mean_o,
+                                                 float* __restrict__ invstd_o, float* __restrict__ scale_o,
+                                                 float* __restrict__ shift_o, long long part_stride) {
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (c >= C) {
+        if (lead) { mean_o[c] = 0.f; invstd_o[c] = 0.f; scale_o[c] = 0.f; shift_o[c] = 0.f; }
+        return;
+    }
+    // parameters first: their loads overlap the partial merge instead of trailing it
+    const float gm = gamma[c], bt = beta[c];
+    const float rm0 = running_mean != nullptr ? running_mean[c] : 0.f;
+    const float rv0 = running_mean != nullptr ? running_var[c] : 0.f;
+    float n, mean, m2;
+    warp_merge_parts(parts, n_parts, Cp, c, n, mean, m2, part_stride);
+    if (!lead) return;
+    const float var = m2 / n;
+    const float invstd = rsqrtf(var + eps);
+    const float sc = gm * invstd;
+    mean_o[c] = mean; invstd_o[c] = invstd; scale_o[c] = sc; shift_o[c] = bt - mean * sc;
+    if (running_mean != nullptr) {
+        const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
+        running_mean[c] = (1.f - momentum) * rm0 + momentum * mean;
+        running_var[c] = (1.f - momentum) * rv0 + momentum * unbiased;
+    }
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ parts, int n_parts, int C, int Cp,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -161,23 +250,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ parts, int n_parts,
     const int c = gt >> 5;
     if (gt == 0 && nbt != nullptr) *nbt += 1;
     if (c >= Cp) return;
-    const bool lead = (threadIdx.x & 31) == 0;
-    if (c >= C) {
-        if (lead) { mean_o[c] = 0.f; invstd_o[c] = 0.f; scale_o[c] = 0.f; shift_o[c] = 0.f; }
-        return;
-    }
-    float n, mean, m2;
-    warp_merge_parts(parts, n_parts, Cp, c, n, mean, m2, part_stride);
-    if (!lead) return;
-    const float var = m2 / n;
-    const float invstd = rsqrtf(var + eps);
-    const float sc = gamma[c] * invstd;
-    mean_o[c] = mean; invstd_o[c] = invstd; scale_o[c] = sc; shift_o[c] = beta[c] - mean * sc;
-    if (running_mean != nullptr) {
-        const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-    }
+    finalize_channel(c, parts, n_parts, C, Cp, gamma, beta, running_mean, running_var, momentum, eps, mean_o, invstd_o,
+                     scale_o, shift_o, part_stride);
 }
 
 __global__ void bn_eval_coeffs_kernel(int C, int Cp, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -194,66 +268,98 @@ __global__ void bn_eval_coeffs_kernel(int C, int Cp, const float* __restrict__ g
 // apply: out = [relu]( scale*y + shift [+ res] )
 // ---------------------------------------------------------------------------
 template <typename T>
+__device__ __forceinline__ void apply_pass(const T* __restrict__ y, const T* __restrict__ res, T* __restrict__ out,
+                                           long long P, int ld_y, int ld_res, int ld_out,
+                                           const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                           const Lay<T>& L) {
+    constexpr int V = Vec<T>::N;
+    if (!L.active) return;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = scale[L.lane * V + k]; sh[k] = shift[L.lane * V + k]; }
+    const int c0 = L.lane * V;
+    const long long stride = (long long)gridDim.x * L.R;
+    for (long long p = (long long)blockIdx.x * L.R + L.r; p < P; p += 4 * stride) {
+        uint4 x[4], rr[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = p + u * stride;
+            ok[u] = q < P;
+            if (ok[u]) {
+                x[u] = ld16<T>(y + q * ld_y + c0);
+                if (res != nullptr) rr[u] = ld16<T>(res + q * ld_res + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            Vec<T> o;
+#pragma unroll
+            for (int k = 0; k < V; ++k) o.v[k] = fmaf(elem<T>(x[u], k), sc[k], sh[k]);
+            if (res != nullptr) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o.v[k] += elem<T>(rr[u], k);
+            }
+            if (relu) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
+            }
+            o.store(out + (p + u * stride) * ld_out + c0);
+        }
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, T* __restrict__ out, long long P, int Cp,
                 int ld_y, int ld_res, int ld_out, const float* __restrict__ scale, const float* __restrict__ shift,
                 int relu) {
-    constexpr int V = Vec<T>::N;
-    const int lanes = Cp / V;
-    const long long total = P * lanes;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / lanes;
-        const int c0 = (int)(i - p * lanes) * V;
-        Vec<T> x = Vec<T>::load(y + p * ld_y + c0);
-        Vec<T> o;
-#pragma unroll
-        for (int k = 0; k < V; ++k) o.v[k] = fmaf(x.v[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k));
-        if (res != nullptr) {
-            const Vec<T> rr = Vec<T>::load(res + p * ld_res + c0);
-#pragma unroll
-            for (int k = 0; k < V; ++k) o.v[k] += rr.v[k];
-        }
-        if (relu) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
-        }
-        o.store(out + p * ld_out + c0);
-    }
+    const Lay<T> L(Cp);
+    apply_pass<T>(y, res, out, P, ld_y, ld_res, ld_out, scale, shift, relu, L);
 }
 
 // ---------------------------------------------------------------------------
 // backward pass 1: per-CTA  sum(dyb), sum(dyb * xhat)   dyb = g * [a > 0]
 // partials[cta][2][Cp]
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(BN_THREADS)
-bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
-                     float* __restrict__ partials, long long P, int Cp, int ld_g, int ld_a, int ld_y,
-                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu) {
+template <typename T, int RELU>
+__device__ __forceinline__ void bwd_reduce_to_partials_t(const T* __restrict__ g, const T* __restrict__ a,
+                                                       const T* __restrict__ y, float* __restrict__ partials,
+                                                       long long P, int Cp, int ld_g, int ld_a, int ld_y,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       float* sm, const float* __restrict__ scale = nullptr,
+                                                       const float* __restrict__ shift = nullptr) {
+    constexpr int relu = RELU;
+    // relu: 0 none | 1 mask = [a > 0] read from the stored activation | 2 mask recomputed as
+    // [fma(y, scale, shift) > 0] -- the very expression the forward pass rounded into `a` (no residual), so the
+    // activation is not read at all
     constexpr int V = Vec<T>::N;
-    const int lanes = Cp / V;
-    const int R = BN_THREADS / lanes;
-    const int lane = threadIdx.x % lanes, r = threadIdx.x / lanes;
-    const bool active = r < R;
-    float s1[V], s2[V], mu[V], is[V];
+    const Lay<T> L(Cp);
+    // s2 accumulates sum(dyb * (y - mu)); the factor invstd is applied once at the end.  Centring on mu keeps
+    // the sum free of the cancellation a raw sum(dyb * y) would have.
+    float s1[V], s2[V], mu[V], sc[V], sh[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-    if (active) {
+    if (L.active) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) { mu[i] = mean[lane * V + i]; is[i] = invstd[lane * V + i]; }
-        const long long stride = (long long)gridDim.x * R;
-        for (long long p = (long long)blockIdx.x * R + r; p < P; p += 2 * stride) {
-            Vec<T> gv[2], yv[2], av[2];
+        for (int i = 0; i < V; ++i) mu[i] = mean[L.lane * V + i];
+        if (relu == 2) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { sc[i] = scale[L.lane * V + i]; sh[i] = shift[L.lane * V + i]; }
+        }
+        const long long stride = (long long)gridDim.x * L.R;
+        for (long long p = (long long)blockIdx.x * L.R + L.r; p < P; p += 2 * stride) {
+            uint4 gv[2], yv[2], av[2];
             bool ok[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {     // 2 pixels x 3 tensors = 6 independent loads in flight
                 const long long q = p + u * stride;
                 ok[u] = q < P;
                 if (ok[u]) {
-                    gv[u] = Vec<T>::load(g + q * ld_g + lane * V);
-                    yv[u] = Vec<T>::load(y + q * ld_y + lane * V);
-                    if (relu) av[u] = Vec<T>::load(a + q * ld_a + lane * V);
+                    gv[u] = ld16<T>(g + q * ld_g + L.lane * V);
+                    yv[u] = ld16<T>(y + q * ld_y + L.lane * V);
+                    if (relu == 1) av[u] = ld16<T>(a + q * ld_a + L.lane * V);
                 }
             }
 #pragma unroll
@@ -261,28 +367,59 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* 
                 if (!ok[u]) continue;
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
-                    const float gg = (relu && !(av[u].v[i] > 0.f)) ? 0.f : gv[u].v[i];
+                    const float yy = elem<T>(yv[u], i);
+                    bool on = true;
+                    if (relu == 1) on = elem<T>(av[u], i) > 0.f;
+                    if (relu == 2) on = fmaf(yy, sc[i], sh[i]) > 0.f;
+                    const float gg = on ? elem<T>(gv[u], i) : 0.f;
                     s1[i] += gg;
-                    s2[i] = fmaf(gg, (yv[u].v[i] - mu[i]) * is[i], s2[i]);
+                    s2[i] = fmaf(gg, yy - mu[i], s2[i]);
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < V; ++i) s2[i] *= invstd[L.lane * V + i];
     }
-    extern __shared__ float sm[];  // [BN_THREADS][2*V]
+    // tree sum over the thread rows of each lane (sm: [blockDim][2V])
     float* mine = sm + threadIdx.x * (2 * V);
 #pragma unroll
     for (int i = 0; i < V; ++i) { mine[i] = s1[i]; mine[V + i] = s2[i]; }
-    __syncthreads();
-    if (active && r == 0) {
-        for (int rr = 1; rr < R; ++rr) {
-            const float* o = sm + (rr * lanes + lane) * (2 * V);
+    int h = 1;
+    while (h < L.R) h <<= 1;
+    int rows = L.R;
+    for (h >>= 1; h >= 1; h >>= 1) {
+        __syncthreads();
+        if (L.active && L.r < h && L.r + h < rows) {
+            const float* o = sm + ((L.r + h) * L.lanes + L.lane) * (2 * V);
 #pragma unroll
-            for (int i = 0; i < V; ++i) { s1[i] += o[i]; s2[i] += o[V + i]; }
+            for (int i = 0; i < V; ++i) { s1[i] += o[i]; s2[i] += o[V + i]; mine[i] = s1[i]; mine[V + i] = s2[i]; }
         }
+        rows = rows < h ? rows : h;
+    }
+    if (L.active && L.r == 0) {
         float* out = partials + (long long)blockIdx.x * 2 * Cp;
 #pragma unroll
-        for (int i = 0; i < V; ++i) { out[lane * V + i] = s1[i]; out[Cp + lane * V + i] = s2[i]; }
+        for (int i = 0; i < V; ++i) { out[L.lane * V + i] = s1[i]; out[Cp + L.lane * V + i] = s2[i]; }
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void bwd_reduce_to_partials(const T* __restrict__ g, const T* __restrict__ a,
+                                                       const T* __restrict__ y, float* __restrict__ partials,
+                                                       long long P, int Cp, int ld_g, int ld_a, int ld_y,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       int relu, float* sm) {
+    if (relu) bwd_reduce_to_partials_t<T, 1>(g, a, y, partials, P, Cp, ld_g, ld_a, ld_y, mean, invstd, sm);
+    else bwd_reduce_to_partials_t<T, 0>(g, a, y, partials, P, Cp, ld_g, ld_a, ld_y, mean, invstd, sm);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
+                     float* __restrict__ partials, long long P, int Cp, int ld_g, int ld_a, int ld_y,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu) {
+    extern __shared__ float sm[];  // [BN_THREADS][2*V]
+    bwd_reduce_to_partials<T>(g, a, y, partials, P, Cp, ld_g, ld_a, ld_y, mean, invstd, relu, sm);
 }
 
 // sums[2][Cp] = sum over partials (one warp per channel)
@@ -314,48 +451,162 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ sums, int C, int 
 }
 
 // backward pass 2: dy = scale * (dyb - c1 - xhat*c2);  dres (=|+=) dyb
+template <typename T, int RELU, bool DRES>
+__device__ __forceinline__ void bwd_elemt_pass_t(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
+                                               T* __restrict__ dy, T* __restrict__ dres, long long P, int ld_g, int ld_a,
+                                               int ld_y, int ld_dy, int ld_dres, const float* __restrict__ mean,
+                                               const float* __restrict__ invstd, const float* __restrict__ scale,
+                                               const float* __restrict__ c1, const float* __restrict__ c2,
+                                               int acc_dy, int acc_dres, const Lay<T>& L,
+                                               const float* __restrict__ shift = nullptr) {
+    constexpr int V = Vec<T>::N;
+    constexpr int relu = RELU;
+    if (!DRES) dres = nullptr;
+    if (!L.active) return;
+    const int c0 = L.lane * V;
+    float mu[V], k2[V], sc[V], k1[V], sh[V];      // dy = sc * (g - k1 - (y - mu) * k2),  k2 = invstd * c2
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        mu[k] = mean[c0 + k]; k2[k] = invstd[c0 + k] * c2[c0 + k]; sc[k] = scale[c0 + k]; k1[k] = c1[c0 + k];
+    }
+    if (relu == 2) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) sh[k] = shift[c0 + k];
+    }
+    const long long stride = (long long)gridDim.x * L.R;
+    for (long long q = (long long)blockIdx.x * L.R + L.r; q < P; q += stride) {
+        uint4 gv, yv, av, od, orr;
+        gv = ld16<T>(g + q * ld_g + c0);
+        yv = ld16<T>(y + q * ld_y + c0);
+        if (relu == 1) av = ld16<T>(a + q * ld_a + c0);
+        if (acc_dy) od = ld16<T>(dy + q * ld_dy + c0);
+        if (dres != nullptr && acc_dres) orr = ld16<T>(dres + q * ld_dres + c0);
+        Vec<T> o, gm;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            float gg = elem<T>(gv, k);
+            const float yy = elem<T>(yv, k);
+            if (relu == 1) gg = elem<T>(av, k) > 0.f ? gg : 0.f;
+            if (relu == 2) gg = fmaf(yy, sc[k], sh[k]) > 0.f ? gg : 0.f;
+            gm.v[k] = gg;
+            o.v[k] = sc[k] * (gg - k1[k] - (yy - mu[k]) * k2[k]);
+        }
+        if (acc_dy) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) o.v[k] += elem<T>(od, k);
+        }
+        o.store(dy + q * ld_dy + c0);
+        if (dres != nullptr) {
+            if (acc_dres) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) gm.v[k] += elem<T>(orr, k);
+            }
+            gm.store(dres + q * ld_dres + c0);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void bwd_elemt_pass(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
+                                               T* __restrict__ dy, T* __restrict__ dres, long long P, int ld_g, int ld_a,
+                                               int ld_y, int ld_dy, int ld_dres, const float* __restrict__ mean,
+                                               const float* __restrict__ invstd, const float* __restrict__ scale,
+                                               const float* __restrict__ c1, const float* __restrict__ c2, int relu,
+                                               int acc_dy, int acc_dres, const Lay<T>& L) {
+    if (relu) bwd_elemt_pass_t<T, 1, true>(g, a, y, dy, dres, P, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1,
+                                           c2, acc_dy, acc_dres, L);
+    else bwd_elemt_pass_t<T, 0, true>(g, a, y, dy, dres, P, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2,
+                                      acc_dy, acc_dres, L);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_elemt_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y, T* __restrict__ dy,
                     T* __restrict__ dres, long long P, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
                     const float* __restrict__ c1, const float* __restrict__ c2, int relu, int acc_dy, int acc_dres) {
-    constexpr int V = Vec<T>::N;
-    const int lanes = Cp / V;
-    const long long total = P * lanes;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / lanes;
-        const int c0 = (int)(i - p * lanes) * V;
-        Vec<T> gv = Vec<T>::load(g + p * ld_g + c0);
-        const Vec<T> yv = Vec<T>::load(y + p * ld_y + c0);
-        if (relu) {
-            const Vec<T> av = Vec<T>::load(a + p * ld_a + c0);
-#pragma unroll
-            for (int k = 0; k < V; ++k) gv.v[k] = av.v[k] > 0.f ? gv.v[k] : 0.f;
-        }
-        Vec<T> o;
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int c = c0 + k;
-            const float xh = (yv.v[k] - __ldg(mean + c)) * __ldg(invstd + c);
-            o.v[k] = __ldg(scale + c) * (gv.v[k] - __ldg(c1 + c) - xh * __ldg(c2 + c));
-        }
-        if (acc_dy) {
-            const Vec<T> old = Vec<T>::load(dy + p * ld_dy + c0);
-#pragma unroll
-            for (int k = 0; k < V; ++k) o.v[k] += old.v[k];
-        }
-        o.store(dy + p * ld_dy + c0);
-        if (dres != nullptr) {
-            if (acc_dres) {
-                const Vec<T> old = Vec<T>::load(dres + p * ld_dres + c0);
-#pragma unroll
-                for (int k = 0; k < V; ++k) gv.v[k] += old.v[k];
+    const Lay<T> L(Cp);
+    bwd_elemt_pass<T>(g, a, y, dy, dres, P, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy,
+                      acc_dres, L);
+}
+
+// ---------------------------------------------------------------------------
+// fused single-rank training BN: one cooperative launch per direction
+// ---------------------------------------------------------------------------
+struct BnFwdArgs {
+    const void *y, *res;
+    void* out;
+    float* partials;
+    long long P;
+    int C, Cp, ld_y, ld_res, ld_out, relu;
+    const float *gamma, *beta;
+    float *running_mean, *running_var;
+    long long* nbt;
+    float momentum, eps;
+    float *mean, *invstd, *scale, *shift;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_fwd_fused_kernel(const BnFwdArgs A) {
+    extern __shared__ float sm[];
+    cg::grid_group grid = cg::this_grid();
+    stats_to_partials<T>((const T*)A.y, A.partials, A.P, A.Cp, A.ld_y, sm);
+    grid.sync();
+    const int warps = blockDim.x >> 5;
+    for (int c = blockIdx.x * warps + (threadIdx.x >> 5); c < A.Cp; c += gridDim.x * warps)
+        finalize_channel(c, A.partials, gridDim.x, A.C, A.Cp, A.gamma, A.beta, A.running_mean, A.running_var, A.momentum,
+                         A.eps, A.mean, A.invstd, A.scale, A.shift, 3LL * A.Cp);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.nbt != nullptr) *A.nbt += 1;
+    grid.sync();
+    const Lay<T> L(A.Cp);
+    apply_pass<T>((const T*)A.y, (const T*)A.res, (T*)A.out, A.P, A.ld_y, A.ld_res, A.ld_out, A.scale, A.shift, A.relu, L);
+}
+
+struct BnBwdArgs {
+    const void *g, *a, *y;
+    void *dy, *dres;
+    float* partials;
+    long long P;
+    int C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres, acc_param;
+    const float *mean, *invstd, *scale, *shift;
+    float *dgamma, *dbeta, *c1, *c2;
+    float inv_count;
+};
+
+template <typename T, int RELU, bool DRES>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_fused_kernel(const BnBwdArgs A) {
+    extern __shared__ float sm[];
+    cg::grid_group grid = cg::this_grid();
+    bwd_reduce_to_partials_t<T, RELU>((const T*)A.g, (const T*)A.a, (const T*)A.y, A.partials, A.P, A.Cp, A.ld_g, A.ld_a,
+                                      A.ld_y, A.mean, A.invstd, sm, A.scale, A.shift);
+    grid.sync();
+    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int n_parts = gridDim.x;
+    for (int c = blockIdx.x * warps + (threadIdx.x >> 5); c < A.Cp; c += gridDim.x * warps) {
+        float s1 = 0.f, s2 = 0.f;
+        if (c < A.C)
+#pragma unroll 8
+            for (int k = lane; k < n_parts; k += 32) {
+                s1 += A.partials[(long long)k * 2 * A.Cp + c];
+                s2 += A.partials[(long long)k * 2 * A.Cp + A.Cp + c];
             }
-            gv.store(dres + p * ld_dres + c0);
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) {
+            A.c1[c] = s1 * A.inv_count;
+            A.c2[c] = s2 * A.inv_count;
+            if (c < A.C) {
+                if (A.dbeta != nullptr) A.dbeta[c] = A.acc_param ? A.dbeta[c] + s1 : s1;
+                if (A.dgamma != nullptr) A.dgamma[c] = A.acc_param ? A.dgamma[c] + s2 : s2;
+            }
         }
     }
+    grid.sync();
+    const Lay<T> L(A.Cp);
+    bwd_elemt_pass_t<T, RELU, DRES>((const T*)A.g, (const T*)A.a, (const T*)A.y, (T*)A.dy, (T*)A.dres, A.P, A.ld_g, A.ld_a,
+                                    A.ld_y, A.ld_dy, A.ld_dres, A.mean, A.invstd, A.scale, A.c1, A.c2, A.acc_dy, A.acc_dres,
+                                    L, A.shift);
 }
 
 // ---------------------------------------------------------------------------
@@ -368,8 +619,101 @@ static int reduce_grid(long long P, int Cp, int V) {
     const int R = BN_THREADS / lanes;
     long long need = (P + (long long)R * 2 - 1) / ((long long)R * 2);   // 2 pixels per thread until the CTA cap, then more
     if (need < 1) need = 1;
-    if (need > BN_MAX_PARTS) need = BN_MAX_PARTS;
+    if (need > BN_SPLIT_PARTS) need = BN_SPLIT_PARTS;
     return (int)need;
+}
+
+// elementwise passes: >= 4 pixels per thread, at most 8 CTAs per SM
+static int elemt_grid(long long P, int Cp, int V) {
+    const int R = BN_THREADS / (Cp / V);
+    long long need = (P + (long long)R * 4 - 1) / ((long long)R * 4);
+    if (need < 1) need = 1;
+    if (need > kNumSMs * 8) need = kNumSMs * 8;
+    return (int)need;
+}
+
+// Cooperative grid: every CTA must be resident, so the size is capped by the occupancy the driver reports.
+template <typename K>
+static int coop_grid(K kernel, size_t smem, long long P, int Cp, int V, int* cache) {
+    if (*cache == 0) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BN_THREADS, smem) != cudaSuccess || per_sm < 1)
+            return 0;
+        *cache = per_sm * sms;
+    }
+    const int R = BN_THREADS / (Cp / V);
+    long long need = (P + (long long)R * 4 - 1) / ((long long)R * 4);
+    if (need < 1) need = 1;
+    if (need > BN_MAX_PARTS) need = BN_MAX_PARTS;
+    if (need > *cache) need = *cache;
+    return (int)need;
+}
+
+template <typename T>
+static int launch_fwd_fused(BnFwdArgs& A, cudaStream_t st) {
+    constexpr int V = Vec<T>::N;
+    static int cap = 0;
+    const size_t smem = (size_t)BN_THREADS * (2 * V + 1) * sizeof(float);
+    const int grid = coop_grid(bn_fwd_fused_kernel<T>, smem, A.P, A.Cp, V, &cap);
+    if (grid < 1) return VAE2_ERR_CUDA;
+    void* args[] = {(void*)&A};
+    if (cudaLaunchCooperativeKernel((const void*)bn_fwd_fused_kernel<T>, dim3(grid), dim3(BN_THREADS), args, smem, st) !=
+        cudaSuccess)
+        return VAE2_ERR_CUDA;
+    return check_launch();
+}
+
+template <typename T, int RELU, bool DRES>
+static int launch_bwd_fused_t(BnBwdArgs& A, cudaStream_t st) {
+    constexpr int V = Vec<T>::N;
+    static int cap = 0;
+    const size_t smem = (size_t)BN_THREADS * 2 * V * sizeof(float);
+    const int grid = coop_grid(bn_bwd_fused_kernel<T, RELU, DRES>, smem, A.P, A.Cp, V, &cap);
+    if (grid < 1) return VAE2_ERR_CUDA;
+    void* args[] = {(void*)&A};
+    if (cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel<T, RELU, DRES>, dim3(grid), dim3(BN_THREADS), args,
+                                    smem, st) != cudaSuccess)
+        return VAE2_ERR_CUDA;
+    return check_launch();
+}
+
+template <typename T>
+static int launch_bwd_fused(BnBwdArgs& A, cudaStream_t st) {
+    const bool dres = A.dres != nullptr;
+    switch (A.relu * 2 + (dres ? 1 : 0)) {
+        case 0: return launch_bwd_fused_t<T, 0, false>(A, st);
+        case 1: return launch_bwd_fused_t<T, 0, true>(A, st);
+        case 2: return launch_bwd_fused_t<T, 1, false>(A, st);
+        case 3: return launch_bwd_fused_t<T, 1, true>(A, st);
+        case 4: return launch_bwd_fused_t<T, 2, false>(A, st);
+        default: return launch_bwd_fused_t<T, 2, true>(A, st);
+    }
+}
+
+int bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int dtype, long long P, int C, int Cp,
+                 int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale,
+                 float* shift, int relu, cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V) || Cp / V > BN_THREADS || P < 1) return VAE2_ERR_ARG;
+    BnFwdArgs A{y, res, out, partials, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
+                nbt, momentum, eps, mean, invstd, scale, shift};
+    return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
+}
+
+int bn_bwd_fused(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                 long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                 const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                 int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_g % V || ld_y % V || ld_dy % V || (relu == 1 && (a == nullptr || ld_a % V)) ||
+        (relu == 2 && shift == nullptr) || relu < 0 || relu > 2 || (dres && ld_dres % V) || Cp / V > BN_THREADS || P < 1)
+        return VAE2_ERR_ARG;
+    BnBwdArgs A{g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
+                accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, 1.0f / (float)P};
+    return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
 }
 
 int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, long long P, int Cp, int ld, cudaStream_t st) {
@@ -409,7 +753,8 @@ int bn_apply(const void* y, const void* res, void* out, int dtype, long long P, 
              const float* scale, const float* shift, int relu, cudaStream_t st) {
     const int V = vec_of(dtype);
     if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V)) return VAE2_ERR_ARG;
-    const int grid = stream_grid(P * (Cp / V), BN_THREADS * 4);
+    if (Cp / V > BN_THREADS) return VAE2_ERR_ARG;
+    const int grid = elemt_grid(P, Cp, V);
     if (dtype == VAE2_DT_F32)
         bn_apply_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)y, (const float*)res, (float*)out, P, Cp, ld_y, ld_res, ld_out, scale, shift, relu);
     else
@@ -450,7 +795,8 @@ int bn_bwd_elemt(const void* g, const void* a, const void* y, void* dy, void* dr
                  cudaStream_t st) {
     const int V = vec_of(dtype);
     if (Cp % V || ld_g % V || ld_y % V || ld_dy % V) return VAE2_ERR_ARG;
-    const int grid = stream_grid(P * (Cp / V), BN_THREADS * 4);
+    if (Cp / V > BN_THREADS) return VAE2_ERR_ARG;
+    const int grid = elemt_grid(P, Cp, V);
     if (dtype == VAE2_DT_F32)
         bn_bwd_elemt_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)g, (const float*)a, (const float*)y, (float*)dy, (float*)dres, P, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy, acc_dres);
     else

@@ -55,6 +55,17 @@ template <> struct Vec<__nv_bfloat16> {
     }
 };
 
+// Raw 16-byte vectors: streaming kernels keep loads packed in registers and unpack element k (a compile-time
+// index after unrolling) at the point of use, so many loads can be in flight without 2x the registers.
+template <typename T> __device__ __forceinline__ uint4 ld16(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ unsigned word_of(const uint4& q, int w) { return w == 0 ? q.x : w == 1 ? q.y : w == 2 ? q.z : q.w; }
+template <typename T> __device__ __forceinline__ float elem(const uint4& q, int k);
+template <> __device__ __forceinline__ float elem<float>(const uint4& q, int k) { return __uint_as_float(word_of(q, k)); }
+template <> __device__ __forceinline__ float elem<__nv_bfloat16>(const uint4& q, int k) {
+    const unsigned w = word_of(q, k >> 1);
+    return __uint_as_float((k & 1) ? (w & 0xffff0000u) : (w << 16));
+}
+
 template <typename T> __device__ __forceinline__ float to_f(T x);
 template <> __device__ __forceinline__ float to_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }

@@ -413,13 +413,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// dwp[i] = sum over split-K slots
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long long n, int nslots) {
+// dwp[i] = sum over split-K slots.  32 float4 columns x 8 slot groups per CTA: a thread adds every 8th slot
+// (independent loads, a short dependent chain), the groups are folded through shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long long n, int nslots) {
+    __shared__ float4 sm[8][32];
+    const int ex = threadIdx.x & 31, sg = threadIdx.x >> 5;
     const long long n4 = n / 4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < nslots; ++s) {
-            const float4 v = reinterpret_cast<const float4*>(ws + (long long)s * n)[i];
+    const long long i = (long long)blockIdx.x * 32 + ex;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+        const float4* src = reinterpret_cast<const float4*>(ws) + i;
+#pragma unroll 4
+        for (int s = sg; s < nslots; s += 8) {
+            const float4 v = src[(long long)s * n4];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    }
+    sm[sg][ex] = a;
+    __syncthreads();
+    if (sg == 0 && i < n4) {
+#pragma unroll
+        for (int g = 1; g < 8; ++g) {
+            const float4 v = sm[g][ex];
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         reinterpret_cast<float4*>(dwp)[i] = a;
@@ -695,7 +711,7 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
     wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
     if (int e = check_launch()) return e;
     const long long n = (long long)p.M_total * g.Cout_p;
-    wgrad_reduce_kernel<<<stream_grid(n / 4, 256, 4), 256, 0, st>>>(ws, dwp, n, p.nranges);
+    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(ws, dwp, n, p.nranges);
     return check_launch();
 }
 

@@ -557,7 +557,10 @@ class BnOp:
 
     Emission is split into sub-steps so that a BnGroupOp can run the members of a SyncBN group through
     ONE collective: stats(+rank-local merge) | all-gather | finalize+apply, and in backward
-    reduce | all-reduce | coeffs+elemt."""
+    reduce | all-reduce | coeffs+elemt.  Without a collective (single rank, batch statistics) each direction
+    is ONE cooperative launch (vae2_bn_fwd_fused / vae2_bn_bwd_fused)."""
+
+    _ws = {}
 
     def __init__(self, plan, y, bn, relu, residual=None, out=None):
         self.y, self.bn, self.relu, self.res = y, bn, relu, residual
@@ -574,9 +577,63 @@ class BnOp:
         self.mean, self.invstd = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.scale, self.shift = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.batch_stats = plan.bn_batch_stats or not self.bn.track_running_stats
-        if self.batch_stats:
+        self.fused = (self.batch_stats and not self.sync and self.out.Cp >= y.Cp
+                      and os.environ.get("VAE2_BN_SPLIT", "0") != "1")
+        if self.batch_stats and not self.fused:
             self.partials = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * y.Cp, **f32)
             self.npart = C.c_int(0)
+
+    @staticmethod
+    def _scratch(plan):
+        """Partials scratch of the fused kernels: consumed inside the launch that writes it, so one buffer
+        per device serves every BN of every plan."""
+        key = plan.device.index
+        ws = BnOp._ws.get(key)
+        if ws is None:
+            ws = BnOp._ws[key] = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * 2048, dtype=torch.float32,
+                                             device=plan.device)
+        return ws
+
+    def _emit_fwd_fused(self, plan):
+        """stats | finalize | apply as ONE cooperative launch (single-rank training statistics)."""
+        pr, bn, y, out, res = plan.prec, self.bn, self.y, self.out, self.res
+        lanes = min(y.Cp, out.Cp)
+        ws = self._scratch(plan).data_ptr()
+        yp, op_, rp = y.ptr, out.ptr, (res.ptr if res is not None else None)
+        ldr = res.ld if res is not None else 0
+        npix, ldy, ldo, C_, Cp = y.npix, y.ld, out.ld, y.C, y.Cp
+        eps = float(bn.eps)
+        mom = 0.0 if bn.momentum is None else float(bn.momentum)
+        gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
+        rm = bn.running_mean.data_ptr() if bn.running_mean is not None else None
+        rv = bn.running_var.data_ptr() if bn.running_var is not None else None
+        nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
+        outs = (self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr())
+        relu = 1 if self.relu else 0
+        plan.fwd.append(lambda st: N.call.vae2_bn_fwd_fused(yp, rp, op_, ws, pr.code, npix, C_, Cp, ldy, ldr, ldo, gp, bp,
+                                                            rm, rv, nbt, mom, eps, *outs, relu, st))
+
+    def _emit_bwd_fused(self, plan):
+        pr = plan.prec
+        y, out, bn, res, g = self.y, self.out, self.bn, self.res, self.g
+        npix, lanes, C_ = y.npix, self.lanes, y.C
+        ws = self._scratch(plan).data_ptr()
+        dgam, dbet = plan.grad_ptr(bn.weight), plan.grad_ptr(bn.bias)
+        c1p, c2p = self.c1.data_ptr(), self.c2.data_ptr()
+        dy = y.grad()
+        acc_dy = y.take_acc_flag()
+        dres_p, ld_dres, acc_res = None, 0, 0
+        if res is not None and res.needs_grad:
+            acc_res = res.take_acc_flag()
+            dres_p, ld_dres = res.grad().ptr, res.ld
+        gp_, ap, yp, dyp = g.ptr, out.ptr, y.ptr, dy.ptr
+        mp, ip, scp, shp = self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr()
+        # ReLU mask: without a residual it is recomputed from y (mode 2) and the stored activation is not read
+        relu = 0 if not self.relu else (1 if res is not None else 2)
+        gld, old, yld, dld = g.ld, out.ld, y.ld, dy.ld
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_fused(gp_, ap, yp, dyp, dres_p, ws, pr.code, npix, C_, lanes, gld,
+                                                            old, yld, dld, ld_dres, mp, ip, scp, shp, dgam, dbet, 0, c1p,
+                                                            c2p, relu, acc_dy, acc_res, st))
 
     def _emit_stats(self, plan, merged_ptr=None):
         """Per-CTA partials (and, for SyncBN, the rank-local merge into the group message)."""
@@ -628,7 +685,8 @@ class BnOp:
     def _bwd_setup(self, plan):
         y = self.y
         f32 = dict(dtype=torch.float32, device=plan.device)
-        self.bparts = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * y.Cp, **f32)
+        if not self.fused:
+            self.bparts = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * y.Cp, **f32)
         self.sums, self.c1, self.c2 = torch.zeros(2 * y.Cp, **f32), torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.bnpart = C.c_int(0)
         self.lanes = min(y.Cp, self.out.Cp)
@@ -689,6 +747,9 @@ class BnGroupOp:
             m._fwd_setup(plan)
         if not (self.sync and ms[0].batch_stats):
             for m in ms:
+                if m.fused:
+                    m._emit_fwd_fused(plan)
+                    continue
                 if m.batch_stats:
                     m._emit_stats(plan)
                 m._emit_finalize(plan)
@@ -716,6 +777,9 @@ class BnGroupOp:
             m._bwd_setup(plan)
         if not (self.sync and ms[0].batch_stats):
             for m in ms:
+                if m.fused:
+                    m._emit_bwd_fused(plan)
+                    continue
                 m._emit_bwd_reduce(plan)
                 m._emit_bwd_apply(plan)
             return

@@ -77,6 +77,10 @@ _PROTOS = {
     "vae2_bn_bwd_coeffs": [vp, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp],
     "vae2_bn_bwd_elemt": [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                           i32, i32, i32, vp],
+    "vae2_bn_fwd_fused": [vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp,
+                          vp, i32, vp],
+    "vae2_bn_bwd_fused": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                          i32, vp, vp, i32, i32, i32, vp],
     "vae2_fuse_sum": [C.POINTER(FuseSrc), i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "vae2_fuse_bwd_same": [vp, vp, C.POINTER(FuseDst), i32, i32, i64, i32, i32, i32, i32, vp],
     "vae2_fuse_bwd_up": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
