@@ -203,6 +203,168 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---- 3x3 stride-1 with ONE halo tile per (pixel patch, K chunk) ---------------------------------------------
+// The nine taps of a 3x3 convolution read nine shifted views of the same pixels.  conv_tc_kernel fetches each
+// view with its own TMA (9x the activation bytes through L2 -> shared memory, which is what bounds it for
+// narrow layers); here the patch is 16 rows x 8 pixels and ONE TMA box [KC][10][18] brings the patch plus its
+// 1-pixel halo.  Tap (dh, dw) is then only a different START ADDRESS of the A descriptor: 8-row groups are the
+// 8 pixels of one patch row (contiguous in the box), consecutive groups are one box row = 10 pixels apart (SBO),
+// and the swizzle is a function of the absolute shared-memory address, so a start that is not aligned to the
+// swizzle atom reads back exactly what TMA wrote (tools/probes/umma_shift_probe.cu checks this on the device).
+// The packed weights of all taps stay resident in shared memory for the CTA's lifetime; a pipeline stage is a
+// halo tile, so a patch costs kchunks barrier round trips instead of 9*kchunks.
+constexpr int kHaloTW = 8, kHaloTH = 16, kHaloBW = kHaloTW + 2, kHaloBH = kHaloTH + 2;
+
+__global__ void __launch_bounds__(kThreads, 3)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t row_bytes = p.KC * 2;
+    const uint32_t a_bytes = kHaloBW * kHaloBH * row_bytes;                 // TMA transaction size of one halo tile
+    const uint32_t a_stage = (a_bytes + 1023) / 1024 * 1024;
+    const uint32_t atom = 8 * row_bytes;                                    // swizzle repeat
+    const uint32_t w_block = (p.NT * row_bytes + atom - 1) / atom * atom;  // one (K chunk, tap) weight tile
+    const uint32_t w_bytes = ((uint32_t)(p.kchunks * p.taps) * w_block + 1023) / 1024 * 1024;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem;
+    uint8_t* asm_ = smem + w_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(asm_ + (size_t)p.stages * a_stage);
+    uint64_t* full = bars;                       // [stages]
+    uint64_t* empty = bars + kMaxStages;         // [stages]
+    uint64_t* acc_full = bars + 2 * kMaxStages;  // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint64_t* w_full = acc_empty + 2;            // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)(p.kchunks * p.taps) * (uint32_t)p.NT * row_bytes);
+            for (int kc = 0; kc < p.kchunks; ++kc)
+                for (int tap = 0; tap < p.taps; ++tap)
+                    tma_load_3d(wsm + (size_t)(kc * p.taps + tap) * w_block, &map_w, w_full, kc * p.KC, 0, p.tap_w[tap]);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int b = tile / per_img;
+                const int r = tile - b * per_img;
+                const int h0 = (r / p.tiles_w) * kHaloTH, w0 = (r % p.tiles_w) * kHaloTW;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], a_bytes);
+                    tma_load_4d(asm_ + (size_t)stage * a_stage, &map_a, &full[stage], kc * p.KC, w0 - 1, h0 - 1, b);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            // descriptor high words: SBO = one box row (A) / 8 rows (weights), version 1, swizzle by span
+            const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+            const uint32_t hi_a = ((kHaloBW * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+            const uint32_t hi_w = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+            const uint32_t w0s = smem_u32(wsm);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t use = (uint32_t)(it >> 1);
+                mbar_wait(&acc_empty[as], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.NT);
+                uint32_t accum = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(asm_ + (size_t)stage * a_stage);
+                    const uint32_t sw = w0s + (uint32_t)(kc * p.taps) * w_block;
+                    for (int tap = 0; tap < p.taps; ++tap) {
+                        const uint32_t ta = sa + (uint32_t)((p.tap_dh[tap] + 1) * kHaloBW + (p.tap_dw[tap] + 1)) * row_bytes;
+                        const uint32_t tw = sw + (uint32_t)tap * w_block;
+                        for (int k = 0; k < p.KC / 16; ++k) {
+                            const uint64_t da = ((uint64_t)hi_a << 32) | (1u << 16) | (((ta + k * 32) >> 4) & 0x3FFF);
+                            const uint64_t db = ((uint64_t)hi_w << 32) | (1u << 16) | (((tw + k * 32) >> 4) & 0x3FFF);
+                            umma_bf16(d_tmem, da, db, idesc, accum);
+                            accum = 1;
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        // ================= epilogue warps (TMEM -> registers -> global) =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;          // tile row == TMEM lane == pixel (row / 8, row % 8) of the patch
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t use = (uint32_t)(it >> 1);
+            const int b = tile / per_img;
+            const int r = tile - b * per_img;
+            const int h = (r / p.tiles_w) * kHaloTH + row / kHaloTW, w = (r % p.tiles_w) * kHaloTW + row % kHaloTW;
+            const bool in_img = h < p.MH && w < p.MW;
+            mbar_wait(&acc_full[as], use & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.NT);
+            __nv_bfloat16* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
+            for (int c0 = 0; c0 < p.NT; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t0 + c0, v);
+                tmem_ld_wait();
+                if (in_img && c0 < p.Cn) {
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + c0 + i);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+                    if (p.accumulate) {
+                        uint4 o[2] = {dst[0], dst[1]};
+                        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(o);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { float2 t = __bfloat1622float2(oh[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+                    }
+                    uint4 o[2];
+                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                    dst[0] = o[0];
+                    dst[1] = o[1];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -554,6 +716,84 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
     p.kchunks = (L.Ck + p.KC - 1) / p.KC;
     p.n_tiles = (L.Cn + 255) / 256;
     p.NT = (((L.Cn + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
+    p.accumulate = L.accumulate;
+    p.bias = L.bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(L.out);
+    // ---- halo path: 3x3, unit strides, all taps' weights resident in shared memory ----
+    {
+        bool halo = L.ntaps == 9 && L.sA == 1 && L.a_estride == 1 && L.sO == 1 && L.oh_off == 0 && L.ow_off == 0 &&
+                    p.n_tiles == 1 && 2 * p.NT <= 512;
+        for (int i = 0; halo && i < 9; ++i) halo = L.dh[i] >= -1 && L.dh[i] <= 1 && L.dw[i] >= -1 && L.dw[i] <= 1;
+        if (const char* e = getenv("VAE2_TC_HALO")) { if (atoi(e) == 0) halo = false; }
+        // K chunk: a halo stage costs one barrier round trip per chunk (not per tap), so the MMA count decides:
+        // fewest 16-channel steps, ties to the wider chunk (fewer TMA boxes)
+        int hkc = 16, best = 1 << 30;
+        for (int kc = 16; kc <= 64; kc *= 2) {
+            const int cost = ((L.Ck + kc - 1) / kc) * (kc / 16) * 8 + (L.Ck + kc - 1) / kc;
+            if (cost <= best) { best = cost; hkc = kc; }
+        }
+        const int hchunks = (L.Ck + hkc - 1) / hkc;
+        const int row_bytes = hkc * 2;
+        const int atom = 8 * row_bytes;                                      // swizzle repeat: 8 rows of one span
+        const int a_stage = (kHaloBW * kHaloBH * row_bytes + 1023) / 1024 * 1024;
+        const int w_block = (p.NT * row_bytes + atom - 1) / atom * atom;
+        const int w_bytes = (hchunks * 9 * w_block + 1023) / 1024 * 1024;
+        const int bar_bytes = 1024 /*align slack*/ + (2 * kMaxStages + 5) * 8 + 16;
+        // as many co-resident CTAs (independent MMA issuers) as shared memory and TMEM allow; a single issuer per SM
+        // loses to conv_tc_kernel's two, so the halo path needs at least 2
+        int ctas = 4;
+        while (ctas > 1 && (w_bytes + 2 * a_stage + bar_bytes > 227 * 1024 / ctas - 1024 ||
+                            next_pow2_cols(2 * p.NT) * ctas > 512)) --ctas;
+        if (halo && ctas >= 2) {
+            p.KC = hkc; p.kchunks = hchunks;
+            int stages = (227 * 1024 / ctas - 1024 - w_bytes - bar_bytes) / a_stage;
+            if (stages > kMaxStages) stages = kMaxStages;
+            if (stages >= 2) {
+                p.stages = stages;
+                p.acc_stages = 2;
+                p.tmem_cols = next_pow2_cols(2 * p.NT);
+                p.TW = kHaloTW; p.TH = kHaloTH;
+                p.tiles_w = (L.MW + kHaloTW - 1) / kHaloTW;
+                p.tiles_h = (L.MH + kHaloTH - 1) / kHaloTH;
+                p.total_tiles = L.B * p.tiles_w * p.tiles_h;
+                CUtensorMap map_a, map_w;
+                {
+                    cuuint64_t dims[4] = {(cuuint64_t)L.Ck, (cuuint64_t)L.AW, (cuuint64_t)L.AH, (cuuint64_t)L.B};
+                    cuuint64_t strides[3] = {(cuuint64_t)L.lda * 2, (cuuint64_t)L.AW * L.lda * 2, (cuuint64_t)L.AH * L.AW * L.lda * 2};
+                    cuuint32_t box[4] = {(cuuint32_t)p.KC, (cuuint32_t)kHaloBW, (cuuint32_t)kHaloBH, 1};
+                    cuuint32_t es[4] = {1, 1, 1, 1};
+                    if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(L.a), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                        halo = false;
+                }
+                if (halo) {
+                    cuuint64_t dims[3] = {(cuuint64_t)L.Ck, (cuuint64_t)L.Cn, (cuuint64_t)L.wtaps};
+                    cuuint64_t strides[2] = {(cuuint64_t)L.Ck * 2, (cuuint64_t)L.Cn * L.Ck * 2};
+                    cuuint32_t box[3] = {(cuuint32_t)p.KC, (cuuint32_t)p.NT, 1};
+                    cuuint32_t es[3] = {1, 1, 1};
+                    if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(L.wq), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                        halo = false;
+                }
+                const size_t smem = (size_t)w_bytes + (size_t)stages * a_stage + bar_bytes;
+                static bool attr_set_h = false;
+                if (!attr_set_h) {
+                    if (cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                        return VAE2_ERR_CUDA;
+                    attr_set_h = true;
+                }
+                if (halo) {
+                    const int grid = p.total_tiles < ctas * kNumSMs ? p.total_tiles : ctas * kNumSMs;
+                    conv_tc_halo_kernel<<<grid, kThreads, smem, st>>>(map_a, map_w, p);
+                    return check_launch();
+                }
+            }
+        }
+    }
+    p.KC = pick_kc(L.Ck);                          // (the halo attempt may have changed the chunking)
+    p.kchunks = (L.Ck + p.KC - 1) / p.KC;
     int tw = 128;
     while (tw > 8 && tw / 2 >= L.MW) tw >>= 1;
     p.TW = tw; p.TH = 128 / tw;
