@@ -139,6 +139,9 @@ int vae2_bn_bwd_elemt(const void* g, const void* a, const void* y, void* dy, voi
  * bwd_elemt above; `partials` is scratch of vae2_bn_max_partials()*3*Cp floats.  SyncBN keeps the split entry
  * points because its collective sits between the phases.  bwd `relu`: 0 none, 1 mask read from the stored
  * activation `a`, 2 mask recomputed as fma(y, scale, shift) > 0 (BN+ReLU without a residual: `a` is not read). */
+/* debug aid: when set (device buffer of 6 x uint64), CTA 0 of the fused kernels records %globaltimer at its phase
+ * boundaries (start | stats done | barrier 1 passed | finalize done | barrier 2 passed | end); null disables */
+int vae2_debug_bn_phase_times(uint64_t* device_buf6);
 int vae2_bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int dtype, int64_t npix, int C,
                       int Cp, int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,

@@ -86,5 +86,16 @@ for P, Cp in SHAPES:
         us = timeit(fn, nbuf)
         print("P=%7d Cp=%3d (%6.1f MB/tensor) %s %8.1f us  %7.0f GB/s  %5.1f%% of HBM peak" %
               (P, Cp, nbytes / 1e6, name, us, nb / us / 1e3, 100 * nb / us / 1e3 / peak))
+    # phase split of the fused kernels (CTA 0's view)
+    prof = torch.zeros(6, dtype=torch.int64, device=dev)
+    N.call.vae2_debug_bn_phase_times(prof.data_ptr())
+    for name, fn in (("fwd fused", fused_fwd), ("bwd fused", fused_bwd), ("bwd fused no-res", fused_bwd_nores)):
+        for i in range(3):
+            fn(i % nbuf)
+        torch.cuda.synchronize()
+        t = prof.cpu().tolist()
+        print("    %-18s phases (us): pass1 %.1f | barrier %.1f | finalize %.1f | barrier %.1f | pass2 %.1f | total %.1f" %
+              ((name,) + tuple((t[i + 1] - t[i]) / 1e3 for i in range(5)) + ((t[5] - t[0]) / 1e3,)))
+    N.call.vae2_debug_bn_phase_times(None)
     del y, res, out, g, dy, dres
     torch.cuda.empty_cache()

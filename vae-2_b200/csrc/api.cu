@@ -133,6 +133,7 @@ int vae2_bn_bwd_reduce(const void* g, const void* a, const void* y, float* parti
                        vae2_stream_t stream) {
     return bn_bwd_reduce(g, a, y, partials, n_partials, dtype, npix, Cp, ld_g, ld_a, ld_y, mean, invstd, relu, S(stream));
 }
+int vae2_debug_bn_phase_times(uint64_t* device_buf6) { bn_debug_set_prof((unsigned long long*)device_buf6); return VAE2_OK; }
 int vae2_bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int dtype, int64_t npix, int C, int Cp,
                       int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* mean,

@@ -52,39 +52,86 @@ int bn_stats_max_partials() { return BN_MAX_PARTS; }
 // ---------------------------------------------------------------------------
 // statistics: per-CTA (count, mean, M2) per channel  -> partials[cta][3][Cp]
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Streaming loop shared by every pass.  A thread visits pixels first, first+stride, ...; its 16-byte vectors
+// are fetched with cp.async into the thread's OWN shared-memory slots D iterations ahead and read back right
+// before use.  The loads in flight therefore live in shared memory (kPipeBytes per CTA), not in registers:
+// ~100 KB per SM in flight at 3 CTAs/SM, which is what HBM needs, while the kernels stay under 85 registers.
+// No block-level synchronisation is involved (a thread only ever reads slots it filled itself).
+// `reverse` walks the list backwards: the second pass of a fused kernel then starts with the lines the first
+// pass touched last, i.e. the ones still in L2.
+// ---------------------------------------------------------------------------
+constexpr int kPipeSlots = 12;                                  // 16-byte slots per thread
+constexpr int kPipeBytes = kPipeSlots * BN_THREADS * 16;        // 48 KB
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int NTENS, typename Body>
+__device__ __forceinline__ void stream_pixels(float* sm, const Lay<T>& L, long long P, bool reverse,
+                                              const T* const (&base)[NTENS], const int (&ld)[NTENS], Body body) {
+    constexpr int V = Vec<T>::N;
+    constexpr int D = kPipeSlots / NTENS;
+    if (!L.active) return;
+    const long long stride = (long long)gridDim.x * L.R;
+    const long long first = (long long)blockIdx.x * L.R + L.r;
+    const long long n = first < P ? (P - first + stride - 1) / stride : 0;
+    const int c0 = L.lane * V;
+    uint4* mine = reinterpret_cast<uint4*>(sm) + threadIdx.x;     // slot s, tensor t: mine[(s*NTENS + t) * BN_THREADS]
+    int s_in = 0;
+    for (int i = 0; i < D - 1; ++i) {
+        if (i < n) {
+            const long long q = first + (reverse ? n - 1 - i : (long long)i) * stride;
+#pragma unroll
+            for (int t = 0; t < NTENS; ++t) cp_async16(mine + (s_in * NTENS + t) * BN_THREADS, base[t] + q * ld[t] + c0);
+        }
+        cp_async_commit();
+        s_in = s_in + 1 == D ? 0 : s_in + 1;
+    }
+    int s_out = 0;
+    for (long long i = 0; i < n; ++i) {
+        const long long j = i + D - 1;
+        if (j < n) {
+            const long long q = first + (reverse ? n - 1 - j : j) * stride;
+#pragma unroll
+            for (int t = 0; t < NTENS; ++t) cp_async16(mine + (s_in * NTENS + t) * BN_THREADS, base[t] + q * ld[t] + c0);
+        }
+        cp_async_commit();
+        s_in = s_in + 1 == D ? 0 : s_in + 1;
+        cp_async_wait<D - 1>();
+        uint4 v[NTENS];
+#pragma unroll
+        for (int t = 0; t < NTENS; ++t) v[t] = mine[(s_out * NTENS + t) * BN_THREADS];
+        s_out = s_out + 1 == D ? 0 : s_out + 1;
+        body(first + (reverse ? n - 1 - i : i) * stride, v);
+    }
+    cp_async_wait<0>();
+}
+
 template <typename T>
-__device__ __forceinline__ void stats_pass(const T* __restrict__ y, long long P, int ld, const Lay<T>& L,
+__device__ __forceinline__ void stats_pass(const T* __restrict__ y, long long P, int ld, const Lay<T>& L, float* sm,
                                            float (&mean)[Vec<T>::N], float (&m2)[Vec<T>::N], float& n) {
     constexpr int V = Vec<T>::N;
 #pragma unroll
     for (int i = 0; i < V; ++i) { mean[i] = 0.f; m2[i] = 0.f; }
     n = 0.f;
-    if (!L.active) return;
-    // 4 independent 16-byte loads in flight per thread before the (serial) Welford updates
-    const long long stride = (long long)gridDim.x * L.R;
-    for (long long p = (long long)blockIdx.x * L.R + L.r; p < P; p += 4 * stride) {
-        uint4 x[4];
-        bool ok[4];
+    const T* const base[1] = {y};
+    const int lds[1] = {ld};
+    stream_pixels<T, 1>(sm, L, P, false, base, lds, [&](long long, const uint4 (&v)[1]) {
+        n += 1.f;
+        const float inv = 1.f / n;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long q = p + u * stride;
-            ok[u] = q < P;
-            if (ok[u]) x[u] = ld16<T>(y + q * ld + L.lane * V);
+        for (int i = 0; i < V; ++i) {
+            const float xv = elem<T>(v[0], i);
+            const float d = xv - mean[i];
+            mean[i] += d * inv;
+            m2[i] = fmaf(d, xv - mean[i], m2[i]);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (!ok[u]) continue;
-            n += 1.f;
-            const float inv = 1.f / n;
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float xv = elem<T>(x[u], i);
-                const float d = xv - mean[i];
-                mean[i] += d * inv;
-                m2[i] = fmaf(d, xv - mean[i], m2[i]);
-            }
-        }
-    }
+    });
 }
 
 // CTA merge (Chan) over the thread rows r = 0..R-1 of each lane: a log2(R)-step tree in shared memory
@@ -92,6 +139,7 @@ __device__ __forceinline__ void stats_pass(const T* __restrict__ y, long long P,
 template <int V>
 __device__ __forceinline__ void cta_merge_welford(float* sm, int lanes, int R, int lane, int r, bool active,
                                                   float (&mean)[V], float (&m2)[V], float& n) {
+    __syncthreads();      // the scratch aliases the streaming slots of threads that may still be reading theirs
     float* mine = sm + threadIdx.x * (2 * V + 1);
 #pragma unroll
     for (int i = 0; i < V; ++i) { mine[i] = mean[i]; mine[V + i] = m2[i]; }
@@ -129,7 +177,7 @@ __device__ __forceinline__ void stats_to_partials(const T* __restrict__ y, float
     constexpr int V = Vec<T>::N;
     const Lay<T> L(Cp);
     float mean[V], m2[V], n;
-    stats_pass<T>(y, P, ld, L, mean, m2, n);
+    stats_pass<T>(y, P, ld, L, sm, mean, m2, n);
     cta_merge_welford<V>(sm, L.lanes, L.R, L.lane, L.r, L.active, mean, m2, n);
     if (L.active && L.r == 0) {
         float* out = partials + (long long)blockIdx.x * 3 * Cp;
@@ -149,7 +197,7 @@ __device__ __forceinline__ void stats_to_partials(const T* __restrict__ y, float
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_stats_kernel(const T* __restrict__ y, float* __restrict__ partials, long long P, int Cp, int ld) {
-    extern __shared__ float sm[];          // [BN_THREADS][2*V + 1]
+    extern __shared__ __align__(16) float sm[];          // [BN_THREADS][2*V + 1]
     stats_to_partials<T>(y, partials, P, Cp, ld, sm);
 }
 
@@ -271,42 +319,39 @@ template <typename T>
 __device__ __forceinline__ void apply_pass(const T* __restrict__ y, const T* __restrict__ res, T* __restrict__ out,
                                            long long P, int ld_y, int ld_res, int ld_out,
                                            const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                                           const Lay<T>& L) {
+                                           const Lay<T>& L, float* sm, bool reverse) {
     constexpr int V = Vec<T>::N;
     if (!L.active) return;
     float sc[V], sh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) { sc[k] = scale[L.lane * V + k]; sh[k] = shift[L.lane * V + k]; }
     const int c0 = L.lane * V;
-    const long long stride = (long long)gridDim.x * L.R;
-    for (long long p = (long long)blockIdx.x * L.R + L.r; p < P; p += 4 * stride) {
-        uint4 x[4], rr[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long q = p + u * stride;
-            ok[u] = q < P;
-            if (ok[u]) {
-                x[u] = ld16<T>(y + q * ld_y + c0);
-                if (res != nullptr) rr[u] = ld16<T>(res + q * ld_res + c0);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (!ok[u]) continue;
+    if (res != nullptr) {
+        const T* const base[2] = {y, res};
+        const int lds[2] = {ld_y, ld_res};
+        stream_pixels<T, 2>(sm, L, P, reverse, base, lds, [&](long long q, const uint4 (&v)[2]) {
             Vec<T> o;
 #pragma unroll
-            for (int k = 0; k < V; ++k) o.v[k] = fmaf(elem<T>(x[u], k), sc[k], sh[k]);
-            if (res != nullptr) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) o.v[k] += elem<T>(rr[u], k);
-            }
+            for (int k = 0; k < V; ++k) o.v[k] = fmaf(elem<T>(v[0], k), sc[k], sh[k]) + elem<T>(v[1], k);
             if (relu) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
             }
-            o.store(out + (p + u * stride) * ld_out + c0);
-        }
+            o.store(out + q * ld_out + c0);
+        });
+    } else {
+        const T* const base[1] = {y};
+        const int lds[1] = {ld_y};
+        stream_pixels<T, 1>(sm, L, P, reverse, base, lds, [&](long long q, const uint4 (&v)[1]) {
+            Vec<T> o;
+#pragma unroll
+            for (int k = 0; k < V; ++k) o.v[k] = fmaf(elem<T>(v[0], k), sc[k], sh[k]);
+            if (relu) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
+            }
+            o.store(out + q * ld_out + c0);
+        });
     }
 }
 
@@ -315,8 +360,9 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, T* __restrict__ out, long long P, int Cp,
                 int ld_y, int ld_res, int ld_out, const float* __restrict__ scale, const float* __restrict__ shift,
                 int relu) {
+    extern __shared__ __align__(16) float sm[];
     const Lay<T> L(Cp);
-    apply_pass<T>(y, res, out, P, ld_y, ld_res, ld_out, scale, shift, relu, L);
+    apply_pass<T>(y, res, out, P, ld_y, ld_res, ld_out, scale, shift, relu, L, sm, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -348,39 +394,32 @@ __device__ __forceinline__ void bwd_reduce_to_partials_t(const T* __restrict__ g
 #pragma unroll
             for (int i = 0; i < V; ++i) { sc[i] = scale[L.lane * V + i]; sh[i] = shift[L.lane * V + i]; }
         }
-        const long long stride = (long long)gridDim.x * L.R;
-        for (long long p = (long long)blockIdx.x * L.R + L.r; p < P; p += 2 * stride) {
-            uint4 gv[2], yv[2], av[2];
-            bool ok[2];
+        auto acc = [&](const uint4& gq, const uint4& yq, const uint4& aq) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {     // 2 pixels x 3 tensors = 6 independent loads in flight
-                const long long q = p + u * stride;
-                ok[u] = q < P;
-                if (ok[u]) {
-                    gv[u] = ld16<T>(g + q * ld_g + L.lane * V);
-                    yv[u] = ld16<T>(y + q * ld_y + L.lane * V);
-                    if (relu == 1) av[u] = ld16<T>(a + q * ld_a + L.lane * V);
-                }
+            for (int i = 0; i < V; ++i) {
+                const float yy = elem<T>(yq, i);
+                bool on = true;
+                if (relu == 1) on = elem<T>(aq, i) > 0.f;
+                if (relu == 2) on = fmaf(yy, sc[i], sh[i]) > 0.f;
+                const float gg = on ? elem<T>(gq, i) : 0.f;
+                s1[i] += gg;
+                s2[i] = fmaf(gg, yy - mu[i], s2[i]);
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (!ok[u]) continue;
-#pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    const float yy = elem<T>(yv[u], i);
-                    bool on = true;
-                    if (relu == 1) on = elem<T>(av[u], i) > 0.f;
-                    if (relu == 2) on = fmaf(yy, sc[i], sh[i]) > 0.f;
-                    const float gg = on ? elem<T>(gv[u], i) : 0.f;
-                    s1[i] += gg;
-                    s2[i] = fmaf(gg, yy - mu[i], s2[i]);
-                }
-            }
+        };
+        if (relu == 1) {
+            const T* const base[3] = {g, y, a};
+            const int lds[3] = {ld_g, ld_y, ld_a};
+            stream_pixels<T, 3>(sm, L, P, false, base, lds, [&](long long, const uint4 (&v)[3]) { acc(v[0], v[1], v[2]); });
+        } else {
+            const T* const base[2] = {g, y};
+            const int lds[2] = {ld_g, ld_y};
+            stream_pixels<T, 2>(sm, L, P, false, base, lds, [&](long long, const uint4 (&v)[2]) { acc(v[0], v[1], v[1]); });
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) s2[i] *= invstd[L.lane * V + i];
     }
-    // tree sum over the thread rows of each lane (sm: [blockDim][2V])
+    // tree sum over the thread rows of each lane (sm: [blockDim][2V]; aliases the streaming slots)
+    __syncthreads();
     float* mine = sm + threadIdx.x * (2 * V);
 #pragma unroll
     for (int i = 0; i < V; ++i) { mine[i] = s1[i]; mine[V + i] = s2[i]; }
@@ -418,7 +457,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* __restrict__ y,
                      float* __restrict__ partials, long long P, int Cp, int ld_g, int ld_a, int ld_y,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int relu) {
-    extern __shared__ float sm[];  // [BN_THREADS][2*V]
+    extern __shared__ __align__(16) float sm[];  // [BN_THREADS][2*V]
     bwd_reduce_to_partials<T>(g, a, y, partials, P, Cp, ld_g, ld_a, ld_y, mean, invstd, relu, sm);
 }
 
@@ -457,7 +496,7 @@ __device__ __forceinline__ void bwd_elemt_pass_t(const T* __restrict__ g, const 
                                                int ld_y, int ld_dy, int ld_dres, const float* __restrict__ mean,
                                                const float* __restrict__ invstd, const float* __restrict__ scale,
                                                const float* __restrict__ c1, const float* __restrict__ c2,
-                                               int acc_dy, int acc_dres, const Lay<T>& L,
+                                               int acc_dy, int acc_dres, const Lay<T>& L, float* sm, bool reverse,
                                                const float* __restrict__ shift = nullptr) {
     constexpr int V = Vec<T>::N;
     constexpr int relu = RELU;
@@ -473,12 +512,8 @@ __device__ __forceinline__ void bwd_elemt_pass_t(const T* __restrict__ g, const 
 #pragma unroll
         for (int k = 0; k < V; ++k) sh[k] = shift[c0 + k];
     }
-    const long long stride = (long long)gridDim.x * L.R;
-    for (long long q = (long long)blockIdx.x * L.R + L.r; q < P; q += stride) {
-        uint4 gv, yv, av, od, orr;
-        gv = ld16<T>(g + q * ld_g + c0);
-        yv = ld16<T>(y + q * ld_y + c0);
-        if (relu == 1) av = ld16<T>(a + q * ld_a + c0);
+    auto one = [&](long long q, const uint4& gv, const uint4& yv, const uint4& av) {
+        uint4 od, orr;
         if (acc_dy) od = ld16<T>(dy + q * ld_dy + c0);
         if (dres != nullptr && acc_dres) orr = ld16<T>(dres + q * ld_dres + c0);
         Vec<T> o, gm;
@@ -503,6 +538,15 @@ __device__ __forceinline__ void bwd_elemt_pass_t(const T* __restrict__ g, const 
             }
             gm.store(dres + q * ld_dres + c0);
         }
+    };
+    if (relu == 1) {
+        const T* const base[3] = {g, y, a};
+        const int lds[3] = {ld_g, ld_y, ld_a};
+        stream_pixels<T, 3>(sm, L, P, reverse, base, lds, [&](long long q, const uint4 (&v)[3]) { one(q, v[0], v[1], v[2]); });
+    } else {
+        const T* const base[2] = {g, y};
+        const int lds[2] = {ld_g, ld_y};
+        stream_pixels<T, 2>(sm, L, P, reverse, base, lds, [&](long long q, const uint4 (&v)[2]) { one(q, v[0], v[1], v[1]); });
     }
 }
 
@@ -512,11 +556,11 @@ __device__ __forceinline__ void bwd_elemt_pass(const T* __restrict__ g, const T*
                                                int ld_y, int ld_dy, int ld_dres, const float* __restrict__ mean,
                                                const float* __restrict__ invstd, const float* __restrict__ scale,
                                                const float* __restrict__ c1, const float* __restrict__ c2, int relu,
-                                               int acc_dy, int acc_dres, const Lay<T>& L) {
+                                               int acc_dy, int acc_dres, const Lay<T>& L, float* sm) {
     if (relu) bwd_elemt_pass_t<T, 1, true>(g, a, y, dy, dres, P, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1,
-                                           c2, acc_dy, acc_dres, L);
+                                           c2, acc_dy, acc_dres, L, sm, false);
     else bwd_elemt_pass_t<T, 0, true>(g, a, y, dy, dres, P, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2,
-                                      acc_dy, acc_dres, L);
+                                      acc_dy, acc_dres, L, sm, false);
 }
 
 template <typename T>
@@ -525,15 +569,28 @@ bn_bwd_elemt_kernel(const T* __restrict__ g, const T* __restrict__ a, const T* _
                     T* __restrict__ dres, long long P, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
                     const float* __restrict__ c1, const float* __restrict__ c2, int relu, int acc_dy, int acc_dres) {
+    extern __shared__ __align__(16) float sm[];
     const Lay<T> L(Cp);
     bwd_elemt_pass<T>(g, a, y, dy, dres, P, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy,
-                      acc_dres, L);
+                      acc_dres, L, sm);
 }
 
 // ---------------------------------------------------------------------------
 // fused single-rank training BN: one cooperative launch per direction
 // ---------------------------------------------------------------------------
+// optional phase timestamps (globaltimer ns) of CTA 0, for tools/microbench_bn.py; null in production
+static unsigned long long* g_bn_prof = nullptr;
+void bn_debug_set_prof(unsigned long long* p) { g_bn_prof = p; }
+__device__ __forceinline__ void prof_mark(unsigned long long* prof, int i) {
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        prof[i] = t;
+    }
+}
+
 struct BnFwdArgs {
+    unsigned long long* prof;
     const void *y, *res;
     void* out;
     float* partials;
@@ -549,21 +606,29 @@ struct BnFwdArgs {
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_fwd_fused_kernel(const BnFwdArgs A) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     cg::grid_group grid = cg::this_grid();
+    prof_mark(A.prof, 0);
     stats_to_partials<T>((const T*)A.y, A.partials, A.P, A.Cp, A.ld_y, sm);
+    prof_mark(A.prof, 1);
     grid.sync();
+    prof_mark(A.prof, 2);
     const int warps = blockDim.x >> 5;
     for (int c = blockIdx.x * warps + (threadIdx.x >> 5); c < A.Cp; c += gridDim.x * warps)
         finalize_channel(c, A.partials, gridDim.x, A.C, A.Cp, A.gamma, A.beta, A.running_mean, A.running_var, A.momentum,
                          A.eps, A.mean, A.invstd, A.scale, A.shift, 3LL * A.Cp);
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.nbt != nullptr) *A.nbt += 1;
+    prof_mark(A.prof, 3);
     grid.sync();
+    prof_mark(A.prof, 4);
     const Lay<T> L(A.Cp);
-    apply_pass<T>((const T*)A.y, (const T*)A.res, (T*)A.out, A.P, A.ld_y, A.ld_res, A.ld_out, A.scale, A.shift, A.relu, L);
+    apply_pass<T>((const T*)A.y, (const T*)A.res, (T*)A.out, A.P, A.ld_y, A.ld_res, A.ld_out, A.scale, A.shift, A.relu, L,
+                  sm, true);
+    prof_mark(A.prof, 5);
 }
 
 struct BnBwdArgs {
+    unsigned long long* prof;
     const void *g, *a, *y;
     void *dy, *dres;
     float* partials;
@@ -577,11 +642,14 @@ struct BnBwdArgs {
 template <typename T, int RELU, bool DRES>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_fused_kernel(const BnBwdArgs A) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     cg::grid_group grid = cg::this_grid();
+    prof_mark(A.prof, 0);
     bwd_reduce_to_partials_t<T, RELU>((const T*)A.g, (const T*)A.a, (const T*)A.y, A.partials, A.P, A.Cp, A.ld_g, A.ld_a,
                                       A.ld_y, A.mean, A.invstd, sm, A.scale, A.shift);
+    prof_mark(A.prof, 1);
     grid.sync();
+    prof_mark(A.prof, 2);
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int n_parts = gridDim.x;
     for (int c = blockIdx.x * warps + (threadIdx.x >> 5); c < A.Cp; c += gridDim.x * warps) {
@@ -602,11 +670,14 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
             }
         }
     }
+    prof_mark(A.prof, 3);
     grid.sync();
+    prof_mark(A.prof, 4);
     const Lay<T> L(A.Cp);
     bwd_elemt_pass_t<T, RELU, DRES>((const T*)A.g, (const T*)A.a, (const T*)A.y, (T*)A.dy, (T*)A.dres, A.P, A.ld_g, A.ld_a,
                                     A.ld_y, A.ld_dy, A.ld_dres, A.mean, A.invstd, A.scale, A.c1, A.c2, A.acc_dy, A.acc_dres,
-                                    L, A.shift);
+                                    L, sm, true, A.shift);
+    prof_mark(A.prof, 5);
 }
 
 // ---------------------------------------------------------------------------
@@ -655,7 +726,7 @@ template <typename T>
 static int launch_fwd_fused(BnFwdArgs& A, cudaStream_t st) {
     constexpr int V = Vec<T>::N;
     static int cap = 0;
-    const size_t smem = (size_t)BN_THREADS * (2 * V + 1) * sizeof(float);
+    const size_t smem = kPipeBytes;   // streaming slots; the merge scratch aliases them
     const int grid = coop_grid(bn_fwd_fused_kernel<T>, smem, A.P, A.Cp, V, &cap);
     if (grid < 1) return VAE2_ERR_CUDA;
     void* args[] = {(void*)&A};
@@ -669,7 +740,7 @@ template <typename T, int RELU, bool DRES>
 static int launch_bwd_fused_t(BnBwdArgs& A, cudaStream_t st) {
     constexpr int V = Vec<T>::N;
     static int cap = 0;
-    const size_t smem = (size_t)BN_THREADS * 2 * V * sizeof(float);
+    const size_t smem = kPipeBytes;   // streaming slots; the merge scratch aliases them
     const int grid = coop_grid(bn_bwd_fused_kernel<T, RELU, DRES>, smem, A.P, A.Cp, V, &cap);
     if (grid < 1) return VAE2_ERR_CUDA;
     void* args[] = {(void*)&A};
@@ -698,7 +769,7 @@ int bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int
                  float* shift, int relu, cudaStream_t st) {
     const int V = vec_of(dtype);
     if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V) || Cp / V > BN_THREADS || P < 1) return VAE2_ERR_ARG;
-    BnFwdArgs A{y, res, out, partials, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
+    BnFwdArgs A{g_bn_prof, y, res, out, partials, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
                 nbt, momentum, eps, mean, invstd, scale, shift};
     return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
 }
@@ -711,7 +782,7 @@ int bn_bwd_fused(const void* g, const void* a, const void* y, void* dy, void* dr
     if (Cp % V || ld_g % V || ld_y % V || ld_dy % V || (relu == 1 && (a == nullptr || ld_a % V)) ||
         (relu == 2 && shift == nullptr) || relu < 0 || relu > 2 || (dres && ld_dres % V) || Cp / V > BN_THREADS || P < 1)
         return VAE2_ERR_ARG;
-    BnBwdArgs A{g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
+    BnBwdArgs A{g_bn_prof, g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
                 accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, 1.0f / (float)P};
     return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
 }
@@ -721,7 +792,7 @@ int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, lon
     if (Cp % V || ld % V || Cp / V > BN_THREADS) return VAE2_ERR_ARG;
     const int grid = reduce_grid(P, Cp, V);
     if (n_partials_out) *n_partials_out = grid;
-    const size_t smem = (size_t)BN_THREADS * (2 * V + 1) * sizeof(float);
+    const size_t smem = kPipeBytes;   // streaming slots; the merge scratch aliases them
     if (dtype == VAE2_DT_F32)
         bn_stats_kernel<float><<<grid, BN_THREADS, smem, st>>>((const float*)y, partials, P, Cp, ld);
     else
@@ -756,9 +827,9 @@ int bn_apply(const void* y, const void* res, void* out, int dtype, long long P, 
     if (Cp / V > BN_THREADS) return VAE2_ERR_ARG;
     const int grid = elemt_grid(P, Cp, V);
     if (dtype == VAE2_DT_F32)
-        bn_apply_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)y, (const float*)res, (float*)out, P, Cp, ld_y, ld_res, ld_out, scale, shift, relu);
+        bn_apply_kernel<float><<<grid, BN_THREADS, kPipeBytes, st>>>((const float*)y, (const float*)res, (float*)out, P, Cp, ld_y, ld_res, ld_out, scale, shift, relu);
     else
-        bn_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, P, Cp, ld_y, ld_res, ld_out, scale, shift, relu);
+        bn_apply_kernel<__nv_bfloat16><<<grid, BN_THREADS, kPipeBytes, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, P, Cp, ld_y, ld_res, ld_out, scale, shift, relu);
     return check_launch();
 }
 
@@ -769,7 +840,7 @@ int bn_bwd_reduce(const void* g, const void* a, const void* y, float* partials, 
     if (Cp % V || ld_g % V || ld_y % V || Cp / V > BN_THREADS) return VAE2_ERR_ARG;
     const int grid = reduce_grid(P, Cp, V);
     if (n_partials_out) *n_partials_out = grid;
-    const size_t smem = (size_t)BN_THREADS * 2 * V * sizeof(float);
+    const size_t smem = kPipeBytes;   // streaming slots; the merge scratch aliases them
     if (dtype == VAE2_DT_F32)
         bn_bwd_reduce_kernel<float><<<grid, BN_THREADS, smem, st>>>((const float*)g, (const float*)a, (const float*)y, partials, P, Cp, ld_g, ld_a, ld_y, mean, invstd, relu);
     else
@@ -798,9 +869,9 @@ int bn_bwd_elemt(const void* g, const void* a, const void* y, void* dy, void* dr
     if (Cp / V > BN_THREADS) return VAE2_ERR_ARG;
     const int grid = elemt_grid(P, Cp, V);
     if (dtype == VAE2_DT_F32)
-        bn_bwd_elemt_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)g, (const float*)a, (const float*)y, (float*)dy, (float*)dres, P, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy, acc_dres);
+        bn_bwd_elemt_kernel<float><<<grid, BN_THREADS, kPipeBytes, st>>>((const float*)g, (const float*)a, (const float*)y, (float*)dy, (float*)dres, P, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy, acc_dres);
     else
-        bn_bwd_elemt_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, P, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy, acc_dres);
+        bn_bwd_elemt_kernel<__nv_bfloat16><<<grid, BN_THREADS, kPipeBytes, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, P, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd, scale, c1, c2, relu, acc_dy, acc_dres);
     return check_launch();
 }
 

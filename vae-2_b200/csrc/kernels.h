@@ -55,6 +55,7 @@ int bn_apply(const void* y, const void* res, void* out, int dtype, long long P, 
 int bn_bwd_reduce(const void* g, const void* a, const void* y, float* partials, int* n_partials_out, int dtype,
                   long long P, int Cp, int ld_g, int ld_a, int ld_y, const float* mean, const float* invstd, int relu,
                   cudaStream_t st);
+void bn_debug_set_prof(unsigned long long* p);
 int bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int dtype, long long P, int C, int Cp,
                  int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale,

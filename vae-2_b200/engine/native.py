@@ -77,6 +77,7 @@ _PROTOS = {
     "vae2_bn_bwd_coeffs": [vp, i32, i32, f32, vp, vp, i32, vp, vp, vp, vp],
     "vae2_bn_bwd_elemt": [vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                           i32, i32, i32, vp],
+    "vae2_debug_bn_phase_times": [vp],
     "vae2_bn_fwd_fused": [vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp,
                           vp, i32, vp],
     "vae2_bn_bwd_fused": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
