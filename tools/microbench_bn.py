@@ -21,6 +21,8 @@ try:
 except Exception:
     pass
 SHAPES = [(524288, 256), (524288, 32), (131072, 48), (32768, 80), (8192, 144)]
+if os.environ.get("BN_SHAPES"):
+    SHAPES = [tuple(int(v) for v in t.split("x")) for t in os.environ["BN_SHAPES"].split(",")]
 st = torch.cuda.current_stream().cuda_stream
 f32 = dict(dtype=torch.float32, device=dev)
 

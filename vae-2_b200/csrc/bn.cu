@@ -18,6 +18,7 @@
 // elementwise pass.  The stand-alone kernels stay for SyncBN (a collective sits between the phases)
 // and for eval-mode statistics.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -211,6 +212,24 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
     n = nn;
 }
 
+// 5-step butterfly of Chan merges; the symmetric form leaves every lane with the same result
+__device__ __forceinline__ void warp_tree_merge(float& n, float& mean, float& m2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+        const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+        const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+        const float nn = n + nb;
+        if (nn > 0.f) {
+            const float d = mb - mean;
+            const float f = nb / nn;
+            mean = (nb > 0.f && n > 0.f) ? mean + d * f : (nb > 0.f ? mb : mean);
+            m2 = m2 + m2b + ((nb > 0.f && n > 0.f) ? d * d * n * f : 0.f);
+        }
+        n = nn;
+    }
+}
+
 // One WARP per channel: lanes fold partials lane, lane+32, ... then a 5-step shuffle tree of Chan
 // merges (the merge is associative), so the latency is ~n_parts/32 dependent loads, not n_parts.
 __device__ __forceinline__ void warp_merge_parts(const float* __restrict__ parts, int n_parts, int Cp, int c,
@@ -225,28 +244,15 @@ __device__ __forceinline__ void warp_merge_parts(const float* __restrict__ parts
             const int k = k0 + 32 * j;
             const bool valid = k < n_parts;
             const float* p = parts + (long long)(valid ? k : k0) * part_stride;
-            a[j][0] = valid ? p[c] : 0.f;          // count 0: skipped by the merge
-            a[j][1] = p[Cp + c];
-            a[j][2] = p[2 * Cp + c];
+            // __ldcg: in the fused kernels these were written by other CTAs earlier in the same launch
+            a[j][0] = valid ? __ldcg(p + c) : 0.f;          // count 0: skipped by the merge
+            a[j][1] = __ldcg(p + Cp + c);
+            a[j][2] = __ldcg(p + 2 * Cp + c);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) chan_merge(n, mean, m2, a[j][0], a[j][1], a[j][2]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float nb = __shfl_xor_sync(0xffffffffu, n, o);
-        const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
-        const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
-        // symmetric form so that both partners end with the same value
-        const float nn = n + nb;
-        if (nn > 0.f) {
-            const float d = mb - mean;
-            const float f = nb / nn;
-            mean = (nb > 0.f && n > 0.f) ? mean + d * f : (nb > 0.f ? mb : mean);
-            m2 = m2 + m2b + ((nb > 0.f && n > 0.f) ? d * d * n * f : 0.f);
-        }
-        n = nn;
-    }
+    warp_tree_merge(n, mean, m2);
 }
 
 // merge n_parts partial sets -> one (count, mean, M2) set  (per-rank partial for SyncBN all-gather)
@@ -324,6 +330,8 @@ __device__ __forceinline__ void apply_pass(const T* __restrict__ y, const T* __r
     if (!L.active) return;
     float sc[V], sh[V];
 #pragma unroll
+    // (fused kernels: written by another CTA before the grid barrier and first read here, so the L1 path is safe;
+    //  going to L2 for these few hot addresses from every thread of the grid serialises on one L2 slice)
     for (int k = 0; k < V; ++k) { sc[k] = scale[L.lane * V + k]; sh[k] = shift[L.lane * V + k]; }
     const int c0 = L.lane * V;
     if (res != nullptr) {
@@ -609,14 +617,78 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
     extern __shared__ __align__(16) float sm[];
     cg::grid_group grid = cg::this_grid();
     prof_mark(A.prof, 0);
+    // parameters of the channel this CTA will finalize: cold in HBM, so fetched under the statistics pass
+    float gm0 = 0.f, bt0 = 0.f, rm00 = 0.f, rv00 = 0.f;
+    if (threadIdx.x == 0 && (int)blockIdx.x < A.C) {
+        gm0 = A.gamma[blockIdx.x]; bt0 = A.beta[blockIdx.x];
+        if (A.running_mean != nullptr) { rm00 = A.running_mean[blockIdx.x]; rv00 = A.running_var[blockIdx.x]; }
+    }
     stats_to_partials<T>((const T*)A.y, A.partials, A.P, A.Cp, A.ld_y, sm);
     prof_mark(A.prof, 1);
     grid.sync();
     prof_mark(A.prof, 2);
-    const int warps = blockDim.x >> 5;
-    for (int c = blockIdx.x * warps + (threadIdx.x >> 5); c < A.Cp; c += gridDim.x * warps)
-        finalize_channel(c, A.partials, gridDim.x, A.C, A.Cp, A.gamma, A.beta, A.running_mean, A.running_var, A.momentum,
-                         A.eps, A.mean, A.invstd, A.scale, A.shift, 3LL * A.Cp);
+    // One CTA per channel: every thread fetches <= 3 partials at once (one L2 round trip for the whole merge),
+    // warp butterflies, then the 8 warp results meet in shared memory.
+    for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {
+        const int n_parts = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float gm = gm0, bt = bt0, rm0 = rm00, rv0 = rv00;      // first channel: fetched before the statistics pass
+        if (threadIdx.x == 0 && c < A.C && c != blockIdx.x) {
+            gm = A.gamma[c]; bt = A.beta[c];
+            if (A.running_mean != nullptr) { rm0 = A.running_mean[c]; rv0 = A.running_var[c]; }
+        }
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        if (c < A.C) {
+            float a[3][3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int k = threadIdx.x + j * BN_THREADS;
+                const bool valid = k < n_parts;
+                const float* p = A.partials + (long long)(valid ? k : 0) * 3 * A.Cp;
+                a[j][0] = valid ? __ldcg(p + c) : 0.f;
+                a[j][1] = __ldcg(p + A.Cp + c);
+                a[j][2] = __ldcg(p + 2 * A.Cp + c);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) chan_merge(n, mean, m2, a[j][0], a[j][1], a[j][2]);
+            warp_tree_merge(n, mean, m2);
+        }
+        __syncthreads();
+        if (lane == 0) { sm[warp * 3] = n; sm[warp * 3 + 1] = mean; sm[warp * 3 + 2] = m2; }
+        __syncthreads();
+        if (warp == 0) {
+            const int w = lane & 7;
+            n = sm[w * 3]; mean = sm[w * 3 + 1]; m2 = sm[w * 3 + 2];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {      // butterfly over the 8 warp results (lanes 8.. mirror lanes 0..7)
+                const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+                const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+                const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+                const float nn = n + nb;
+                if (nn > 0.f) {
+                    const float d = mb - mean;
+                    const float f = nb / nn;
+                    mean = (nb > 0.f && n > 0.f) ? mean + d * f : (nb > 0.f ? mb : mean);
+                    m2 = m2 + m2b + ((nb > 0.f && n > 0.f) ? d * d * n * f : 0.f);
+                }
+                n = nn;
+            }
+            if (lane == 0) {
+                if (c >= A.C) {
+                    A.mean[c] = 0.f; A.invstd[c] = 0.f; A.scale[c] = 0.f; A.shift[c] = 0.f;
+                } else {
+                    const float var = m2 / n;
+                    const float invstd = rsqrtf(var + A.eps);
+                    const float sc = gm * invstd;
+                    A.mean[c] = mean; A.invstd[c] = invstd; A.scale[c] = sc; A.shift[c] = bt - mean * sc;
+                    if (A.running_mean != nullptr) {
+                        const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
+                        A.running_mean[c] = (1.f - A.momentum) * rm0 + A.momentum * mean;
+                        A.running_var[c] = (1.f - A.momentum) * rv0 + A.momentum * unbiased;
+                    }
+                }
+            }
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.nbt != nullptr) *A.nbt += 1;
     prof_mark(A.prof, 3);
     grid.sync();
@@ -650,18 +722,27 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
     prof_mark(A.prof, 1);
     grid.sync();
     prof_mark(A.prof, 2);
-    const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    const int n_parts = gridDim.x;
-    for (int c = blockIdx.x * warps + (threadIdx.x >> 5); c < A.Cp; c += gridDim.x * warps) {
+    for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {      // one CTA per channel, one L2 round trip
+        const int n_parts = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         float s1 = 0.f, s2 = 0.f;
-        if (c < A.C)
-#pragma unroll 8
-            for (int k = lane; k < n_parts; k += 32) {
-                s1 += A.partials[(long long)k * 2 * A.Cp + c];
-                s2 += A.partials[(long long)k * 2 * A.Cp + A.Cp + c];
+        if (c < A.C) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int k = threadIdx.x + j * BN_THREADS;
+                if (k < n_parts) {
+                    s1 += __ldcg(A.partials + (long long)k * 2 * A.Cp + c);
+                    s2 += __ldcg(A.partials + (long long)k * 2 * A.Cp + A.Cp + c);
+                }
             }
+        }
         s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (lane == 0) {
+        __syncthreads();
+        if (lane == 0) { sm[warp * 2] = s1; sm[warp * 2 + 1] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s1 = 0.f; s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < BN_THREADS / 32; ++w) { s1 += sm[w * 2]; s2 += sm[w * 2 + 1]; }
             A.c1[c] = s1 * A.inv_count;
             A.c2[c] = s2 * A.inv_count;
             if (c < A.C) {
@@ -719,6 +800,9 @@ static int coop_grid(K kernel, size_t smem, long long P, int Cp, int V, int* cac
     if (need < 1) need = 1;
     if (need > BN_MAX_PARTS) need = BN_MAX_PARTS;
     if (need > *cache) need = *cache;
+    static int env_cap = -1;
+    if (env_cap < 0) { const char* e = getenv("VAE2_BN_MAXGRID"); env_cap = e ? atoi(e) : 0; }
+    if (env_cap > 0 && need > env_cap) need = env_cap;
     return (int)need;
 }
 
