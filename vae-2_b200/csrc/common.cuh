@@ -92,6 +92,24 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return v;
 }
 
+// Division by a run-time constant without the ~25-instruction integer divide: q = n / d for 0 <= n < 2^31
+// (Granlund-Montgomery round-up method: m = floor(2^32 * (2^l - d) / d) + 1, q = (mulhi(m, n) + n) >> l).
+struct FastDiv {
+    unsigned d, m, l;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    f.l = l;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
+    return (unsigned)(((unsigned long long)__umulhi(f.m, n) + n) >> f.l);
+}
+
 // Grid sizing for streaming kernels: a multiple of the SM count, capped by the work.
 inline int stream_grid(long long work_items, int per_block, int waves = 8) {
     long long need = (work_items + per_block - 1) / per_block;

@@ -43,7 +43,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 template <typename TA, int BM, int BN, int MODE>
 __global__ void __launch_bounds__(NTHREADS)
 conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, const float* __restrict__ bias,
-                  void* __restrict__ Cdst, ConvGeom g, int accumulate, int k_per_split) {
+                  void* __restrict__ Cdst, ConvGeom g, int accumulate, int k_per_split, FastDiv div_wo, FastDiv div_ho) {
     constexpr int AS = BM + 4;               // smem row stride (floats); keeps 16B alignment
     constexpr int A_VECS = BM * BK / 4;      // float4 per A tile
     constexpr int A_PER_T = A_VECS / NTHREADS;
@@ -237,14 +237,18 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
                 const long long p = k0 + a_kk[j];
                 ar[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (a_ok[j] && p < k_end) {
-                    const int wo = (int)(p % g.Wo);
-                    const long long t = p / g.Wo;
-                    const int ho = (int)(t % g.Ho);
-                    const int nb = (int)(t / g.Ho);
-                    const int ih = ho * g.stride - g.pad + a_tap_ky[j];
-                    const int iw = wo * g.stride - g.pad + a_tap_kx[j];
-                    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
-                        ar[j] = load4<TA>(Asrc + (((long long)nb * g.H + ih) * g.W + iw) * g.ldx + a_ci[j]);
+                    if (g.k == 1 && g.stride == 1) {
+                        ar[j] = load4<TA>(Asrc + p * g.ldx + a_ci[j]);          // 1x1: output pixel == input pixel
+                    } else {
+                        const unsigned t = fast_div((unsigned)p, div_wo);       // pixel index < 2^31 (checked by the launcher)
+                        const int wo = (int)((unsigned)p - t * div_wo.d);
+                        const unsigned nb = fast_div(t, div_ho);
+                        const int ho = (int)(t - nb * div_ho.d);
+                        const int ih = ho * g.stride - g.pad + a_tap_ky[j];
+                        const int iw = wo * g.stride - g.pad + a_tap_kx[j];
+                        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                            ar[j] = load4<TA>(Asrc + (((long long)nb * g.H + ih) * g.W + iw) * g.ldx + a_ci[j]);
+                    }
                 }
             }
             br = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -321,14 +325,21 @@ static int launch_igemm(const void* A, const void* Bm, const float* bias, void* 
     if (MODE == MODE_FWD) { M = (long long)g.B * g.Ho * g.Wo; N = g.Cout_p; }
     else if (MODE == MODE_DGRAD) { M = (long long)g.B * g.H * g.W; N = g.Cin_p; }
     else { M = (long long)taps * g.Cin_p; N = g.Cout_p; }
-    const int bn = pick_bn(N);
+    const FastDiv div_wo = make_fastdiv((unsigned)g.Wo), div_ho = make_fastdiv((unsigned)g.Ho);
+    if ((long long)g.B * g.Ho * g.Wo >= (1LL << 31)) return VAE2_ERR_UNSUPPORTED;
+    int bn = pick_bn(N);
+    if (MODE == MODE_WGRAD) {
+        // both tile shapes pad M (taps*Cin_p rows) and N; take the one that wastes less work
+        const long long w64 = ((M + 127) / 128 * 128) * ((N + 63) / 64 * 64), w32 = ((M + 255) / 256 * 256) * ((N + 31) / 32 * 32);
+        bn = (w64 <= w32) ? 64 : 32;
+    }
     if (MODE != MODE_WGRAD) {
         if (bn == 64) {
             dim3 grid((unsigned)((M + 127) / 128), (N + 63) / 64);
-            conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0);
+            conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
         } else {
             dim3 grid((unsigned)((M + 255) / 256), (N + 31) / 32);
-            conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0);
+            conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
         }
     } else {
         const long long Ktot = (long long)g.B * g.Ho * g.Wo;
@@ -343,22 +354,30 @@ static int launch_igemm(const void* A, const void* Bm, const float* bias, void* 
         splits = (Ktot + kps - 1) / kps;
         dim3 grid((unsigned)((M + bm - 1) / bm), (N + bn - 1) / bn, (unsigned)splits);
         if (bn == 64)
-            conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, nullptr, C, g, 0, (int)kps);
+            conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, nullptr, C, g, 0, (int)kps, div_wo, div_ho);
         else
-            conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, nullptr, C, g, 0, (int)kps);
+            conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, nullptr, C, g, 0, (int)kps, div_wo, div_ho);
     }
     return check_launch();
 }
 
 int conv_fwd_simt(const void* x, const float* wp, const float* bias, void* y, int dtype, const ConvGeom& g, cudaStream_t st) {
     if (int e = check_geom(g, dtype)) return e;
-    if (dtype == VAE2_DT_F32) return launch_igemm<float, MODE_FWD>(x, wp, bias, y, g, 0, st);
+    if (dtype == VAE2_DT_F32) {
+        const int e = conv_fwd_direct((const float*)x, wp, bias, (float*)y, g, st);   // register-tiled direct conv first
+        if (e != VAE2_ERR_UNSUPPORTED) return e;
+        return launch_igemm<float, MODE_FWD>(x, wp, bias, y, g, 0, st);
+    }
     return launch_igemm<__nv_bfloat16, MODE_FWD>(x, wp, bias, y, g, 0, st);
 }
 
 int conv_dgrad_simt(const void* dy, const float* wpT, void* dx, int dtype, const ConvGeom& g, int accumulate, cudaStream_t st) {
     if (int e = check_geom(g, dtype)) return e;
-    if (dtype == VAE2_DT_F32) return launch_igemm<float, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st);
+    if (dtype == VAE2_DT_F32) {
+        const int e = conv_dgrad_direct((const float*)dy, wpT, (float*)dx, g, accumulate, st);
+        if (e != VAE2_ERR_UNSUPPORTED) return e;
+        return launch_igemm<float, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st);
+    }
     return launch_igemm<__nv_bfloat16, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st);
 }
 

@@ -42,6 +42,10 @@ int conv_wgrad_simt(const void* x, const void* dy, float* dwp, int dtype, const 
 int bias_grad(const void* dy, float* dbias, int dtype, long long P, int C, int ld, int accumulate, cudaStream_t st);
 
 // bn.cu
+// conv_direct.cu (fp32 register-tiled direct conv; VAE2_ERR_UNSUPPORTED -> caller falls back to the implicit GEMM)
+int conv_fwd_direct(const float* x, const float* wp, const float* bias, float* y, const ConvGeom& g, cudaStream_t st);
+int conv_dgrad_direct(const float* dy, const float* wpT, float* dx, const ConvGeom& g, int accumulate, cudaStream_t st);
+
 int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, long long P, int Cp, int ld, cudaStream_t st);
 int bn_stats_max_partials();
 int bn_merge(const float* partials, int n_partials, int Cp, float* merged, cudaStream_t st);
