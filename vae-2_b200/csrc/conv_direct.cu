@@ -34,8 +34,11 @@ struct Params {
     int B, IH, IW, lda, OH, OW, ldo;
     int CIN, COUT;           // K lanes per tap (multiple of 4); output lanes = TN * nsplit
     int taps, stride;
-    int dh[9], dw[9];        // input pixel of output (oh, ow) under tap t: (oh*stride + dh[t], ow*stride + dw[t])
+    int dh[9], dw[9], wt[9]; // grid point (i, j) under tap t reads input pixel (i*stride + dh[t], j*stride + dw[t])
+                             // and weight slice wt[t]
     int dh_min, dw_min;
+    int MH, MW;              // grid of output points handled by this launch
+    int sO, oh_off, ow_off;  // grid point (i, j) is output pixel (i*sO + oh_off, j*sO + ow_off)
     int nsplit, groups;      // threads = groups * nsplit; thread = (channel slice, pixel group)
     int PW, PH;              // output patch: PW columns x PH rows (PH = TM * row groups)
     int PWin, PHin, pitch;   // staged input patch (pixels) and its pixel pitch in floats (4 * odd)
@@ -90,7 +93,7 @@ conv_direct_kernel(const Params p) {
         const int tap = s / p.nblk, cb = s - tap * p.nblk;
         const int c0 = cb * p.kblk;
         const int kb = min(p.kblk, p.CIN - c0);
-        const float4* src = reinterpret_cast<const float4*>(p.w + ((long long)tap * p.CIN + c0) * p.COUT);
+        const float4* src = reinterpret_cast<const float4*>(p.w + ((long long)p.wt[tap] * p.CIN + c0) * p.COUT);
         float4* dst = reinterpret_cast<float4*>(wsm + (s & 1) * wstage);
         const int nvec = kb * p.COUT / 4;
         for (int v = tid; v < nvec; v += nthreads) cp_async16(dst + v, src + v);
@@ -162,15 +165,17 @@ conv_direct_kernel(const Params p) {
         __syncthreads();                 // everyone is done with buffer s&1 before block s+2 overwrites it
     }
 
-    const int ow = ow0 + col;
-    if (ow >= p.OW) return;
+    const int gj = ow0 + col;
+    if (gj >= p.MW) return;
+    const int ow = gj * p.sO + p.ow_off;
     float bv[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) bv[j] = p.bias != nullptr ? p.bias[n0 + j] : 0.f;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const int oh = oh0 + rowg * TM + i;
-        if (oh >= p.OH) continue;
+        const int gi = oh0 + rowg * TM + i;
+        if (gi >= p.MH) continue;
+        const int oh = gi * p.sO + p.oh_off;
         float* o = p.out + (((long long)b * p.OH + oh) * p.OW + ow) * p.ldo + n0;
 #pragma unroll
         for (int j = 0; j < TN; j += 4) {
@@ -218,10 +223,10 @@ static int launch(Params& p, cudaStream_t st) {
     }
     // patch: a warp is PW = 32 columns (fewer for narrow images) x TM rows; row groups until ~128-192 threads
     int pw = 32;
-    while (pw > 4 && pw / 2 >= p.OW) pw >>= 1;
+    while (pw > 4 && pw / 2 >= p.MW) pw >>= 1;
     p.PW = pw;
     int rowgroups = 1;
-    while (pw * rowgroups * 2 * p.nsplit <= 192 && rowgroups * TM < p.OH) rowgroups *= 2;
+    while (pw * rowgroups * 2 * p.nsplit <= 192 && rowgroups * TM < p.MH) rowgroups *= 2;
     p.pitch = ((p.CIN / 4) % 2 == 1) ? p.CIN : p.CIN + 4;          // 4 * odd words
     // weight block: all input channels of a tap when two such blocks fit 44 KB, else fewer
     int kblk = (22 * 1024 / 4 / p.COUT) / 4 * 4;
@@ -229,6 +234,16 @@ static int launch(Params& p, cudaStream_t st) {
     if (kblk > p.CIN) kblk = p.CIN;
     p.kblk = kblk;
     p.nblk = (p.CIN + kblk - 1) / kblk;
+    // small images: shrink the patch (never below 64 threads) until the grid covers the GPU about twice
+    auto n_tiles = [&](int pw_, int rg_) {
+        return (long long)p.B * ((p.MW + pw_ - 1) / pw_) * ((p.MH + rg_ * TM - 1) / (rg_ * TM));
+    };
+    while (rowgroups > 1 && pw * (rowgroups / 2) * p.nsplit >= 64 && n_tiles(pw, rowgroups) < 2 * kNumSMs) rowgroups /= 2;
+    while (pw > 8 && (pw / 2) * rowgroups * p.nsplit >= 64 && n_tiles(pw, rowgroups) < 2 * kNumSMs) pw >>= 1;
+    // too few warps to hide latency (a few fat CTAs): the GEMM tiling spreads the same work over more of them.
+    // The stride-2 data gradient stays here regardless: the GEMM path spends 3/4 of its FMAs on structural zeros.
+    if (p.sO == 1 && n_tiles(pw, rowgroups) * ((pw * rowgroups * p.nsplit + 31) / 32) < 8LL * kNumSMs) return VAE2_ERR_UNSUPPORTED;
+    p.PW = pw;
     size_t smem = 0;
     for (;; rowgroups /= 2) {
         p.PH = rowgroups * TM;
@@ -240,8 +255,8 @@ static int launch(Params& p, cudaStream_t st) {
     if (smem > 200 * 1024) return VAE2_ERR_UNSUPPORTED;
     p.groups = p.PW * rowgroups;
     if (p.groups * p.nsplit > 192) return VAE2_ERR_UNSUPPORTED;
-    p.tiles_w = (p.OW + p.PW - 1) / p.PW;
-    p.tiles_h = (p.OH + p.PH - 1) / p.PH;
+    p.tiles_w = (p.MW + p.PW - 1) / p.PW;
+    p.tiles_h = (p.MH + p.PH - 1) / p.PH;
     const int grid = p.B * p.tiles_w * p.tiles_h;
     switch (tn) {
         case 24: return launch_t<24>(p, smem, grid, st);
@@ -260,21 +275,49 @@ int conv_fwd_direct(const float* x, const float* wp, const float* bias, float* y
     p.a = x; p.w = wp; p.bias = bias; p.out = y;
     p.B = g.B; p.IH = g.H; p.IW = g.W; p.lda = g.ldx; p.OH = g.Ho; p.OW = g.Wo; p.ldo = g.ldy;
     p.CIN = g.Cin_p; p.COUT = g.Cout_p; p.taps = g.k * g.k; p.stride = g.stride;
-    for (int t = 0; t < p.taps; ++t) { p.dh[t] = t / g.k - g.pad; p.dw[t] = t % g.k - g.pad; }
+    for (int t = 0; t < p.taps; ++t) { p.dh[t] = t / g.k - g.pad; p.dw[t] = t % g.k - g.pad; p.wt[t] = t; }
+    p.MH = g.Ho; p.MW = g.Wo; p.sO = 1; p.oh_off = 0; p.ow_off = 0;
     p.accumulate = 0;
     return direct::launch(p, st);
 }
 
-// dx (=|+=) sum_taps dy[p - off(tap)] * wpT[tap]   (stride 1 only; wpT = [tap][Cout_p][Cin_p])
+// dx (=|+=) sum_taps dy[(p + pad - tap) / stride] * wpT[tap]   (wpT = [tap][Cout_p][Cin_p]).
+// stride 1: one launch with mirrored tap offsets.  stride 2 (3x3): the dx pixels split into the four parity classes
+// (h%2, w%2); class (ph, pw) only receives taps with ky = ph+pad, kx = pw+pad (mod 2) and is a small stride-1
+// convolution over dy whose results land on the class's strided pixel grid -- no FMA is spent on the structural zeros.
 int conv_dgrad_direct(const float* dy, const float* wpT, float* dx, const ConvGeom& g, int accumulate, cudaStream_t st) {
-    if (g.stride != 1) return VAE2_ERR_UNSUPPORTED;
     direct::Params p{};
     p.a = dy; p.w = wpT; p.bias = nullptr; p.out = dx;
     p.B = g.B; p.IH = g.Ho; p.IW = g.Wo; p.lda = g.ldy; p.OH = g.H; p.OW = g.W; p.ldo = g.ldx;
-    p.CIN = g.Cout_p; p.COUT = g.Cin_p; p.taps = g.k * g.k; p.stride = 1;
-    for (int t = 0; t < p.taps; ++t) { p.dh[t] = g.pad - t / g.k; p.dw[t] = g.pad - t % g.k; }
+    p.CIN = g.Cout_p; p.COUT = g.Cin_p; p.stride = 1;
     p.accumulate = accumulate;
-    return direct::launch(p, st);
+    if (g.stride == 1) {
+        p.taps = g.k * g.k;
+        for (int t = 0; t < p.taps; ++t) { p.dh[t] = g.pad - t / g.k; p.dw[t] = g.pad - t % g.k; p.wt[t] = t; }
+        p.MH = g.H; p.MW = g.W; p.sO = 1; p.oh_off = 0; p.ow_off = 0;
+        return direct::launch(p, st);
+    }
+    if (g.stride != 2 || g.k != 3) return VAE2_ERR_UNSUPPORTED;
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            direct::Params q = p;
+            q.MH = (g.H - ph + 1) / 2; q.MW = (g.W - pw + 1) / 2;
+            q.sO = 2; q.oh_off = ph; q.ow_off = pw;
+            if (q.MH <= 0 || q.MW <= 0) continue;
+            int nt = 0;
+            for (int ky = 0; ky < 3; ++ky) {
+                if (((ph + g.pad - ky) & 1) != 0) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    if (((pw + g.pad - kx) & 1) != 0) continue;
+                    q.dh[nt] = (ph + g.pad - ky) / 2; q.dw[nt] = (pw + g.pad - kx) / 2; q.wt[nt] = ky * 3 + kx;
+                    ++nt;
+                }
+            }
+            q.taps = nt;
+            const int e = direct::launch(q, st);
+            if (e != VAE2_OK) return e;      // (unsupported shapes fail on the first class, before anything is written)
+        }
+    return VAE2_OK;
 }
 
 }  // namespace vae2
