@@ -345,8 +345,17 @@ def main():
             "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": tf / tf_burst,
-                         "traffic": None, "kernel": desc, "ms_per_launch": kms, "peak_source": src + " (burst, kernel timed alone)"},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
+                         # summarised in profiles/r1_ncu_full_conv_tc_64x64.txt (bf16 kernel; output stays in L2)
+                         "traffic": 16875520 if args.precision == "bf16" else None,
+                         "kernel": desc, "ms_per_launch": kms, "peak_source": src + " (burst, kernel timed alone)"},
         }
+        if args.precision == "fp32":
+            # the exact-fp32 path runs on the CUDA cores: the tensor roofline above is the contract's yardstick,
+            # the FMA-pipe one is the bound this kernel can actually reach
+            fma_peak = 148 * 128 * 2 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+            line["roofline"]["fma_pipe"] = {"achieved": tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": tf / fma_peak,
+                                            "peak_source": "148 SMs x 128 FP32 lanes x 2 x max SM clock"}
         if flop_per_sample:
             step_tf = flop_per_sample * B / (ms / args.steps * 1e-3) / 1e12
             line["step_conv_tflops"] = {"achieved": step_tf, "peak": tf_sust, "frac": step_tf / tf_sust,
