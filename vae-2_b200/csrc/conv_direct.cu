@@ -234,15 +234,19 @@ static int launch(Params& p, cudaStream_t st) {
     if (kblk > p.CIN) kblk = p.CIN;
     p.kblk = kblk;
     p.nblk = (p.CIN + kblk - 1) / kblk;
-    // small images: shrink the patch (never below 64 threads) until the grid covers the GPU about twice
+    // small images: shrink the patch (never below 128 threads: measured, 64-thread CTAs lose 1.7x) until every
+    // SM has a CTA
     auto n_tiles = [&](int pw_, int rg_) {
         return (long long)p.B * ((p.MW + pw_ - 1) / pw_) * ((p.MH + rg_ * TM - 1) / (rg_ * TM));
     };
-    while (rowgroups > 1 && pw * (rowgroups / 2) * p.nsplit >= 64 && n_tiles(pw, rowgroups) < 2 * kNumSMs) rowgroups /= 2;
-    while (pw > 8 && (pw / 2) * rowgroups * p.nsplit >= 64 && n_tiles(pw, rowgroups) < 2 * kNumSMs) pw >>= 1;
-    // too few warps to hide latency (a few fat CTAs): the GEMM tiling spreads the same work over more of them.
+    while (rowgroups > 1 && pw * (rowgroups / 2) * p.nsplit >= 128 && n_tiles(pw, rowgroups) < kNumSMs) rowgroups /= 2;
+    while (pw > 8 && (pw / 2) * rowgroups * p.nsplit >= 128 && n_tiles(pw, rowgroups) < kNumSMs) pw >>= 1;
+    // 72-lane layers with too few warps to hide latency (a few fat CTAs, 60 KB patches): the GEMM tiling spreads the
+    // same work over more of them (measured 103 vs 154 us at 64x128).
     // The stride-2 data gradient stays here regardless: the GEMM path spends 3/4 of its FMAs on structural zeros.
-    if (p.sO == 1 && n_tiles(pw, rowgroups) * ((pw * rowgroups * p.nsplit + 31) / 32) < 8LL * kNumSMs) return VAE2_ERR_UNSUPPORTED;
+    if (p.sO == 1 && (p.CIN > 36 || p.COUT > 36) &&
+        n_tiles(pw, rowgroups) * ((pw * rowgroups * p.nsplit + 31) / 32) < 8LL * kNumSMs)
+        return VAE2_ERR_UNSUPPORTED;
     p.PW = pw;
     size_t smem = 0;
     for (;; rowgroups /= 2) {
@@ -266,6 +270,144 @@ static int launch(Params& p, cudaStream_t st) {
         case 8: return launch_t<8>(p, smem, grid, st);
         default: return launch_t<4>(p, smem, grid, st);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the narrow layers:  dW[tap][ci][co] += sum_pixels x[pixel*stride + off(tap)][ci] * dy[pixel][co]
+//
+// The GEMM form (conv_simt.cu, M = taps*Cin rows) pads 180 x 20 outputs to 256 x 32 and re-gathers x per K chunk.
+// Here a persistent CTA walks output patches; per patch it stages x (+halo) and dy in shared memory and every
+// thread owns a 4(ci) x TN(co) block of one tap's dW in registers for the CTA's whole lifetime:
+//   thread = (pixel group, tap, ci quad, co slice);  per pixel: one float4 of x, TN/4 float4 of dy, 4*TN FMAs.
+// The pixel groups are folded through shared memory at the end and each CTA issues ONE atomic add per weight
+// (fp32 atomics as in the GEMM form: dW must be zero-filled by the caller).
+struct WgParams {
+    const float* x; const float* dy; float* dw;
+    int B, IH, IW, ldx, OH, OW, ldy;
+    int CIN, COUT, k, taps, stride, pad;
+    int nsplit, rows, groups;          // threads = groups * rows * nsplit, rows = taps * CIN/4
+    int PW, PH, lgPW, PWin, PHin, pitchx, pitchd;
+    int tiles_w, tiles_h, total_tiles;
+};
+
+template <int TN>
+__global__ void __launch_bounds__(256, 2)
+wgrad_direct_kernel(const WgParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                                           // [PHin*PWin][pitchx]
+    float* ds = smem + (size_t)p.PHin * p.PWin * p.pitchx;      // [PH*PW][pitchd]
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int per_group = p.rows * p.nsplit;
+    const int pg = tid / per_group, rem = tid - pg * per_group;
+    const int ns = rem / p.rows, r = rem - ns * p.rows;
+    const int q4 = p.CIN / 4;
+    const int tap = r / q4, ciq = r - tap * q4;
+    const int ky = tap / p.k, kx = tap - ky * p.k;
+    const int n0 = ns * TN;
+    const int npix = p.PH * p.PW;
+    const int per_img = p.tiles_w * p.tiles_h;
+
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = tile / per_img;
+        const int t = tile - b * per_img;
+        const int oh0 = (t / p.tiles_w) * p.PH, ow0 = (t % p.tiles_w) * p.PW;
+        __syncthreads();                       // previous patch fully consumed
+        {
+            const int ih0 = oh0 * p.stride - p.pad, iw0 = ow0 * p.stride - p.pad;
+            const int nvec = p.PHin * p.PWin * q4;
+            for (int v = tid; v < nvec; v += nthreads) {
+                const int pix = v / q4, q = v - pix * q4;
+                const int pr = pix / p.PWin, pc = pix - pr * p.PWin;
+                const int ih = ih0 + pr, iw = iw0 + pc;
+                float* dst = xs + (size_t)pix * p.pitchx + 4 * q;
+                if (ih >= 0 && ih < p.IH && iw >= 0 && iw < p.IW)
+                    cp_async16(dst, p.x + (((long long)b * p.IH + ih) * p.IW + iw) * p.ldx + 4 * q);
+                else
+                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const int d4 = p.COUT / 4;
+            const int nvd = npix * d4;
+            for (int v = tid; v < nvd; v += nthreads) {
+                const int pix = v / d4, q = v - pix * d4;
+                const int pr = pix >> p.lgPW, pc = pix & (p.PW - 1);
+                const int oh = oh0 + pr, ow = ow0 + pc;
+                float* dst = ds + (size_t)pix * p.pitchd + 4 * q;
+                if (oh < p.OH && ow < p.OW)
+                    cp_async16(dst, p.dy + (((long long)b * p.OH + oh) * p.OW + ow) * p.ldy + 4 * q);
+                else
+                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // zero dy: no contribution
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (pg < p.groups) {
+            const float* xb = xs + (size_t)(ky * p.PWin + kx) * p.pitchx + 4 * ciq;
+            const float* db = ds + n0;
+#pragma unroll 1
+            for (int px = pg; px < npix; px += p.groups) {
+                const int pr = px >> p.lgPW, pc = px & (p.PW - 1);
+                const float4 a = *reinterpret_cast<const float4*>(xb + (size_t)(pr * p.stride * p.PWin + pc * p.stride) * p.pitchx);
+                float bv[TN];
+#pragma unroll
+                for (int j = 0; j < TN; j += 4) {
+                    const float4 tt = *reinterpret_cast<const float4*>(db + (size_t)px * p.pitchd + j);
+                    bv[j] = tt.x; bv[j + 1] = tt.y; bv[j + 2] = tt.z; bv[j + 3] = tt.w;
+                }
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    acc[0][j] = fmaf(a.x, bv[j], acc[0][j]);
+                    acc[1][j] = fmaf(a.y, bv[j], acc[1][j]);
+                    acc[2][j] = fmaf(a.z, bv[j], acc[2][j]);
+                    acc[3][j] = fmaf(a.w, bv[j], acc[3][j]);
+                }
+            }
+        }
+    }
+    // fold the pixel groups (fixed order), then one atomic per weight and CTA
+    float* red = smem;                        // [per_group][4*TN]
+    for (int g = 1; g < p.groups; ++g) {
+        __syncthreads();
+        if (pg == g) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) red[(size_t)rem * 4 * TN + i * TN + j] = acc[i][j];
+        }
+        __syncthreads();
+        if (pg == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] += red[(size_t)rem * 4 * TN + i * TN + j];
+        }
+    }
+    if (pg == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* o = p.dw + ((size_t)tap * p.CIN + 4 * ciq + i) * p.COUT + n0;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) atomicAdd(o + j, acc[i][j]);
+        }
+    }
+}
+
+template <int TN>
+static int launch_wg_t(const WgParams& p, size_t smem, int grid, int threads, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(wgrad_direct_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return VAE2_ERR_CUDA;
+        attr = true;
+    }
+    wgrad_direct_kernel<TN><<<grid, threads, smem, st>>>(p);
+    return check_launch();
 }
 
 }  // namespace direct
@@ -318,6 +460,53 @@ int conv_dgrad_direct(const float* dy, const float* wpT, float* dx, const ConvGe
             if (e != VAE2_OK) return e;      // (unsupported shapes fail on the first class, before anything is written)
         }
     return VAE2_OK;
+}
+
+
+// dwp (zero-filled by the caller) += weight gradient; VAE2_ERR_UNSUPPORTED -> caller uses the GEMM form
+int conv_wgrad_direct(const float* x, const float* dy, float* dwp, const ConvGeom& g, cudaStream_t st) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("VAE2_DIRECT_WGRAD"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!enabled) return VAE2_ERR_UNSUPPORTED;
+    if (g.Cin_p > 36 || g.Cout_p > 36 || g.Cin_p % 4 || g.Cout_p % 4) return VAE2_ERR_UNSUPPORTED;
+    direct::WgParams p{};
+    p.x = x; p.dy = dy; p.dw = dwp;
+    p.B = g.B; p.IH = g.H; p.IW = g.W; p.ldx = g.ldx; p.OH = g.Ho; p.OW = g.Wo; p.ldy = g.ldy;
+    p.CIN = g.Cin_p; p.COUT = g.Cout_p; p.k = g.k; p.taps = g.k * g.k; p.stride = g.stride; p.pad = g.pad;
+    int tn = 0;
+    for (int cand : {20, 16, 12, 8, 4})
+        if (p.COUT % cand == 0) { tn = cand; break; }
+    if (tn == 0) return VAE2_ERR_UNSUPPORTED;
+    p.nsplit = p.COUT / tn;
+    p.rows = p.taps * (p.CIN / 4);
+    const int per_group = p.rows * p.nsplit;
+    if (per_group > 256) return VAE2_ERR_UNSUPPORTED;
+    p.groups = 256 / per_group;
+    const int threads = (p.groups * per_group + 31) / 32 * 32;      // idle tail lanes have pg == groups
+    p.PW = 32; p.lgPW = 5;
+    while (p.PW > 8 && p.PW / 2 >= p.OW) { p.PW >>= 1; --p.lgPW; }
+    p.PH = 8;
+    while (p.PH > 1 && p.PH / 2 >= p.OH) p.PH >>= 1;
+    p.PHin = (p.PH - 1) * p.stride + p.k;
+    p.PWin = (p.PW - 1) * p.stride + p.k;
+    p.pitchx = ((p.CIN / 4) % 2 == 1) ? p.CIN : p.CIN + 4;
+    p.pitchd = ((p.COUT / 4) % 2 == 1) ? p.COUT : p.COUT + 4;
+    size_t smem = ((size_t)p.PHin * p.PWin * p.pitchx + (size_t)p.PH * p.PW * p.pitchd) * sizeof(float);
+    const size_t red = (size_t)per_group * 4 * tn * sizeof(float);
+    if (red > smem) smem = red;
+    if (smem > 100 * 1024) return VAE2_ERR_UNSUPPORTED;
+    p.tiles_w = (p.OW + p.PW - 1) / p.PW;
+    p.tiles_h = (p.OH + p.PH - 1) / p.PH;
+    p.total_tiles = p.B * p.tiles_w * p.tiles_h;
+    int grid = 2 * kNumSMs;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    switch (tn) {
+        case 20: return direct::launch_wg_t<20>(p, smem, grid, threads, st);
+        case 16: return direct::launch_wg_t<16>(p, smem, grid, threads, st);
+        case 12: return direct::launch_wg_t<12>(p, smem, grid, threads, st);
+        case 8: return direct::launch_wg_t<8>(p, smem, grid, threads, st);
+        default: return direct::launch_wg_t<4>(p, smem, grid, threads, st);
+    }
 }
 
 }  // namespace vae2

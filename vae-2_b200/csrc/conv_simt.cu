@@ -384,7 +384,11 @@ int conv_dgrad_simt(const void* dy, const float* wpT, void* dx, int dtype, const
 // dwp must be zero-filled by the caller (split-K partial sums are added atomically).
 int conv_wgrad_simt(const void* x, const void* dy, float* dwp, int dtype, const ConvGeom& g, cudaStream_t st) {
     if (int e = check_geom(g, dtype)) return e;
-    if (dtype == VAE2_DT_F32) return launch_igemm<float, MODE_WGRAD>(x, dy, nullptr, dwp, g, 0, st);
+    if (dtype == VAE2_DT_F32) {
+        const int e = conv_wgrad_direct((const float*)x, (const float*)dy, dwp, g, st);
+        if (e != VAE2_ERR_UNSUPPORTED) return e;
+        return launch_igemm<float, MODE_WGRAD>(x, dy, nullptr, dwp, g, 0, st);
+    }
     return launch_igemm<__nv_bfloat16, MODE_WGRAD>(x, dy, nullptr, dwp, g, 0, st);
 }
 

@@ -44,6 +44,7 @@ int bias_grad(const void* dy, float* dbias, int dtype, long long P, int C, int l
 // bn.cu
 // conv_direct.cu (fp32 register-tiled direct conv; VAE2_ERR_UNSUPPORTED -> caller falls back to the implicit GEMM)
 int conv_fwd_direct(const float* x, const float* wp, const float* bias, float* y, const ConvGeom& g, cudaStream_t st);
+int conv_wgrad_direct(const float* x, const float* dy, float* dwp, const ConvGeom& g, cudaStream_t st);
 int conv_dgrad_direct(const float* dy, const float* wpT, float* dx, const ConvGeom& g, int accumulate, cudaStream_t st);
 
 int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, long long P, int Cp, int ld, cudaStream_t st);
