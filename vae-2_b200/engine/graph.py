@@ -577,8 +577,12 @@ class BnOp:
         self.mean, self.invstd = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.scale, self.shift = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.batch_stats = plan.bn_batch_stats or not self.bn.track_running_stats
-        self.fused = (self.batch_stats and not self.sync and self.out.Cp >= y.Cp
-                      and os.environ.get("VAE2_BN_SPLIT", "0") != "1")
+        mode = os.environ.get("VAE2_BN_SPLIT", "0")          # "1": split both directions, "fwd" / "bwd": one of them
+        fuse_max = int(os.environ.get("VAE2_BN_FUSE_MAX_MB", "1000000")) << 20
+        nbytes = y.npix * y.Cp * (4 if plan.prec.code == 0 else 2)
+        can = self.batch_stats and not self.sync and self.out.Cp >= y.Cp and nbytes <= fuse_max
+        self.fused = can and mode not in ("1", "fwd")
+        self.fused_bwd = can and mode not in ("1", "bwd")
         if self.batch_stats and not self.fused:
             self.partials = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * y.Cp, **f32)
             self.npart = C.c_int(0)
@@ -685,7 +689,7 @@ class BnOp:
     def _bwd_setup(self, plan):
         y = self.y
         f32 = dict(dtype=torch.float32, device=plan.device)
-        if not self.fused:
+        if not self.fused_bwd:
             self.bparts = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * y.Cp, **f32)
         self.sums, self.c1, self.c2 = torch.zeros(2 * y.Cp, **f32), torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.bnpart = C.c_int(0)
@@ -777,7 +781,7 @@ class BnGroupOp:
             m._bwd_setup(plan)
         if not (self.sync and ms[0].batch_stats):
             for m in ms:
-                if m.fused:
+                if m.fused_bwd:
                     m._emit_bwd_fused(plan)
                     continue
                 m._emit_bwd_reduce(plan)
