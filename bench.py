@@ -217,8 +217,12 @@ def reference_arm(args, cfg, H, W):
     base, dt = cpu_baseline(cfg, H, W, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": "train frames/sec", "value": base["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": args.workload, "per_gpu_batch": 1}, "cpu_baseline": base,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "net": "VAE^2 HRNet-W18-small-v2 (encz + encdec + D_seq + D_frm)",
+                       "step": "G-step + D-step (fwd, bwd, Adam)", "per_gpu_batch": 1, "global_batch": 1,
+                       "frames_per_sample": FRAMES_PER_SAMPLE, "parallelism": "host cores (1 process)",
+                       "sample": base["sample"]},
+            "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
