@@ -20,7 +20,7 @@ enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 
 constexpr int BK = 16;
 constexpr int TM = 8, TN = 4;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;   // 128x64 and 256x32 tiles; the 128x32 tile runs 128 threads
 
 template <typename T> __device__ __forceinline__ float4 load4(const T* p);
 template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -41,16 +41,16 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 }
 
 template <typename TA, int BM, int BN, int MODE>
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, const float* __restrict__ bias,
                   void* __restrict__ Cdst, ConvGeom g, int accumulate, int k_per_split, FastDiv div_wo, FastDiv div_ho) {
+    constexpr int NTHREADS = (BM / TM) * (BN / TN);   // shadows the namespace constant: 256, or 128 for the 128x32 tile
     constexpr int AS = BM + 4;               // smem row stride (floats); keeps 16B alignment
     constexpr int A_VECS = BM * BK / 4;      // float4 per A tile
     constexpr int A_PER_T = A_VECS / NTHREADS;
     constexpr int B_VECS = BK * BN / 4;
     constexpr int NTX = BN / TN;             // threads along N
     static_assert(A_VECS % NTHREADS == 0, "A tile / threads");
-    static_assert((BM / TM) * NTX == NTHREADS, "thread tile");
 
     __shared__ __align__(16) float As[BK][AS];
     __shared__ __align__(16) float Bs[BK][BN];
@@ -337,6 +337,10 @@ static int launch_igemm(const void* A, const void* Bm, const float* bias, void* 
         if (bn == 64) {
             dim3 grid((unsigned)((M + 127) / 128), (N + 63) / 64);
             conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
+        } else if (((M + 255) / 256) * ((N + 31) / 32) < 2 * kNumSMs) {
+            // small layer: half-height tiles (128 threads) so that the grid still covers the GPU about twice
+            dim3 grid((unsigned)((M + 127) / 128), (N + 31) / 32);
+            conv_igemm_kernel<TA, 128, 32, MODE><<<grid, 128, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
         } else {
             dim3 grid((unsigned)((M + 255) / 256), (N + 31) / 32);
             conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
