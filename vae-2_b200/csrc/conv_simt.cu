@@ -65,6 +65,27 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
     int N, Cch;  // Cch: channels per tap on the K axis (FWD/DGRAD)
     if (MODE == MODE_FWD)   { M = (long long)g.B * g.Ho * g.Wo; N = g.Cout_p; Cch = g.Cin_p; }
     if (MODE == MODE_DGRAD) { M = (long long)g.B * g.H * g.W;   N = g.Cin_p;  Cch = g.Cout_p; }
+    // stride-2 data gradient by parity class (k_per_split carries class+1 in this mode): only the dx pixels with
+    // (h%2, w%2) == (ph, pw) are rows of this launch and only the taps that reach them are visited, so no FMA is
+    // spent on the structural zeros of the transposed convolution
+    const int cls = (MODE == MODE_DGRAD) ? k_per_split - 1 : -1;
+    const int ph = cls >= 0 ? (cls >> 1) : 0, pw = cls >= 0 ? (cls & 1) : 0;
+    const int OHc = cls >= 0 ? (g.H - ph + 1) / 2 : g.H, OWc = cls >= 0 ? (g.W - pw + 1) / 2 : g.W;
+    if (cls >= 0) M = (long long)g.B * OHc * OWc;
+    int n_valid = taps;
+    unsigned tap_code = 0;            // 4 bits per visited tap
+    if (cls >= 0) {
+        n_valid = 0;
+        for (int ky = 0; ky < g.k; ++ky) {
+            if (((ph + g.pad - ky) & 1) != 0) continue;
+            for (int kx = 0; kx < g.k; ++kx) {
+                if (((pw + g.pad - kx) & 1) != 0) continue;
+                tap_code |= (unsigned)(ky * g.k + kx) << (4 * n_valid);
+                ++n_valid;
+            }
+        }
+    }
+    auto tap_of = [&](int i) { return cls >= 0 ? (int)((tap_code >> (4 * i)) & 15u) : i; };
     if (MODE == MODE_WGRAD) { M = (long long)taps * g.Cin_p;    N = g.Cout_p; Cch = 0; }
 
     float acc[TM][TN];
@@ -88,13 +109,14 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
             const long long m = m0 + v / 4;
             a_ok[j] = m < M;
             const long long mm = a_ok[j] ? m : 0;
-            const int OW = (MODE == MODE_FWD) ? g.Wo : g.W;
-            const int OH = (MODE == MODE_FWD) ? g.Ho : g.H;
+            const int OW = (MODE == MODE_FWD) ? g.Wo : OWc;
+            const int OH = (MODE == MODE_FWD) ? g.Ho : OHc;
             const int w = (int)(mm % OW);
             const long long t = mm / OW;
             a_h[j] = (int)(t % OH);
             a_n[j] = (int)(t / OH);
             a_w[j] = w;
+            if (cls >= 0) { a_h[j] = a_h[j] * 2 + ph; a_w[j] = a_w[j] * 2 + pw; }
         }
         const float* Bw = reinterpret_cast<const float*>(Bsrc);
         const int ldb = N;
@@ -146,10 +168,10 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
             if (b_active) *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = br;
         };
         const int nkc = (Cch + BK - 1) / BK;
-        const int n_iter = taps * nkc;
-        int tap = 0, kc = 0;
-        resolve_tap(0);
-        gload(0, 0);
+        const int n_iter = n_valid * nkc;
+        int tap = 0, kc = 0;             // tap = position in the visited-tap sequence
+        resolve_tap(tap_of(0));
+        gload(tap_of(0), 0);
         sstore();
         __syncthreads();
         for (int it = 0; it < n_iter; ++it) {
@@ -157,8 +179,8 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
             if (nkcv >= Cch) { nkcv = 0; ntap = tap + 1; }
             const bool has_next = it + 1 < n_iter;
             if (has_next) {
-                if (ntap != tap) resolve_tap(ntap);
-                gload(ntap, nkcv);
+                if (ntap != tap) resolve_tap(tap_of(ntap));
+                gload(tap_of(ntap), nkcv);
             }
             // only the channels that exist in this chunk (Cch is a multiple of 4): an 18->20-lane
             // tensor costs 20 k-steps per tap, not 32
@@ -197,7 +219,14 @@ conv_igemm_kernel(const TA* __restrict__ Asrc, const void* __restrict__ Bsrc, co
                 const long long m = m0 + ty * TM + i;
                 if (m < M) {
                     float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
-                    TA* p = out + m * ldo + n;
+                    long long pix = m;
+                    if (cls >= 0) {                 // class row -> dx pixel
+                        const int ww = (int)(m % OWc);
+                        const long long t = m / OWc;
+                        const int hh = (int)(t % OHc);
+                        pix = ((t / OHc) * g.H + hh * 2 + ph) * g.W + ww * 2 + pw;
+                    }
+                    TA* p = out + pix * ldo + n;
                     if (MODE == MODE_DGRAD && accumulate) {
                         const float4 o = load4<TA>(p);
                         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -318,13 +347,16 @@ static int check_geom(const ConvGeom& g, int dtype) {
 
 template <typename TA, int MODE>
 static int launch_igemm(const void* A, const void* Bm, const float* bias, void* C, const ConvGeom& g, int accumulate,
-                        cudaStream_t st) {
+                        cudaStream_t st, int cls = -1) {
     const int taps = g.k * g.k;
     long long M;
     int N;
     if (MODE == MODE_FWD) { M = (long long)g.B * g.Ho * g.Wo; N = g.Cout_p; }
     else if (MODE == MODE_DGRAD) { M = (long long)g.B * g.H * g.W; N = g.Cin_p; }
     else { M = (long long)taps * g.Cin_p; N = g.Cout_p; }
+    if (MODE == MODE_DGRAD && cls >= 0) M = (long long)g.B * ((g.H - (cls >> 1) + 1) / 2) * ((g.W - (cls & 1) + 1) / 2);
+    if (M <= 0) return VAE2_OK;
+    const int kcls = cls + 1;
     const FastDiv div_wo = make_fastdiv((unsigned)g.Wo), div_ho = make_fastdiv((unsigned)g.Ho);
     if ((long long)g.B * g.Ho * g.Wo >= (1LL << 31)) return VAE2_ERR_UNSUPPORTED;
     int bn = pick_bn(N);
@@ -336,14 +368,14 @@ static int launch_igemm(const void* A, const void* Bm, const float* bias, void* 
     if (MODE != MODE_WGRAD) {
         if (bn == 64) {
             dim3 grid((unsigned)((M + 127) / 128), (N + 63) / 64);
-            conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
+            conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, kcls, div_wo, div_ho);
         } else if (((M + 255) / 256) * ((N + 31) / 32) < 2 * kNumSMs) {
             // small layer: half-height tiles (128 threads) so that the grid still covers the GPU about twice
             dim3 grid((unsigned)((M + 127) / 128), (N + 31) / 32);
-            conv_igemm_kernel<TA, 128, 32, MODE><<<grid, 128, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
+            conv_igemm_kernel<TA, 128, 32, MODE><<<grid, 128, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, kcls, div_wo, div_ho);
         } else {
             dim3 grid((unsigned)((M + 255) / 256), (N + 31) / 32);
-            conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, 0, div_wo, div_ho);
+            conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, kcls, div_wo, div_ho);
         }
     } else {
         const long long Ktot = (long long)g.B * g.Ho * g.Wo;
@@ -380,8 +412,16 @@ int conv_dgrad_simt(const void* dy, const float* wpT, void* dx, int dtype, const
     if (dtype == VAE2_DT_F32) {
         const int e = conv_dgrad_direct((const float*)dy, wpT, (float*)dx, g, accumulate, st);
         if (e != VAE2_ERR_UNSUPPORTED) return e;
-        return launch_igemm<float, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st);
     }
+    if (g.stride == 2 && g.k == 3) {            // four parity-class launches (see the kernel)
+        for (int cls = 0; cls < 4; ++cls) {
+            const int e = dtype == VAE2_DT_F32 ? launch_igemm<float, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st, cls)
+                                               : launch_igemm<__nv_bfloat16, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st, cls);
+            if (e != VAE2_OK) return e;
+        }
+        return VAE2_OK;
+    }
+    if (dtype == VAE2_DT_F32) return launch_igemm<float, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st);
     return launch_igemm<__nv_bfloat16, MODE_DGRAD>(dy, wpT, nullptr, dx, g, accumulate, st);
 }
 
