@@ -88,6 +88,9 @@ CONV_CASES = [  # (B, Cin, Cout, H, W, k, s, bias)
     (1, 36, 36, 33, 47, 3, 2, False),
     (1, 72, 144, 16, 16, 3, 2, False),
     (3, 144, 18, 5, 6, 1, 1, False),
+    (2, 36, 18, 9, 40, 1, 1, False),      # 1x1 between narrow branches (fp32: direct fwd/dgrad/wgrad kernels)
+    (1, 18, 72, 21, 26, 3, 2, False),     # stride 2, narrow -> 72 lanes, odd height (parity-class dgrad)
+    (2, 36, 36, 40, 70, 3, 1, False),     # several patches per image, W not a multiple of the 32-column warp
 ]
 
 
