@@ -28,7 +28,8 @@ import torch.distributed as dist  # noqa: E402
 
 WORKLOADS = {
     # name: (yaml, H, W, per-GPU batch, algorithmic conv FLOP per sample for a full iteration)
-    "w18_256x512": ("vae2_hrnet_w18_small_v2_256x512.yaml", 256, 512, {"fp32": 2, "bf16": 4}, 7.60e12),
+    # per-GPU batch: the largest that leaves ~30 GB of the 180 GB free (fp32 B=4 peaks at 148 GB, bf16 B=6 at 129 GB)
+    "w18_256x512": ("vae2_hrnet_w18_small_v2_256x512.yaml", 256, 512, {"fp32": 4, "bf16": 6}, 7.60e12),
     "w18_1024x2048": ("vae2_hrnet_w18_small_v2_1024x2048.yaml", 1024, 2048, 1, 121.6e12),
     "tiny_32x64": ("vae2_hrnet_tiny_32x64.yaml", 32, 64, 2, None),
 }

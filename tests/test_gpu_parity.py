@@ -288,3 +288,55 @@ def test_cuda_graph_replay_matches_eager():
         E.use_cuda_graphs(False)
     for u, v, w in zip(a, b1, b2):
         assert rel_err(v, u) < 1e-6 and rel_err(w, u) < 1e-6
+
+
+@pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graphs"])
+def test_activation_arena_matches_private_memory(graphs):
+    """Three alternating G/D iterations with parameter updates: the phase-shared activation arena (the G networks and the
+    D networks live in the same memory, one phase after the other) must give the losses that private per-plan
+    buffers give.  Also: interleaving the phases (D forward while a G backward is pending) must raise."""
+    import os
+    name = "tiny_b2_32x64"
+
+    def run(arena):
+        os.environ["VAE2_ACT_ARENA"] = "1" if arena else "0"
+        E.ActArena.reset()
+        gold, cfg, g, d = _load_case(name, "trained")
+        B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+        g, d = g.to(DEV).train(), d.to(DEV).train()
+        # plain SGD: linear in the gradients, so the run-to-run rounding noise of the atomically-summed weight gradients
+        # is not amplified (Adam's g/sqrt(v) turns a 1e-9 gradient of random sign into a full-size update)
+        og = torch.optim.SGD([p for n, p in g.named_parameters() if "D_model" not in n], lr=1e-7)
+        od = torch.optim.SGD(d.parameters(), lr=1e-7)
+        xd, x2d, x3d = xt.to(DEV), x2t.to(DEV), x3t.to(DEV)
+        hist = []
+        E.use_cuda_graphs(graphs)
+        try:
+            for it in range(3):
+                losses, x1p, x2p, x3p = _run_g_step(g, xd, x2d, x3d, eps_z, code)
+                og.zero_grad(set_to_none=True)
+                losses[0].mean().backward()
+                og.step()
+                dl = d(x2d, x2p.detach())
+                od.zero_grad(set_to_none=True)
+                dl[0].mean().backward()
+                od.step()
+                hist.append([float(l.mean()) for l in losses] + [float(dl[0].mean())])
+            if arena:
+                losses, _, x2p, _ = _run_g_step(g, xd, x2d, x3d, eps_z, code)     # G backward left pending ...
+                with pytest.raises(RuntimeError, match="share activation memory"):
+                    d(x2d, x2p.detach())                                             # ... so phase D must refuse
+                del losses
+        finally:
+            E.use_cuda_graphs(False)
+            os.environ.pop("VAE2_ACT_ARENA", None)
+            E.ActArena.reset()
+        return np.array(hist)
+
+    private, private2, shared = run(False), run(False), run(True)
+    # yardstick: two private-memory runs differ by the rounding noise of the atomically-summed weight gradients,
+    # amplified by the (randomly initialised, ill-conditioned) networks over the following iterations
+    noise = np.abs(private2 - private) / np.abs(private)
+    diff = np.abs(shared - private) / np.abs(private)
+    assert np.array_equal(shared[0, :7], private[0, :7]), "first G step (no update yet) must be bit-identical"
+    assert diff.max() <= 5.0 * noise.max() + 1e-6, (diff.max(), noise.max())

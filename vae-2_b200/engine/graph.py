@@ -64,6 +64,68 @@ class GradArena:
         cls._arenas.clear()
 
 
+class ActArena:
+    """Activation memory shared between the PHASES of a training iteration.
+
+    The generator step (FullModel_encdec: encz + encdec + 4 discriminator passes) and the discriminator step
+    (FullModel_D: 8 discriminator passes) never overlap in time: each runs forward -> backward to completion.  Plans
+    recorded while a phase is active bump-allocate their activation buffers from a chunk list that every phase walks
+    from the start, so phase "D" lives in the memory phase "G" used a moment ago; the resident footprint is the
+    maximum over phases instead of the sum (113 -> ~75 GB at B=2 fp32).  Within a phase all plans are disjoint.
+    Safety: a forward of an arena-backed plan while a plan of ANOTHER phase still waits for its backward raises
+    (EngineModule._run), and buffers that no kernel rewrites completely (concat roots: the lanes behind the last
+    segment) are re-zeroed at the start of every forward.  Outside a phase (direct module calls, tests) plans get
+    private memory as before.  VAE2_ACT_ARENA=0 disables the sharing."""
+    CHUNK_BYTES = 2 << 30
+    phase = None
+    live = {}
+    _pools = {}
+
+    @classmethod
+    def enabled(cls):
+        return os.environ.get("VAE2_ACT_ARENA", "1") != "0"
+
+    @classmethod
+    def alloc(cls, device, tdtype, numel):
+        if cls.phase is None or not cls.enabled():
+            return None
+        esize = torch.empty(0, dtype=tdtype).element_size()
+        pool = cls._pools.setdefault((str(device), tdtype), {"chunks": [], "cur": {}})
+        cur = pool["cur"].setdefault(cls.phase, [0, 0])
+        n = pad_to(numel, 128)
+        while True:
+            ci, off = cur
+            if ci >= len(pool["chunks"]):
+                pool["chunks"].append(torch.empty(max(n, cls.CHUNK_BYTES // esize), dtype=tdtype, device=device))
+            chunk = pool["chunks"][ci]
+            if off + n <= chunk.numel():
+                cur[1] = off + n
+                t = chunk[off:off + numel]
+                t.zero_()
+                return t
+            cur[0], cur[1] = ci + 1, 0
+
+    @classmethod
+    def reset(cls):
+        cls._pools.clear()
+        cls.live.clear()
+
+
+class activation_phase:
+    """Context manager used by the wrapper modules: plans recorded inside share activation memory across phases."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.prev = ActArena.phase
+        ActArena.phase = self.name
+
+    def __exit__(self, *exc):
+        ActArena.phase = self.prev
+        return False
+
+
 class Act:
     """A channels-last activation [B][H][W][ld] (possibly a channel slice of a wider root)."""
 
@@ -73,7 +135,11 @@ class Act:
         pr = plan.prec
         if root is None:
             self.Cp = pad_to(C_, pr.tot_align) if Cp is None else Cp
-            self.buf = torch.zeros(self.B * H * W * self.Cp, dtype=pr.tdtype, device=plan.device)
+            self.buf = ActArena.alloc(plan.device, pr.tdtype, self.B * H * W * self.Cp)
+            if self.buf is None:
+                self.buf = torch.zeros(self.B * H * W * self.Cp, dtype=pr.tdtype, device=plan.device)
+            else:
+                plan.arena_phase = ActArena.phase
             self.ld, self.c_off, self.parent = self.Cp, 0, None
             plan.all_acts.append(self)
         else:
@@ -155,6 +221,8 @@ class Plan:
         self.n_collectives_fwd = self.n_collectives_bwd = 0
         self._garena, self._goff = None, 0
         self.all_acts = []
+        self.arena_phase = None               # set when an activation buffer comes from the phase-shared ActArena
+        self.concat_roots = []
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
         self.fp32_tc = os.environ.get("VAE2_FP32_TC", "0") == "1"
         self.use_tc_wgrad = os.environ.get("VAE2_DISABLE_TC_WGRAD", "0") != "1"
@@ -188,6 +256,7 @@ class Plan:
         seg_p = [pad_to(c, pr.seg_align) for c in Cs]
         total = pad_to(sum(seg_p), pr.tot_align)
         root = Act(self, sum(Cs), H, W, Cp=total, name=name)
+        self.concat_roots.append(root)
         cmap, off, slices = [], 0, []
         for c, cp in zip(Cs, seg_p):
             slices.append(Act(self, c, H, W, root=root, c_off=off, Cp=cp, name="%s[%d]" % (name, off)))
@@ -299,6 +368,11 @@ class Plan:
         self.fwd.append(lambda st: N.call.vae2_pack_weights(self.pk_dev.data_ptr(), self.n_convs, st))
         for o in self.ops:
             o.emit_fwd(self)
+        if self.arena_phase is not None:
+            # shared memory: the lanes of a concat root that no producer writes must not keep another phase's data.
+            # First thing of the eager prologue, i.e. before the input/code ops write their slices.
+            for r in self.concat_roots:
+                self.pre_fwd.insert(0, lambda st, b=r.buf: b.zero_())
         # backward program (reverse order; accumulate flags resolved statically)
         if self.training:
             if os.environ.get("VAE2_PRIVATE_GRADS", "0") != "1":

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .graph import Plan, Recorder
+from .graph import ActArena, Plan, Recorder, activation_phase  # noqa: F401
 
 _STATE = {
     "precision": os.environ.get("VAE2_PRECISION", "fp32"),
@@ -46,10 +46,15 @@ class _Lease:
     def __init__(self, plan):
         self.plan = plan
         plan.busy = True
+        if plan.arena_phase is not None:
+            ActArena.live[plan.arena_phase] = ActArena.live.get(plan.arena_phase, 0) + 1
 
     def release(self):
         if self.plan is not None:
             self.plan.busy = False
+            if self.plan.arena_phase is not None:
+                ph = self.plan.arena_phase
+                ActArena.live[ph] = max(0, ActArena.live.get(ph, 0) - 1)
             self.plan = None
 
     def __del__(self):
@@ -143,6 +148,12 @@ class EngineModule(nn.Module):
                 plan.finalize()
                 plan.param_ptrs = tuple(p.data_ptr() for p in plan.params)
             pool.append(plan)
+        if plan.arena_phase is not None:
+            for other, n in ActArena.live.items():
+                if other != plan.arena_phase and n > 0:
+                    raise RuntimeError("vae2_b200: a network of phase %r still waits for its backward while phase %r runs; "
+                                       "the phases share activation memory (set VAE2_ACT_ARENA=0 to interleave them)"
+                                       % (other, plan.arena_phase))
         params = [p for p in plan.params]
         with torch.cuda.device(dev):
             outs = _PlanFn.apply(plan, len(inputs), *inputs, *params)

@@ -52,6 +52,13 @@ class FullModel_encdec(nn.Module):
 
     def forward(self, xt, x2t, x3t, multiplier, is_baseline=False, baseline_mode="VAE_NATIVE",
                 sampling_mode="default", xt_last=None, x3t_last=None, eps=None):
+        # generator phase: its networks share activation memory with the discriminator phase (engine.ActArena)
+        with _E.activation_phase("G"):
+            return self._forward(xt, x2t, x3t, multiplier, is_baseline, baseline_mode, sampling_mode, xt_last, x3t_last,
+                                 eps)
+
+    def _forward(self, xt, x2t, x3t, multiplier, is_baseline=False, baseline_mode="VAE_NATIVE",
+                 sampling_mode="default", xt_last=None, x3t_last=None, eps=None):
         assert sampling_mode in ["default", "prior_sampling", "momentum_sampling"]
         if sampling_mode == "momentum_sampling":
             assert xt_last is not None
@@ -113,6 +120,10 @@ class FullModel_D(nn.Module):
         self.criterion_gan, self.gan_lambda = criterion_gan, gan_lambda
 
     def forward(self, x2t, x2t_predict):
+        with _E.activation_phase("D"):
+            return self._forward(x2t, x2t_predict)
+
+    def _forward(self, x2t, x2t_predict):
         real, fake = x2t.detach(), x2t_predict.detach()
         B = real.shape[0]
         L = self.D_model_sequence.clip_length
