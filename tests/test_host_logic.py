@@ -149,3 +149,52 @@ def test_syncbn_message_algebra_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, True, True, 11.0), (1, True, True, True, 11.0)]
+
+
+def test_activation_arena_shares_memory_across_phases_only():
+    """engine.ActArena (host logic, CPU tensors): buffers of one phase are disjoint, the next phase walks the same
+    chunks from the start, an allocation larger than a chunk gets a chunk of its own, and nothing is shared outside
+    a phase or with VAE2_ACT_ARENA=0."""
+    A = E.ActArena
+    dev = torch.device("cpu")
+    old_chunk = A.CHUNK_BYTES
+    A.reset()
+    A.CHUNK_BYTES = 4096 * 4          # 4096 floats per chunk
+    try:
+        assert A.alloc(dev, torch.float32, 100) is None, "no phase active: the caller allocates privately"
+
+        def span(t):
+            return (t.data_ptr(), t.data_ptr() + t.numel() * t.element_size())
+
+        with E.activation_phase("G"):
+            g = [A.alloc(dev, torch.float32, n) for n in (1000, 3000, 500, 3500, 700)]
+        with E.activation_phase("D"):
+            d = [A.alloc(dev, torch.float32, n) for n in (2000, 2000, 4000)]
+        for group in (g, d):
+            assert all(t.numel() == n for t, n in zip(group, [t.numel() for t in group]))
+            assert all(float(t.abs().sum()) == 0.0 for t in group), "fresh buffers are zero"
+            s = sorted(span(t) for t in group)
+            assert all(a[1] <= b[0] for a, b in zip(s, s[1:])), "buffers of one phase must not overlap"
+            bases = [c.data_ptr() for c in next(iter(A._pools.values()))["chunks"]]
+            assert all(min((t.data_ptr() - b) % 512 for b in bases if b <= t.data_ptr()) == 0 for t in group), \
+                "128-element alignment inside the chunk"
+        assert d[0].data_ptr() == g[0].data_ptr(), "the second phase starts where the first one started"
+        pool = next(iter(A._pools.values()))
+        total = sum(c.numel() for c in pool["chunks"])
+        assert total < sum(t.numel() for t in g + d), "footprint is below the sum over phases"
+        with E.activation_phase("D"):
+            big = A.alloc(dev, torch.float32, 10000)          # larger than a chunk: gets a chunk of its own
+        assert big.numel() == 10000 and any(c.numel() >= 10000 for c in pool["chunks"])
+        # nesting restores the outer phase; disabling turns sharing off
+        with E.activation_phase("G"):
+            with E.activation_phase("D"):
+                pass
+            assert A.phase == "G"
+        assert A.phase is None
+        os.environ["VAE2_ACT_ARENA"] = "0"
+        with E.activation_phase("G"):
+            assert A.alloc(dev, torch.float32, 10) is None
+    finally:
+        os.environ.pop("VAE2_ACT_ARENA", None)
+        A.CHUNK_BYTES = old_chunk
+        A.reset()
