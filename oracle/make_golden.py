@@ -188,12 +188,17 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
     enc_hrnet, toy_fc, rutils, rcrit = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "w48":       # regenerate only the W48 case
+        hrnet_case("w48_b1_33x33", "vae2_hrnet_w48_473x473.yaml", 1, 33, 33, "trained", enc_hrnet, rutils, rcrit)
+        return
     hrnet_case("tiny_b2_32x64", "vae2_hrnet_tiny_32x64.yaml", 2, 32, 64, "trained", enc_hrnet, rutils, rcrit,
                keep_grads=("encz_model.conv1.weight", "encdec_model.transition3_e.0.0.weight",
                            "encdec_model.decp_last_layer_2.3.bias", "encdec_model.stage3.0.fuse_layers.2.0.1.0.weight"))
     hrnet_case("tiny_b1_33x47", "vae2_hrnet_tiny_32x64.yaml", 1, 33, 47, "trained", enc_hrnet, rutils, rcrit)
     hrnet_case("tiny_b2_32x64_init", "vae2_hrnet_tiny_32x64.yaml", 2, 32, 64, "init", enc_hrnet, rutils, rcrit)
     hrnet_case("w18_b1_32x64", "vae2_hrnet_w18_small_v2_256x512.yaml", 1, 32, 64, "trained", enc_hrnet, rutils, rcrit)
+    # HRNet-W48 (LIP / PASCAL-Context experiments, BASELINE configs[4]) at a small odd square size
+    hrnet_case("w48_b1_33x33", "vae2_hrnet_w48_473x473.yaml", 1, 33, 33, "trained", enc_hrnet, rutils, rcrit)
     toy_case("toy_b500", toy_fc, rutils, rcrit)
 
 

@@ -116,7 +116,7 @@ def _run_g_step(g, xt, x2t, x3t, eps_z, code, **kw):
 
 
 GOLD_CASES = [("tiny_b2_32x64", "trained"), ("tiny_b1_33x47", "trained"), ("tiny_b2_32x64_init", "init"),
-              ("w18_b1_32x64", "trained")]
+              ("w18_b1_32x64", "trained"), ("w48_b1_33x33", "trained")]
 
 
 def _act_tol(gold, k):
@@ -157,9 +157,16 @@ def test_g_and_d_step_match_reference_golden_fp32(name, wmode):
     xd, x2d, x3d = xt.to(DEV), x2t.to(DEV), x3t.to(DEV)
     losses, x1p, x2p, x3p = _run_g_step(g, xd, x2d, x3d, eps_z, code)
     got = np.array([float(l) for l in losses])
-    np.testing.assert_allclose(got, gold["g_losses"], rtol=FP32_TOL, err_msg="G losses vs reference fp32")
-    np.testing.assert_allclose(got, gold["g_losses64"], rtol=FP32_TOL, err_msg="G losses vs reference fp64")
-    assert rel_err(x2p, gold["x2p"]) < FP32_TOL, "x2p (encoder output)"
+    # 1e-4 relative (north_star), widened only by the measured conditioning of the case: how far the REFERENCE's
+    # own fp32 losses are from its fp64 losses (W48 at 33x33 with random weights: its two decoders' predictions are
+    # 1.6e-2 apart, which leaves 8e-4 / 1e-3 on the x1-L1 and GAN terms while the x3-L1 term happens to agree to
+    # 2e-6 -- so the yardstick is the worst term of the case, not each term's own luck)
+    ltol = max(FP32_TOL, 3.0 * float(np.max(np.abs(gold["g_losses"] - gold["g_losses64"]) / np.abs(gold["g_losses64"]))))
+    assert np.all(np.abs(got - gold["g_losses64"]) <= ltol * np.abs(gold["g_losses64"])), \
+        ("G losses vs reference fp64", got, gold["g_losses64"], ltol)
+    assert np.all(np.abs(got - gold["g_losses"]) <= 2 * ltol * np.abs(gold["g_losses"])), \
+        ("G losses vs reference fp32", got, gold["g_losses"], ltol)
+    assert rel_err(x2p, gold["x2p"]) < max(FP32_TOL, 3.0 * rel_err(gold["x2p"], gold["x2p64"])), "x2p (encoder output)"
     for a, k in ((x1p, "x1p"), (x2p, "x2p"), (x3p, "x3p")):
         assert rel_err(a, gold[k + "64"]) < _act_tol(gold, k), k + " vs reference fp64"
         assert rel_err(a, gold[k]) < 2 * _act_tol(gold, k), k + " vs reference fp32"
@@ -185,7 +192,7 @@ def test_g_and_d_step_match_reference_golden_fp32(name, wmode):
     assert int(sd["D_model_frame.bn1.num_batches_tracked"]) == 3
     # D step
     dl = d(x2t=x2d, x2t_predict=x2p.detach())
-    np.testing.assert_allclose(np.array([float(l) for l in dl]), gold["d_losses"], rtol=FP32_TOL, err_msg="D losses")
+    np.testing.assert_allclose(np.array([float(l) for l in dl]), gold["d_losses"], rtol=FP32_TOL if ltol < 2 * FP32_TOL else 2 * ltol, err_msg="D losses")
     d.zero_grad()
     dl[0].backward()
     dn = dict(zip(gold["d_grad_names"].tolist(), gold["d_grad_norms"]))
