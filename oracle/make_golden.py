@@ -148,6 +148,60 @@ def hrnet_case(fname, cfg_name, B, H, W, wmode, enc_hrnet, rutils, rcrit, keep_g
     print(fname, "g_losses", out["g_losses"], "d_losses", out["d_losses"], os.path.getsize(path) // 1024, "KiB")
 
 
+SUB = 8   # spatial subsampling stride of the full-size fixtures (whole tensors would be 4.7 MB each)
+
+
+def _summ(t):
+    """What a full-size fixture keeps of a prediction: every 8th pixel, plus per-channel mean and L2 norm over ALL pixels."""
+    t = t.detach()
+    d = t.double()
+    return (t[..., ::SUB, ::SUB].float().numpy().copy(), d.mean(dim=(0, 2, 3)).numpy().copy(),
+            d.pow(2).sum(dim=(0, 2, 3)).sqrt().numpy().copy())
+
+
+def hrnet_case_fullsize(fname, cfg_name, B, H, W, wmode, enc_hrnet, rutils, rcrit, backward=True):
+    """BASELINE-size case (configs[1]: W18 256x512; configs[4]: W48 473x473): the G step of the unmodified reference in
+    training mode (batch-statistics BN), fp32 and fp64.  Predictions are stored subsampled (see _summ); with
+    ``backward`` the fp32 parameter-gradient norms are stored as well, otherwise the pass runs under no_grad."""
+    import contextlib
+    cfg = load_cfg(cfg_name)
+    g, _ = build_reference(cfg, enc_hrnet, rutils, rcrit)
+    sd = g.state_dict()
+    O.fill_state_dict(sd, seed_tag=fname, mode=wmode)
+    g.load_state_dict(sd)
+    sd0 = {k: v.clone() for k, v in sd.items()}
+    Z = cfg.MODEL.EXTRA.Z_DIM
+    xt, x2t, x3t = O.make_clips(fname, B, H, W)
+    eps_z, code = O.make_eps(fname, B, Z, H, W)
+    out = {"meta": np.array([B, H, W, Z]), "cfg": np.array(cfg_name), "wmode": np.array(wmode), "sub": np.array(SUB)}
+    g.train()
+    with (contextlib.nullcontext() if backward else torch.no_grad()), RandnQueue(eps_z + [code]):
+        losses, x1p, x2p, x3p = g(xt=xt, x2t=x2t, x3t=x3t, multiplier=1.0)
+    out["g_losses"] = np.array([float(l) for l in losses], dtype=np.float64)
+    for k, t in (("x1p", x1p), ("x2p", x2p), ("x3p", x3p)):
+        out[k], out[k + "_mean"], out[k + "_l2"] = _summ(t)
+    if backward:
+        g.zero_grad()
+        losses[0].backward()
+        n, nr, sm = grad_summary(g)
+        out["g_grad_names"], out["g_grad_norms"], out["g_grad_sums"] = n, nr, sm
+    sd_after = g.state_dict()
+    for k in ("encz_model.bn1.running_mean", "encdec_model.decf_bn2.running_mean", "D_model_frame.bn1.running_var"):
+        out["after:" + k] = sd_after[k].numpy().copy()
+    del g, losses, x1p, x2p, x3p
+    g64, _ = build_reference(cfg, enc_hrnet, rutils, rcrit)
+    g64.load_state_dict(sd0)
+    g64 = g64.double().train()
+    with torch.no_grad(), RandnQueue([e.double() for e in eps_z] + [code.double()]):
+        l64, a64, b64, c64 = g64(xt=xt.double(), x2t=x2t.double(), x3t=x3t.double(), multiplier=1.0)
+    out["g_losses64"] = np.array([float(l) for l in l64], dtype=np.float64)
+    for k, t in (("x1p64", a64), ("x2p64", b64), ("x3p64", c64)):
+        out[k], out[k + "_mean"], out[k + "_l2"] = _summ(t)
+    path = os.path.join(ROOT, "tests", "golden", fname + ".npz")
+    np.savez_compressed(path, **out)
+    print(fname, "g_losses", out["g_losses"], "g_losses64", out["g_losses64"], os.path.getsize(path) // 1024, "KiB")
+
+
 def toy_case(fname, toy_fc, rutils, rcrit):
     cfg = load_cfg("vae2_hrnet_tiny_32x64.yaml")  # only MODEL.EXTRA.IS_BASELINE/BASELINE_MODE are read
     nets = [toy_fc.get_encz_model(cfg), toy_fc.get_encdec_model(cfg), toy_fc.get_D_model(cfg)]
@@ -188,6 +242,14 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
     enc_hrnet, toy_fc, rutils, rcrit = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "w18_full":   # BASELINE configs[1] size (about 2 min, 30 GB of host memory)
+        hrnet_case_fullsize("w18_b1_256x512", "vae2_hrnet_w18_small_v2_256x512.yaml", 1, 256, 512, "trained",
+                            enc_hrnet, rutils, rcrit, backward=True)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "w48_full":   # BASELINE configs[4] LIP size, forward only (about 15 min)
+        hrnet_case_fullsize("w48_b1_473x473", "vae2_hrnet_w48_473x473.yaml", 1, 473, 473, "trained",
+                            enc_hrnet, rutils, rcrit, backward=False)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "w48":       # regenerate only the W48 case
         hrnet_case("w48_b1_33x33", "vae2_hrnet_w48_473x473.yaml", 1, 33, 33, "trained", enc_hrnet, rutils, rcrit)
         return

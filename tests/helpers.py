@@ -66,3 +66,32 @@ class RandnQueue:
 def rel_err(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _plain(v):
+    if isinstance(v, dict):
+        return {k: _plain(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [_plain(x) for x in v]
+    if isinstance(v, (np.floating, np.integer)):
+        return float(v)
+    if isinstance(v, np.ndarray):
+        return v.tolist()
+    return v
+
+
+def log_err(case, **vals):
+    """Measured parity errors, one JSON line per case: printed (pytest -s / -rP shows it) and appended to
+    gpurun_out/parity_errors.jsonl so a GPU run brings them back ('log measured errors per case')."""
+    import json
+    rec = {"case": case}
+    rec.update(_plain(vals))
+    line = json.dumps(rec)
+    print("PARITY", line)
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.jsonl"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass

@@ -1,0 +1,409 @@
+"""GPU parity at the sizes bench.py times (BASELINE configs[1] and [4]) and for the paths round 1 left unpinned:
+bf16 gradients, module-boundary activation taps, the SyncBN split/merge kernels, the toy wrapper, CUDA-graph side
+effects.  Every case logs its measured errors (tests/helpers.log_err -> gpurun_out/parity_errors.jsonl).
+
+Tolerances (BASELINE.json north_star): fp32 <= 1e-4 relative on activations and loss; bf16 <= 1e-2 relative on ELBO.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import (E, O, M, T, U, Cr, RandnQueue, build_product, case_inputs, cfg_of, golden, log_err, rel_err)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+N = E.native
+FP32_TOL = 1e-4
+BF16_ELBO_TOL = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _fp32_default():
+    E.set_precision("fp32")
+    E.use_cuda_graphs(False)
+    yield
+    E.set_precision("fp32")
+    E.use_cuda_graphs(False)
+    E.ActArena.reset()
+    torch.cuda.empty_cache()
+
+
+def _load(name, wmode="trained"):
+    gold = golden(name)
+    cfg = cfg_of(str(gold["cfg"]))
+    g, d = build_product(cfg)
+    O.fill_state_dict(g.state_dict(), seed_tag=name, mode=wmode)
+    return gold, cfg, g, d
+
+
+def _g_step(g, xt, x2t, x3t, eps_z, code, **kw):
+    dev = xt.device
+    with RandnQueue([code]):
+        return g(xt=xt, x2t=x2t, x3t=x3t, multiplier=1.0, eps=[e.to(dev) for e in eps_z], **kw)
+
+
+def _sub_err(pred, gold, key):
+    """Relative error of a device prediction against a subsampled full-size fixture + per-channel L2 norms of the
+    whole tensor."""
+    s = int(gold["sub"])
+    sub = rel_err(pred[..., ::s, ::s], gold[key])
+    l2 = pred.double().pow(2).sum(dim=(0, 2, 3)).sqrt().cpu().numpy()
+    return sub, float(np.max(np.abs(l2 - gold[key + "_l2"]) / gold[key + "_l2"]))
+
+
+# ---- (a) BASELINE configs[1]: W18-small-v2, 256x512, B=1 -- the very plans bench.py times -------------------------------
+def test_w18_256x512_gstep_fp32_vs_oracle_and_reference():
+    name = "w18_b1_256x512"
+    gold, cfg, g, d = _load(name)
+    B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+    assert (H, W) == (256, 512)
+    sd0 = {k: v.clone() for k, v in g.state_dict().items()}
+    # CPU oracle, same seeded inputs, training-mode BN (forward only: ~15 s on the box's host cores)
+    torch.set_num_threads(max(1, (torch.get_num_threads() or 1)))
+    with torch.no_grad():
+        ol, o1, o2, o3 = O.full_encdec_forward({k: v.clone() for k, v in sd0.items()}, cfg, xt, x2t, x3t, eps_z, code)
+    ol = np.array([float(l) for l in ol])
+    g = g.to(DEV).train()
+    losses, x1p, x2p, x3p = _g_step(g, xt.to(DEV), x2t.to(DEV), x3t.to(DEV), eps_z, code)
+    got = np.array([float(l) for l in losses])
+    e_or = np.abs(got - ol) / np.abs(ol)
+    e_ref = np.abs(got - gold["g_losses"]) / np.abs(gold["g_losses"])
+    e_64 = np.abs(got - gold["g_losses64"]) / np.abs(gold["g_losses64"])
+    ref_own = np.abs(gold["g_losses"] - gold["g_losses64"]) / np.abs(gold["g_losses64"])
+    x2_or = rel_err(x2p, o2)
+    acts = {k: rel_err(a, o) for k, a, o in (("x1p", x1p, o1), ("x2p", x2p, o2), ("x3p", x3p, o3))}
+    subs = {k: _sub_err(a, gold, k) for k, a in (("x1p", x1p), ("x2p", x2p), ("x3p", x3p))}
+    subs64 = {k: _sub_err(a, gold, k + "64") for k, a in (("x1p", x1p), ("x2p", x2p), ("x3p", x3p))}
+    ref_act = {k: rel_err(gold[k], gold[k + "64"]) for k in ("x1p", "x2p", "x3p")}
+    log_err("w18_256x512_fp32", loss_vs_oracle=e_or.max(), loss_vs_ref32=e_ref.max(), loss_vs_ref64=e_64.max(),
+            ref32_vs_ref64_loss=ref_own.max(), act_vs_oracle=acts, act_sub_vs_ref32={k: v[0] for k, v in subs.items()},
+            act_l2_vs_ref32={k: v[1] for k, v in subs.items()}, act_sub_vs_ref64={k: v[0] for k, v in subs64.items()},
+            ref32_vs_ref64_act=ref_act)
+    ltol = max(FP32_TOL, 3.0 * float(ref_own.max()))
+    assert e_64.max() <= ltol and e_ref.max() <= 2 * ltol and e_or.max() <= 2 * ltol, (got, ol, gold["g_losses"])
+    # encoder prediction: the north-star 1e-4, against the oracle on the WHOLE tensor and the reference on the fixture
+    assert x2_or < max(FP32_TOL, 3.0 * ref_act["x2p"]), x2_or
+    assert subs["x2p"][0] < max(FP32_TOL, 3.0 * ref_act["x2p"]) and subs["x2p"][1] < FP32_TOL
+    for k in ("x1p", "x3p"):     # decoders amplify the encoder's rounding noise: judged by the reference's own fp32 noise
+        tol = max(FP32_TOL, 3.0 * ref_act[k])
+        assert acts[k] < 2 * tol and subs64[k][0] < tol and subs[k][0] < 2 * tol, (k, acts[k], subs[k], subs64[k], tol)
+    # backward at this size: gradient norms against the reference's own
+    g.zero_grad()
+    losses[0].backward()
+    norms = dict(zip(gold["g_grad_names"].tolist(), gold["g_grad_norms"]))
+    en = np.array([abs(float(p.grad.double().norm()) - norms[k]) / norms[k] for k, p in g.named_parameters()
+                   if norms[k] > 1e-9 and ".0.bias" not in k])
+    log_err("w18_256x512_fp32_grads", median=np.median(en), q90=np.quantile(en, 0.9), max=en.max())
+    assert np.median(en) < 2e-2 and np.quantile(en, 0.9) < 1e-1, (np.median(en), np.quantile(en, 0.9))
+    sd = g.state_dict()
+    for k in ("encz_model.bn1.running_mean", "encdec_model.decf_bn2.running_mean", "D_model_frame.bn1.running_var"):
+        assert rel_err(sd[k], gold["after:" + k]) < 1e-4, k
+    E.check_finite(block=True)
+
+
+def test_w18_256x512_bf16_elbo_vs_reference():
+    E.set_precision("bf16")
+    name = "w18_b1_256x512"
+    gold, cfg, g, d = _load(name)
+    B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+    g = g.to(DEV).train()
+    losses, x1p, x2p, x3p = _g_step(g, xt.to(DEV), x2t.to(DEV), x3t.to(DEV), eps_z, code)
+    got, ref = np.array([float(l) for l in losses]), gold["g_losses64"]
+    elbo_got, elbo_ref = got[1:5].sum(), ref[1:5].sum()
+    e = abs(elbo_got - elbo_ref) / abs(elbo_ref)
+    sub = _sub_err(x2p, gold, "x2p64")
+    log_err("w18_256x512_bf16", elbo=e, terms=(np.abs(got - ref) / np.abs(ref)).tolist(), x2p_sub=sub[0], x2p_l2=sub[1])
+    assert e < BF16_ELBO_TOL, (got, ref)
+    assert sub[0] < 5e-2, sub
+    losses[0].backward()
+    assert all(torch.isfinite(p.grad).all() for p in g.parameters() if p.grad is not None)
+    E.check_finite(block=True)
+
+
+# ---- BASELINE configs[4]: HRNet-W48 at the LIP size 473x473 (odd sizes 473 -> 237 -> 119 -> 60), forward ---------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_w48_473x473_forward_vs_reference(prec):
+    name = "w48_b1_473x473"
+    try:
+        gold = golden(name)
+    except FileNotFoundError:
+        pytest.skip("fixture %s not generated" % name)
+    E.set_precision(prec)
+    gold, cfg, g, d = _load(name)
+    B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+    g = g.to(DEV).train()
+    with torch.no_grad():
+        losses, x1p, x2p, x3p = _g_step(g, xt.to(DEV), x2t.to(DEV), x3t.to(DEV), eps_z, code)
+    got, ref = np.array([float(l) for l in losses]), gold["g_losses64"]
+    ref_own = np.abs(gold["g_losses"] - ref) / np.abs(ref)
+    e = np.abs(got - ref) / np.abs(ref)
+    sub = _sub_err(x2p, gold, "x2p64")
+    own = rel_err(gold["x2p"], gold["x2p64"])
+    log_err("w48_473x473_" + prec, loss=e.tolist(), ref32_vs_ref64_loss=ref_own.tolist(), x2p_sub=sub[0], x2p_l2=sub[1],
+            ref32_vs_ref64_x2p=own)
+    if prec == "fp32":
+        assert e.max() <= max(FP32_TOL, 3.0 * ref_own.max()), (got, ref)
+        assert sub[0] < max(FP32_TOL, 3.0 * own), sub
+    else:
+        elbo = abs(got[1:5].sum() - ref[1:5].sum()) / abs(ref[1:5].sum())
+        assert elbo < BF16_ELBO_TOL, (got, ref)
+    E.check_finite(block=True)
+
+
+# ---- (b) bf16 backward: per-parameter gradients against the fp64 oracle, G step and D step ------------------------------
+def _oracle_g_grads(sd, cfg, inputs, dtype):
+    xt, x2t, x3t, eps_z, code = inputs
+    s = {k: (v.detach().clone().to(dtype).requires_grad_("running" not in k) if v.is_floating_point() else v.clone())
+         for k, v in sd.items()}
+    c = lambda t: t.to(dtype)
+    losses, _, x2p, _ = O.full_encdec_forward(s, cfg, c(xt), c(x2t), c(x3t), [c(e) for e in eps_z], c(code))
+    losses[0].backward()
+    return s, losses, x2p.detach()
+
+
+def _cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("name", ["tiny_b2_32x64", "w18_b1_32x64"])
+def test_bf16_gradients_vs_fp64_oracle(name):
+    """The tensor-core path end to end: halo-tile dgrad, stride-2 parity-class dgrad, tcgen05 wgrad through concat lane
+    maps, mask-from-y BN backward.  Bound: per-parameter relative error against the fp64 oracle, median <= 3e-2 and
+    cosine >= 0.999 (median) / >= 0.98 (5th percentile); LSGAN terms and x2p checked as well; then the D step."""
+    E.set_precision("bf16")
+    gold, cfg, g, d = _load(name)
+    B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+    sd0 = {k: v.clone() for k, v in g.state_dict().items()}
+    s64, l64, x2p64 = _oracle_g_grads(sd0, cfg, (xt, x2t, x3t, eps_z, code), torch.float64)
+    g, d = g.to(DEV).train(), d.to(DEV).train()
+    xd, x2d, x3d = xt.to(DEV), x2t.to(DEV), x3t.to(DEV)
+    losses, x1p, x2p, x3p = _g_step(g, xd, x2d, x3d, eps_z, code)
+    got, ref = np.array([float(l) for l in losses]), np.array([float(l) for l in l64])
+    g.zero_grad()
+    losses[0].backward()
+    errs, coss = [], []
+    for k, p in g.named_parameters():
+        r = s64[k].grad
+        if r is None or float(r.norm()) < 1e-9 or k.endswith(".0.bias"):
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        errs.append(rel_err(p.grad, r))
+        coss.append(_cos(p.grad, r))
+    errs, coss = np.array(errs), np.array(coss)
+    x2e = rel_err(x2p, x2p64)
+    gan_e = np.abs(got[5:7] - ref[5:7]) / np.abs(ref[5:7])
+    log_err("bf16_grads_" + name, n=len(errs), median=np.median(errs), q90=np.quantile(errs, 0.9), max=errs.max(),
+            cos_median=np.median(coss), cos_q05=np.quantile(coss, 0.05), cos_min=coss.min(), x2p=x2e, gan=gan_e.tolist(),
+            loss_terms=(np.abs(got - ref) / np.abs(ref)).tolist())
+    assert len(errs) > 100
+    assert np.median(errs) <= 3e-2, np.median(errs)
+    assert np.median(coss) >= 0.999 and np.quantile(coss, 0.05) >= 0.98, (np.median(coss), np.quantile(coss, 0.05))
+    assert x2e < 2e-2 and gan_e.max() < 5e-2, (x2e, gan_e)
+    # D step in bf16 against the reference's golden D losses and gradient norms
+    dl = d(x2t=x2d, x2t_predict=x2p64.float().to(DEV))
+    de = np.abs(np.array([float(l) for l in dl]) - gold["d_losses"]) / np.abs(gold["d_losses"])
+    d.zero_grad()
+    dl[0].backward()
+    dn = dict(zip(gold["d_grad_names"].tolist(), gold["d_grad_norms"]))
+    en = np.array([abs(float(p.grad.double().norm()) - dn[k]) / dn[k] for k, p in d.named_parameters()
+                   if dn[k] > 1e-9 and not k.endswith("last_layer.0.bias")])
+    log_err("bf16_dstep_" + name, d_losses=de.tolist(), gradnorm_median=np.median(en), gradnorm_q90=np.quantile(en, 0.9))
+    assert de.max() < 3e-2, de
+    assert np.median(en) < 5e-2, np.median(en)
+    E.check_finite(block=True)
+
+
+# ---- (c) module-boundary activations -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny_b2_32x64", "w18_b1_32x64"])
+def test_activation_taps_match_oracle_fp32(name):
+    """stem, layer1, stage3.* and stage4.* outputs of the posterior net and of the encoder/decoder trunks."""
+    gold, cfg, g, d = _load(name)
+    B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    taps = {}
+    x = torch.cat([xt, x3t], 1)
+    with torch.no_grad():
+        ref = O.encz_forward(O.split_sd(sd, "encz_model."), cfg, x, True, taps)
+    net = g.encz_model.to(DEV).train()
+    outs = net(x=x.to(DEV))
+    for a, b in zip(outs, ref):
+        assert rel_err(a, b) < FP32_TOL
+    plan = [p for pool in net._plans().values() for p in pool][-1]
+    assert set(taps) <= set(plan.taps) and len(taps) >= 2 + 3 + 4, (sorted(taps), sorted(plan.taps))
+    worst = {}
+    for k, t in taps.items():
+        worst[k] = rel_err(plan.taps[k].to_nchw(), t)
+    # encoder + decoders: z from the oracle's reparameterisation so that both sides see the same maps
+    Zd = cfg.MODEL.EXTRA.Z_DIM
+    z = O.reparam([m[:, :Zd] for m in ref], [m[:, Zd:] for m in ref], eps_z)
+    taps2 = {}
+    with torch.no_grad():
+        O.encdec_forward(O.split_sd(sd, "encdec_model."), cfg, xt, z, code, True, taps2)
+    ed = g.encdec_model.to(DEV).train()
+    with RandnQueue([code]):
+        ed(x=xt.to(DEV), z=[t.to(DEV) for t in z])
+    plan2 = [p for pool in ed._plans().values() for p in pool][-1]
+    for k, t in taps2.items():
+        worst["encdec:" + k] = rel_err(plan2.taps[k].to_nchw(), t)
+    log_err("taps_" + name, **worst)
+    assert len(taps2) >= 3 * 9
+    enc_keys = [k for k in worst if not k.startswith("encdec:dec")]
+    assert max(worst[k] for k in enc_keys) < FP32_TOL, {k: worst[k] for k in enc_keys if worst[k] >= FP32_TOL}
+    # decoders consume the encoder's prediction (its 1e-5 rounding noise amplified by random weights): 10x slack
+    assert max(worst.values()) < 10 * FP32_TOL, {k: v for k, v in worst.items() if v >= 10 * FP32_TOL}
+
+
+# ---- (d) SyncBN kernels on one GPU: two "ranks" = two halves of the batch ------------------------------------------------
+def _to_act(x, code, tdt, Cp):
+    B, C_, H, W = x.shape
+    out = torch.zeros(B * H * W * Cp, dtype=tdt, device=DEV)
+    xd = x.contiguous().to(DEV)
+    N.call.vae2_nchw_to_act(xd.data_ptr(), out.data_ptr(), code, B, C_, Cp, H, W, Cp, C_, 0, _st())
+    return out
+
+
+def _from_act(a, code, B, C_, H, W, Cp):
+    out = torch.zeros(B, C_, H, W, dtype=torch.float32, device=DEV)
+    N.call.vae2_act_to_nchw(a.data_ptr(), out.data_ptr(), code, B, C_, H, W, Cp, C_, 0, 0, _st())
+    return out.cpu()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,relu", [((4, 18, 17, 23), True), ((2, 270, 9, 12), False), ((6, 64, 32, 64), True)])
+def test_syncbn_split_kernels_two_halves_equal_whole_batch(shape, relu, prec):
+    """vae2_bn_stats + vae2_bn_merge per half -> concatenated message (what the all-gather delivers) ->
+    vae2_bn_finalize_strided(n_parts=2) -> vae2_bn_apply; backward: per-half reduce, summed (the all-reduce),
+    vae2_bn_bwd_coeffs with the global count, per-half elemt.  Must equal F.batch_norm over the whole batch, which is
+    what torch's SyncBatchNorm computes (lib/.. tools/train.py:217; torch nn/modules/_functions.py:39-122)."""
+    code, tdt, al, tol = (0, torch.float32, 4, 2e-5) if prec == "fp32" else (1, torch.bfloat16, 8, 2e-2)
+    B, C_, H, W = shape
+    Cp = (C_ + al - 1) // al * al
+    tag = "sbn%s" % (shape,)
+    y = O.det_normal(tag + "y", shape, 2.0, 0.5)
+    y[B // 2:] += 0.7                         # the halves have different statistics
+    go = O.det_normal(tag + "go", shape)
+    if prec == "bf16":
+        y, go = y.bfloat16().float(), go.bfloat16().float()
+    gam, bet = O.det_uniform(tag + "g", (C_,), 0.5, 1.5), O.det_normal(tag + "b", (C_,), 0.1)
+    rm, rv = O.det_normal(tag + "rm", (C_,), 0.1), O.det_uniform(tag + "rv", (C_,), 0.5, 1.5)
+    yr, gr, br = y.clone().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    rm_r, rv_r = rm.clone(), rv.clone()
+    o = F.batch_norm(yr, rm_r, rv_r, gr, br, True, 0.01, 1e-5)
+    o = F.relu(o) if relu else o
+    o.backward(go)
+
+    f32 = dict(dtype=torch.float32, device=DEV)
+    halves = [(0, B // 2), (B // 2, B)]
+    group_pad = 8                              # this BN's message sits inside a wider group message: stride > 3*Cp
+    stride = 3 * Cp + group_pad
+    gathered = torch.zeros(2 * stride, **f32)
+    ya = [_to_act(y[a:b], code, tdt, Cp) for a, b in halves]
+    ga = [_to_act(go[a:b], code, tdt, Cp) for a, b in halves]
+    P = [(b - a) * H * W for a, b in halves]
+    npart = C.c_int(0)
+    parts = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * Cp, **f32)
+    for r in range(2):
+        N.call.vae2_bn_stats(ya[r].data_ptr(), parts.data_ptr(), C.byref(npart), code, P[r], Cp, Cp, _st())
+        N.call.vae2_bn_merge(parts.data_ptr(), npart.value, Cp, gathered.data_ptr() + 4 * r * stride, _st())
+    gd, bd, rmd, rvd = gam.to(DEV), bet.to(DEV), rm.to(DEV), rv.to(DEV)
+    nbt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    mean, invstd, scale, shift = (torch.zeros(Cp, **f32) for _ in range(4))
+    N.call.vae2_bn_finalize_strided(gathered.data_ptr(), 2, stride, C_, Cp, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(),
+                                    rvd.data_ptr(), nbt.data_ptr(), 0.01, 1e-5, mean.data_ptr(), invstd.data_ptr(),
+                                    scale.data_ptr(), shift.data_ptr(), _st())
+    oa = [torch.zeros_like(t) for t in ya]
+    for r in range(2):
+        N.call.vae2_bn_apply(ya[r].data_ptr(), None, oa[r].data_ptr(), code, P[r], Cp, Cp, Cp, Cp, scale.data_ptr(),
+                             shift.data_ptr(), 1 if relu else 0, _st())
+    out = torch.cat([_from_act(oa[r], code, halves[r][1] - halves[r][0], C_, H, W, Cp) for r in range(2)], 0)
+    e_fwd = rel_err(out, o.detach())
+    e_mean = rel_err(mean[:C_].cpu(), y.mean((0, 2, 3)))
+    e_run = max(rel_err(rmd.cpu(), rm_r), rel_err(rvd.cpu(), rv_r))
+    assert e_fwd < tol and e_mean < 1e-5 and e_run < 1e-5 and int(nbt) == 1, (e_fwd, e_mean, e_run)
+    # backward
+    parts2 = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * Cp, **f32)
+    sums = [torch.zeros(2 * Cp, **f32) for _ in range(2)]
+    for r in range(2):
+        N.call.vae2_bn_bwd_reduce(ga[r].data_ptr(), oa[r].data_ptr(), ya[r].data_ptr(), parts2.data_ptr(), C.byref(npart),
+                                  code, P[r], Cp, Cp, Cp, Cp, mean.data_ptr(), invstd.data_ptr(), 1 if relu else 0, _st())
+        N.call.vae2_bn_bwd_finalize(parts2.data_ptr(), npart.value, C_, Cp, sums[r].data_ptr(), _st())
+    gsum = sums[0] + sums[1]                   # the all-reduce
+    dgs, dbs, dxs = [], [], []
+    for r in range(2):
+        dg, db = torch.zeros(C_, **f32), torch.zeros(C_, **f32)
+        c1, c2 = torch.zeros(Cp, **f32), torch.zeros(Cp, **f32)
+        N.call.vae2_bn_bwd_coeffs(gsum.data_ptr(), C_, Cp, 1.0 / (P[0] + P[1]), dg.data_ptr(), db.data_ptr(), 0,
+                                  sums[r].data_ptr(), c1.data_ptr(), c2.data_ptr(), _st())
+        dya = torch.zeros_like(ya[r])
+        N.call.vae2_bn_bwd_elemt(ga[r].data_ptr(), oa[r].data_ptr(), ya[r].data_ptr(), dya.data_ptr(), None, code, P[r],
+                                 Cp, Cp, Cp, Cp, Cp, Cp, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+                                 c1.data_ptr(), c2.data_ptr(), 1 if relu else 0, 0, 0, _st())
+        dgs.append(dg.cpu())
+        dbs.append(db.cpu())
+        dxs.append(_from_act(dya, code, halves[r][1] - halves[r][0], C_, H, W, Cp))
+    e_dx = rel_err(torch.cat(dxs, 0), yr.grad)
+    e_dg = rel_err(dgs[0] + dgs[1], gr.grad)    # DDP sums (averages) the per-rank parameter gradients
+    e_db = rel_err(dbs[0] + dbs[1], br.grad)
+    log_err("syncbn_%s_%s" % (prec, "x".join(map(str, shape))), fwd=e_fwd, mean=e_mean, running=e_run, dx=e_dx, dgamma=e_dg,
+            dbeta=e_db)
+    assert e_dx < 5 * tol and e_dg < 5 * tol and e_db < 5 * tol, (e_dx, e_dg, e_db)
+
+
+# ---- (e) BASELINE configs[0]: the toy wrapper on the device --------------------------------------------------------------
+def test_toy_wrapper_matches_reference_golden():
+    gold = golden("toy_b500")
+    cfg = cfg_of("vae2_hrnet_tiny_32x64.yaml")
+    nets = [T.get_encz_model(cfg), T.get_encdec_model(cfg), T.get_D_model(cfg)]
+    g = U.FullToyModel_encdec(nets[0], nets[1], nets[2], Cr.L1Loss(), Cr.KLLoss(), Cr.lsgan_adversarial_loss(),
+                              1.0, 0.1, 1.0, 1.0)
+    O.fill_state_dict(g.state_dict(), seed_tag="toy_b500", mode="trained")
+    g = g.to(DEV).train()
+    xt, x2t, x3t = (torch.from_numpy(gold[k]).to(DEV) for k in ("xt", "x2t", "x3t"))
+    eps, code = O.det_normal("toy_b500:eps", (500, 8)), O.det_normal("toy_b500:code", (500, 8))
+    with RandnQueue([code]):
+        losses, x1p, x2p, x3p = g(xt=xt, x2t=x2t, x3t=x3t, multiplier=0.5, eps=eps.to(DEV))
+    got = np.array([float(l) for l in losses])
+    e = np.abs(got - gold["losses"]) / np.abs(gold["losses"])
+    acts = [rel_err(a, gold[k]) for a, k in ((x1p, "x1p"), (x2p, "x2p"), (x3p, "x3p"))]
+    g.zero_grad()
+    losses[0].backward()
+    norms = dict(zip(gold["grad_names"].tolist(), gold["grad_norms"]))
+    en = np.array([abs(float(p.grad.double().norm()) - norms[k]) / norms[k] for k, p in g.named_parameters()
+                   if p.grad is not None and norms.get(k, 0) > 1e-9])
+    log_err("toy_b500", losses=e.tolist(), acts=acts, gradnorm_max=en.max())
+    assert e.max() < FP32_TOL and max(acts) < FP32_TOL and en.max() < 1e-3 and len(en) >= 20, (e, acts, en.max())
+    # the D wrapper
+    dw = U.FullToyModel_D(nets[2], Cr.lsgan_adversarial_loss()).to(DEV)
+    dl = dw(x2t, x2p.detach())
+    ref = 0.5 * (((nets[2](x2t) - 1) ** 2).sum() + (nets[2](x2p.detach()) ** 2).sum()) / 500
+    assert abs(float(dl[0]) - float(ref)) / abs(float(ref)) < FP32_TOL
+
+
+# ---- CUDA graphs: forward side effects happen once per call --------------------------------------------------
+def test_cuda_graph_capture_applies_bn_side_effects_once():
+    name = "tiny_b2_32x64"
+    stats = {}
+    for graphs in (False, True):
+        gold, cfg, g, d = _load(name)
+        B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+        net = g.D_model_frame.to(DEV).train()
+        E.use_cuda_graphs(graphs)
+        try:
+            for _ in range(3):                       # first call captures, the next two replay
+                net(x2t[:, :3].to(DEV))
+        finally:
+            E.use_cuda_graphs(False)
+        stats[graphs] = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}
+    for k, v in stats[False].items():
+        if "num_batches" in k:
+            assert int(v) == 3 and int(stats[True][k]) == 3, (k, int(v), int(stats[True][k]))
+        else:
+            assert rel_err(stats[True][k], v) < 1e-6, k

@@ -198,3 +198,39 @@ def test_activation_arena_shares_memory_across_phases_only():
         os.environ.pop("VAE2_ACT_ARENA", None)
         A.CHUNK_BYTES = old_chunk
         A.reset()
+
+
+def test_activation_arena_recycles_dropped_plans():
+    """A dropped plan's extents go back to its phase's free list: re-recording (new batch size, moved parameters,
+    reset_plans) must not grow the arena (the bump allocator used to leak them)."""
+    A = E.ActArena
+    dev = torch.device("cpu")
+    old_chunk = A.CHUNK_BYTES
+    A.reset()
+    A.CHUNK_BYTES = 8192 * 4
+
+    class Owner:
+        def __init__(self):
+            self.arena_extents = []
+    try:
+        a, b = Owner(), Owner()
+        with E.activation_phase("G"):
+            ta = [A.alloc(dev, torch.float32, n, owner=a) for n in (1000, 2000)]
+            tb = [A.alloc(dev, torch.float32, n, owner=b) for n in (500,)]
+        pool = next(iter(A._pools.values()))
+        before = sum(c.numel() for c in pool["chunks"])
+        ptrs = sorted(t.data_ptr() for t in ta)
+        A.give_back(a.arena_extents)
+        with E.activation_phase("G"):
+            c = Owner()
+            tc = [A.alloc(dev, torch.float32, n, owner=c) for n in (2500, 400)]
+        assert tc[0].data_ptr() == ptrs[0], "coalesced extents of the dropped plan are reused first-fit"
+        assert sum(ch.numel() for ch in pool["chunks"]) == before, "no growth"
+        spans = sorted((t.data_ptr(), t.data_ptr() + 4 * t.numel()) for t in tc + tb)
+        assert all(x[1] <= y[0] for x, y in zip(spans, spans[1:])), "live buffers stay disjoint"
+        with E.activation_phase("D"):
+            td = A.alloc(dev, torch.float32, 100, owner=Owner())
+        assert td.data_ptr() == pool["chunks"][0].data_ptr(), "other phases still start at the chunk base"
+    finally:
+        A.CHUNK_BYTES = old_chunk
+        A.reset()

@@ -87,3 +87,23 @@ def test_known_answers():
     assert float(O.l1_loss(torch.ones(4, 3), torch.zeros(4, 3))) == 3.0
     assert float(O.lsgan_loss(torch.zeros(2, 5), "real")) == 5.0
     assert O.branch_sizes(473, 473) == [(473, 473), (237, 237), (119, 119), (60, 60)]
+
+
+def test_oracle_matches_reference_at_baseline_size_w18_256x512():
+    """BASELINE configs[1] size: the oracle's G-step forward (training-mode BN, no autograd: ~15 s) against the
+    subsampled fixture the unmodified reference produced (oracle/make_golden.py w18_full)."""
+    name = "w18_b1_256x512"
+    gold = golden(name)
+    cfg = cfg_of(str(gold["cfg"]))
+    B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+    sd = _sd(cfg, name, "trained")
+    with torch.no_grad():
+        losses, x1p, x2p, x3p = O.full_encdec_forward(sd, cfg, xt, x2t, x3t, eps_z, code)
+    np.testing.assert_allclose(np.array([float(l) for l in losses]), gold["g_losses"], rtol=2e-5)
+    s = int(gold["sub"])
+    for a, k in ((x1p, "x1p"), (x2p, "x2p"), (x3p, "x3p")):
+        assert rel_err(a[..., ::s, ::s], gold[k]) < 2e-5, k
+        l2 = a.double().pow(2).sum(dim=(0, 2, 3)).sqrt().numpy()
+        np.testing.assert_allclose(l2, gold[k + "_l2"], rtol=2e-5)
+    for k in ("encz_model.bn1.running_mean", "encdec_model.decf_bn2.running_mean", "D_model_frame.bn1.running_var"):
+        assert rel_err(sd[k], gold["after:" + k]) < 1e-5, k

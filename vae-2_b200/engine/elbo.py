@@ -11,8 +11,19 @@ import torch
 
 from . import native as N
 
-_pending_flags = []   # (names, device int32 tensor) from earlier steps, checked lazily
+import os
+
+_pending_flags = []   # (names, device int32 tensor, event) of launches whose finite-flags were not read yet
+MAX_PENDING = 16      # callers that never check (FullModel_D, stand-alone criteria) are drained beyond this
 LAUNCHES = {"n": 0}
+
+
+def finite_check_mode():
+    """'eager' (default): the wrappers read this step's flags BEFORE returning the losses, so a nan/inf raises
+    before backward / optimizer.step like the reference's _anomoly_detection (lib/utils/utils.py:63-65), at the
+    cost of ONE host sync per step instead of the reference's 14.  'lazy': flags are read at the next wrapper
+    call (no sync at all; a bad step is reported one step late)."""
+    return os.environ.get("VAE2_FINITE_CHECK", "eager")
 
 
 def _table(structs, dev):
@@ -33,6 +44,22 @@ def check_finite(block=False):
             keep.append((names, flags, ev))
     _pending_flags[:] = keep        # a reported launch is consumed even when it raises
     assert failed is None, "{} got nan or inf".format(failed)
+
+
+def _bound_pending():
+    """Keep the pending list short when nobody calls check_finite: completed launches are consumed first (no
+    stall), and past MAX_PENDING the oldest are waited for."""
+    if len(_pending_flags) > MAX_PENDING:
+        check_finite(block=False)
+    if len(_pending_flags) > MAX_PENDING:
+        old = _pending_flags[:len(_pending_flags) - MAX_PENDING]
+        del _pending_flags[:len(old)]
+        failed = None
+        for names, flags, ev in old:
+            for n, b in zip(names, flags.tolist()):
+                if b != 0 and failed is None:
+                    failed = n
+        assert failed is None, "{} got nan or inf".format(failed)
 
 
 class _Terms(torch.autograd.Function):
@@ -70,6 +97,7 @@ class _Terms(torch.autograd.Function):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         _pending_flags.append((names, flags, ev))
+        _bound_pending()
         ctx.spec, ctx.nslots = spec, nslots
         ctx.save_for_backward(*tensors)
         ctx.n_z = len(z_outs)

@@ -86,13 +86,25 @@ class ActArena:
         return os.environ.get("VAE2_ACT_ARENA", "1") != "0"
 
     @classmethod
-    def alloc(cls, device, tdtype, numel):
+    def alloc(cls, device, tdtype, numel, owner=None):
+        """Bump-allocate from the current phase's cursor, after a first-fit look at the extents that dropped plans
+        of this phase gave back (Plan.release): re-recording a plan (new batch size, parameters moved, reset_plans)
+        reuses its predecessor's memory instead of growing the arena."""
         if cls.phase is None or not cls.enabled():
             return None
         esize = torch.empty(0, dtype=tdtype).element_size()
-        pool = cls._pools.setdefault((str(device), tdtype), {"chunks": [], "cur": {}})
-        cur = pool["cur"].setdefault(cls.phase, [0, 0])
+        key = (str(device), tdtype)
+        pool = cls._pools.setdefault(key, {"chunks": [], "cur": {}, "free": {}})
         n = pad_to(numel, 128)
+        free = pool["free"].setdefault(cls.phase, [])
+        for i, (ci, off, sz) in enumerate(free):
+            if sz >= n:
+                if sz == n:
+                    free.pop(i)
+                else:
+                    free[i] = (ci, off + n, sz - n)
+                return cls._take(pool, key, ci, off, n, numel, owner)
+        cur = pool["cur"].setdefault(cls.phase, [0, 0])
         while True:
             ci, off = cur
             if ci >= len(pool["chunks"]):
@@ -100,10 +112,37 @@ class ActArena:
             chunk = pool["chunks"][ci]
             if off + n <= chunk.numel():
                 cur[1] = off + n
-                t = chunk[off:off + numel]
-                t.zero_()
-                return t
+                return cls._take(pool, key, ci, off, n, numel, owner)
+            if chunk.numel() - off >= 128:      # the tail of a chunk that did not fit stays usable for smaller buffers
+                free.append((ci, off, chunk.numel() - off))
             cur[0], cur[1] = ci + 1, 0
+
+    @classmethod
+    def _take(cls, pool, key, ci, off, n, numel, owner):
+        t = pool["chunks"][ci][off:off + numel]
+        t.zero_()
+        if owner is not None:
+            owner.arena_extents.append((key, cls.phase, ci, off, n))
+        return t
+
+    @classmethod
+    def give_back(cls, extents):
+        for key, phase, ci, off, n in extents:
+            pool = cls._pools.get(key)
+            if pool is None or ci >= len(pool["chunks"]):
+                continue                 # the arena was reset in the meantime
+            free = pool["free"].setdefault(phase, [])
+            free.append((ci, off, n))
+        for pool in cls._pools.values():  # coalesce neighbours
+            for phase, free in pool["free"].items():
+                free.sort()
+                out = []
+                for e in free:
+                    if out and out[-1][0] == e[0] and out[-1][1] + out[-1][2] == e[1]:
+                        out[-1] = (e[0], out[-1][1], out[-1][2] + e[2])
+                    else:
+                        out.append(e)
+                free[:] = out
 
     @classmethod
     def reset(cls):
@@ -135,7 +174,7 @@ class Act:
         pr = plan.prec
         if root is None:
             self.Cp = pad_to(C_, pr.tot_align) if Cp is None else Cp
-            self.buf = ActArena.alloc(plan.device, pr.tdtype, self.B * H * W * self.Cp)
+            self.buf = ActArena.alloc(plan.device, pr.tdtype, self.B * H * W * self.Cp, owner=plan)
             if self.buf is None:
                 self.buf = torch.zeros(self.B * H * W * self.Cp, dtype=pr.tdtype, device=plan.device)
             else:
@@ -222,6 +261,9 @@ class Plan:
         self._garena, self._goff = None, 0
         self.all_acts = []
         self.arena_phase = None               # set when an activation buffer comes from the phase-shared ActArena
+        self.arena_extents = []               # (pool key, phase, chunk, offset, size) of those buffers
+        self.released = False
+        self.taps = {}                        # name -> Act at module boundaries (debug / parity tests: Act.to_nchw)
         self.concat_roots = []
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
         self.fp32_tc = os.environ.get("VAE2_FP32_TC", "0") == "1"
@@ -387,6 +429,13 @@ class Plan:
         self.n_launch_fwd, self.n_launch_bwd = len(self.fwd), len(self.bwd)
         return self
 
+    def release(self):
+        """Drop this plan: its arena extents go back to the phase's free list (the plan must not run again)."""
+        self.released = True
+        ActArena.give_back(self.arena_extents)
+        self.arena_extents = []
+        self.graph_fwd = self.graph_bwd = None
+
     def grad_view(self, p):
         i = self._param_index[id(p)]
         return self.flat_grad[self._grad_off[i]:self._grad_off[i] + p.numel()].view(p.shape)
@@ -407,10 +456,14 @@ class Plan:
         eager = N.COUNTERS["native_calls"] - c0
         if use_graph:
             if self.graph_fwd is None:
+                # The warm-up pass inside _capture IS this call's execution (capturing launches nothing), so the
+                # graph is not replayed on top of it: forward side effects (BN running statistics,
+                # num_batches_tracked) must happen exactly once per call, as in eager mode and in the reference.
                 c1 = N.COUNTERS["native_calls"]
                 self.graph_fwd = self._capture(self.fwd)
                 self.native_fwd = (N.COUNTERS["native_calls"] - c1) // 2   # warm-up pass + capture pass
-            self.graph_fwd.replay()
+            else:
+                self.graph_fwd.replay()
             body = self.native_fwd
         else:
             c1 = N.COUNTERS["native_calls"]
@@ -431,9 +484,10 @@ class Plan:
         if use_graph:
             if self.graph_bwd is None:
                 c1 = N.COUNTERS["native_calls"]
-                self.graph_bwd = self._capture(self.bwd)
+                self.graph_bwd = self._capture(self.bwd)      # its warm-up pass is this call's execution
                 self.native_bwd = (N.COUNTERS["native_calls"] - c1) // 2
-            self.graph_bwd.replay()
+            else:
+                self.graph_bwd.replay()
             body = self.native_bwd
         else:
             c1 = N.COUNTERS["native_calls"]

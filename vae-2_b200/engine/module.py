@@ -115,6 +115,10 @@ class EngineModule(nn.Module):
         return d
 
     def reset_plans(self):
+        for pool in self._plans().values():
+            for plan in pool:
+                if not plan.busy:
+                    plan.release()
         self.__dict__["_plan_cache"] = {}
 
     def _sync_world(self):
@@ -137,7 +141,10 @@ class EngineModule(nn.Module):
         pool = self._plans().setdefault(key, [])
         plan = next((p for p in pool if not p.busy), None)
         if plan is not None and plan.param_ptrs != tuple(p.data_ptr() for p in plan.params):
-            pool.clear()      # parameters were re-allocated (.to(), .cuda(), ...): recorded pointers are stale
+            for old in pool:  # parameters were re-allocated (.to(), .cuda(), ...): recorded pointers are stale
+                if not old.busy:
+                    old.release()
+            pool.clear()
             plan = None
         if plan is None:
             with torch.cuda.device(dev):

@@ -4,7 +4,8 @@ keywords ``predict=/target=``, ``mu=/logvar=``, ``sample=/mode=``, same value: s
 
 Each module is one launch of the table-driven ELBO kernel (engine/elbo.py, csrc/elbo.cu);
 ``utils.utils.FullModel_encdec`` batches all terms of a step into two launches instead.
-The segmentation losses of the reference (CrossEntropy/OHEM, :11-58) are outside the VAE^2 path.
+The segmentation losses of the reference (CrossEntropy/OHEM, :11-58) are outside the VAE^2 path and fall through
+to the reference's own module (see _fallthrough.py).
 """
 import os
 import sys
@@ -17,7 +18,15 @@ if _LIB not in sys.path:
     sys.path.insert(0, _LIB)
 from _engine_loader import engine  # noqa: E402
 
+import _fallthrough  # noqa: E402
+
 _E = engine()
+
+# legacy segmentation losses (reference :11-58) are outside the VAE^2 path: taken from the reference's own module
+# when its lib/ is on sys.path behind this tree, so that ``from core.criterion import *`` (tools/train.py:32) sees them
+_ref = _fallthrough.reference_module("core.criterion")
+if _ref is not None:
+    CrossEntropy, OhemCrossEntropy = _ref.CrossEntropy, _ref.OhemCrossEntropy
 
 
 class L1Loss(nn.Module):

@@ -353,11 +353,16 @@ class HighResolutionNet(EngineModule):
         g = lambda n: getattr(self, p + n)
         x = rec.conv_bn(x, g("conv1"), g("bn1"), relu=True)
         x = rec.conv_bn(x, g("conv2"), g("bn2"), relu=True)
+        taps = rec.plan.taps          # module-boundary activations by the oracle's tap names (parity tests)
+        taps[p + "stem"] = x
         x = _emit_stack(rec, g("layer1"), x)
+        taps[p + "layer1"] = x
         xs = _emit_transition(rec, g("transition1"), [x], 1)
         ys = self._emit_stage(rec, g("stage2"), xs)
         xs = _emit_transition(rec, g("transition2"), ys, len(ys))
         ys = self._emit_stage(rec, g("stage3"), xs)
+        for i, t in enumerate(ys):
+            taps["%sstage3.%d" % (p, i)] = t
         if code_maps is None:
             xs = _emit_transition(rec, g("transition3"), ys, len(ys))
         else:
@@ -371,6 +376,8 @@ class HighResolutionNet(EngineModule):
             cat, slices = rec.concat([a.C for a in xs], xs[0].H, xs[0].W, name=p + "headcat")
             outs = [slices[0]] + [None] * (len(xs) - 1)
         ys = self._emit_stage(rec, g("stage4"), xs, outs)
+        for i, t in enumerate(ys):
+            taps["%sstage4.%d" % (p, i)] = t
         if not head_cat:
             return ys, None
         for b in range(1, len(ys)):      # bilinear up-sample straight into the concat slices (:833-839)

@@ -24,7 +24,18 @@ if _LIB not in sys.path:
     sys.path.insert(0, _LIB)
 from _engine_loader import engine  # noqa: E402
 
+import _fallthrough  # noqa: E402
+
 _E = engine()
+
+
+def __getattr__(name):
+    """PEP 562: names this module does not define (FullModel, FullModel_all, get_confusion_matrix -- the legacy
+    segmentation path, reference :21-37, :302-352, :434-457) come from the reference's own utils.utils when its lib/
+    is on sys.path behind this tree."""
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _fallthrough.reference_attr("utils.utils", name)
 
 
 def _fast_losses(*crits):
@@ -109,6 +120,10 @@ class FullModel_encdec(nn.Module):
         losses_all = self.x1recon_lambda * xt_recon_loss + self.x2recon_lambda * x2t_recon_loss + \
             self.x3recon_lambda * x3t_recon_loss + kl_w * z_KL_loss + \
             self.gan_lambda * (x2t_gan_sequence_loss + x2t_gan_frame_loss)                       # :150-152
+        if _E.finite_check_mode() == "eager":
+            # reference :94, :107 assert BEFORE backward / optimizer.step; one blocking read of this step's
+            # device-side counters (z maps and the three predictions) keeps that guarantee
+            _E.check_finite(block=True)
         return [torch.unsqueeze(losses_all, 0), xt_recon_loss, x2t_recon_loss, x3t_recon_loss, z_KL_loss,
                 x2t_gan_sequence_loss, x2t_gan_frame_loss], xt_predict, x2t_predict, x3t_predict
 
