@@ -30,7 +30,9 @@ WORKLOADS = {
     # name: (yaml, H, W, per-GPU batch, algorithmic conv FLOP per sample for a full iteration)
     # per-GPU batch: the largest that leaves ~30 GB of the 180 GB free (fp32 B=4 peaks at 148 GB, bf16 B=6 at 129 GB)
     "w18_256x512": ("vae2_hrnet_w18_small_v2_256x512.yaml", 256, 512, {"fp32": 4, "bf16": 6}, 7.60e12),
-    "w18_1024x2048": ("vae2_hrnet_w18_small_v2_1024x2048.yaml", 1024, 2048, 1, 121.6e12),
+    "w18_1024x2048": ("vae2_hrnet_w18_small_v2_1024x2048.yaml", 1024, 2048, 1, 121.6e12),     # BASELINE configs[2]
+    "w48_473x473": ("vae2_hrnet_w48_473x473.yaml", 473, 473, {"fp32": 1, "bf16": 2}, 126.9e12),   # configs[4], LIP
+    "w48_520x520": ("vae2_hrnet_w48_520x520.yaml", 520, 520, {"fp32": 1, "bf16": 2}, 152.3e12),   # configs[4], PASCAL-Ctx
     "tiny_32x64": ("vae2_hrnet_tiny_32x64.yaml", 32, 64, 2, None),
 }
 FRAMES_PER_SAMPLE = 9
@@ -114,67 +116,155 @@ def build_models(cfg, dev, world, local_rank):
     return g, d, opt_g, opt_d
 
 
+def reduce_tensor(t):
+    """lib/core/function.py:32-43: the logging reduction of a loss to rank 0 (in place, under no_grad)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        with torch.no_grad():
+            dist.reduce(t, dst=0)
+    return t
+
+
 def train_step(g, d, opt_g, opt_d, xt, x2t, x3t):
+    """One iteration of the reference's adversarial_train (lib/core/function.py:491-512)."""
     losses, _, x2p, _ = g(xt=xt, x2t=x2t, x3t=x3t, multiplier=1.0, is_baseline=False, baseline_mode="VAE_NATIVE")
+    lg = reduce_tensor(losses[0])
     opt_g.zero_grad()
     losses[0].backward()
     opt_g.step()
     dl = d(x2t=x2t, x2t_predict=x2p.detach())
+    ld = reduce_tensor(dl[0])
     opt_d.zero_grad()
     dl[0].backward()
     opt_d.step()
-    return losses[0], dl[0]
+    return lg, ld
 
 
-def conv_microbench(dev, E, steps=20):
-    """The dominant launch of the step, timed alone with CUDA events on its own stream: the
-    64->64 3x3 s1 conv at full resolution (16 % of the W18 MACs).  Returns
-    (TFLOP/s algorithmic, ms per launch, description)."""
-    import ctypes as C
-    N = E.native
-    prec = E.get_precision()
-    code, tdt, al = (0, torch.float32, 4) if prec == "fp32" else (1, torch.bfloat16, 16)
-    B, H, W, Cin, Cout, k = 1, 256, 512, 64, 64, 3
-    x = torch.randn(B * H * W * Cin, device=dev).to(tdt)
-    y = torch.zeros(B * H * W * Cout, dtype=tdt, device=dev)
-    wp = torch.randn(k * k * Cin * Cout, device=dev) * 0.05
-    eng = 0
-    if prec == "bf16":   # tcgen05 path: packed bf16 weights [tap][Cout][Cin]
-        wp, eng = wp.to(torch.bfloat16), 1
-    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin, ldx=Cin, Ho=H, Wo=W, Cout_p=Cout, ldy=Cout, k=k, stride=1, pad=1)
-    s = torch.cuda.Stream(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    with torch.cuda.stream(s):
-        for _ in range(3):
-            N.call.vae2_conv2d_fwd(x.data_ptr(), wp.data_ptr(), None, y.data_ptr(), code, C.byref(g), eng, s.cuda_stream)
-        for a, b in ev:
-            flush.zero_()
-            a.record(s)
-            N.call.vae2_conv2d_fwd(x.data_ptr(), wp.data_ptr(), None, y.data_ptr(), code, C.byref(g), eng, s.cuda_stream)
-            b.record(s)
-    s.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)[steps // 2]
-    flop = 2.0 * B * H * W * Cin * Cout * k * k
-    return flop / (ms * 1e-3) / 1e12, ms, "conv3x3 s1 64->64 @256x512 B=1 fwd (%s, %s, L2 flushed between launches)" % (prec, "tcgen05" if eng else "CUDA-core FMA")
+def step_roofline(E, dev, step_fn, hbm_peak, tf_peak, src):
+    """Roofline of the kernel with the LARGEST TIME SHARE of the step (not a hand-picked shape): one extra iteration
+    runs eagerly with every C-ABI launch bracketed by CUDA events on the launching stream (engine/profiler.py),
+    grouped by kernel; achieved = that kernel's algorithmic FLOPs (bytes) summed over its launches / its summed time."""
+    graphs = E.module._STATE["cuda_graphs"]
+    E.use_cuda_graphs(False)
+    try:
+        step_fn()                                   # eager warm-up of the same plans (no re-recording)
+        torch.cuda.synchronize(dev)
+        with E.KernelProfile() as kp:
+            step_fn()
+    finally:
+        E.use_cuda_graphs(graphs)
+    fams = kp.by_kernel()
+    total = sum(f["ms"] for f in fams) or 1.0
+    top = fams[0]
+
+    def fr(r):
+        t = r["ms"] * 1e-3
+        tf, gb = r["flop"] / t / 1e12, r["bytes"] / t / 1e9
+        t_tensor, t_hbm = r["flop"] / (tf_peak * 1e12), r["bytes"] / (hbm_peak * 1e9)
+        return {"tflops": tf, "tensor_frac": tf / tf_peak, "gbs": gb, "hbm_frac": gb / hbm_peak,
+                "bound": "tensor" if t_tensor >= t_hbm else "hbm", "frac": max(t_tensor, t_hbm) / t}
+    f = fr(top)
+    shp = top["top_shape"]
+    fs = fr(shp)
+    traffic, tsrc = ncu_traffic(top["kernel"], shp["shape"])
+    roof = {"bound": f["bound"], "achieved": f["tflops"] if f["bound"] == "tensor" else f["gbs"],
+            "peak": tf_peak if f["bound"] == "tensor" else hbm_peak, "unit": "TFLOP/s" if f["bound"] == "tensor" else "GB/s",
+            "frac": f["frac"], "traffic": traffic, "traffic_source": tsrc,
+            "kernel": top["kernel"], "share_of_step": top["ms"] / total, "launches": top["n"],
+            "ms_per_launch": top["ms"] / top["n"], "tensor": {"achieved": f["tflops"], "peak": tf_peak, "frac": f["tensor_frac"]},
+            "hbm": {"achieved": f["gbs"], "peak": hbm_peak, "frac": f["hbm_frac"]},
+            "top_shape": {"shape": shp["shape"], "launches": shp["n"], "ms_per_launch": shp["ms"] / shp["n"],
+                          "algorithmic_flop_per_launch": shp["flop"] / shp["n"],
+                          "algorithmic_bytes_per_launch": shp["bytes"] / shp["n"], "tensor_frac": fs["tensor_frac"],
+                          "hbm_frac": fs["hbm_frac"]},
+            "peak_source": src + " (sustained bf16 / copy bandwidth; kernel timed inside the step)",
+            "how": "CUDA events around every launch of one eager iteration, grouped by kernel; dominant by summed time"}
+    table = [{"kernel": x["kernel"], "share": x["ms"] / total, "ms": x["ms"], "n": x["n"], **{k: v for k, v in fr(x).items()
+              if k in ("tensor_frac", "hbm_frac", "bound", "frac")}} for x in fams[:12]]
+    return roof, table, total
 
 
-def cpu_port_step(cfg, sd, opt, H, W, B, tag):
-    """One G+D iteration of the reference algorithm on the host CPU (oracle port + torch autograd + Adam)."""
-    from oracle import vae2_oracle as O
+def ncu_traffic(kernel, shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full summary
+    (profiles/ncu_traffic.json, written by tools/ncu_summarise.py from the .ncu-rep of the same build); None if that
+    kernel has not been captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        db = json.load(open(path))
+    except ValueError:
+        return None, None
+    base = kernel.split("+")[0].split("::")[-1]
+    best = None
+    for e in db.get("kernels", []):
+        if base in e.get("kernel", ""):
+            if best is None or e.get("shape") == shape:
+                best = e
+    if best is None:
+        return None, None
+    return best.get("dram_bytes"), "%s (%s, %s)" % (db.get("source", "profiles/ncu_traffic.json"), best.get("kernel"), best.get("shape"))
+
+
+# ---- reference arm: the reference's own CPU implementation of the path on the box's host cores ------------------------
+def _ref_tree():
+    for p in (os.path.join(ROOT, "oracle", "_ref"), os.environ.get("VAE2_REFERENCE", "/root/reference")):
+        if p and os.path.isfile(os.path.join(p, "lib", "models", "enc_hrnet.py")):
+            return p
+    return None
+
+
+def cpu_reference_setup(cfg):
+    """The UNMODIFIED reference modules (oracle/_ref, vendored by oracle/make_ref.py) when present -- kind
+    'reference' -- else the oracle port driven by torch autograd -- kind 'port'.  Returns (kind, step_fn)."""
+    import numpy as np
+    ref = _ref_tree()
     Z = cfg.MODEL.EXTRA.Z_DIM
-    xt, x2t, x3t = (torch.randn(B, 9, H, W) for _ in range(3))
-    eps_z = [torch.randn(B, Z, h, w) for h, w in O.branch_sizes(H, W)]
-    code = torch.randn(B, Z, 1, 1)
-    losses, _, x2p, _ = O.full_encdec_forward(sd, cfg, xt, x2t, x3t, eps_z, code)
-    opt[0].zero_grad()
-    losses[0].backward()
-    opt[0].step()
-    dl = O.full_d_forward(sd, cfg, x2t, x2p.detach())
-    opt[1].zero_grad()
-    dl[0].backward()
-    opt[1].step()
-    return float(losses[0])
+    if ref is not None:
+        np.int = int                       # numpy >= 1.24 removed it (enc_hrnet.py:321,596,700)
+        # the reference's lib/ must win over this repo's mirror for models / utils / core
+        for m in [k for k in sys.modules if k.split(".")[0] in ("models", "utils", "core")]:
+            del sys.modules[m]
+        sys.path[:] = [p for p in sys.path if not p.endswith(os.path.join("vae-2_b200", "lib"))]
+        sys.path.insert(0, os.path.join(ref, "lib"))
+        import models.enc_hrnet as M
+        import utils.utils as U
+        import core.criterion as Cr
+        assert ref in M.__file__, M.__file__
+        nets = [M.get_encz_model(cfg), M.get_encdec_model(cfg), M.get_D_sequence_model(cfg), M.get_D_frame_model(cfg)]
+        g = U.FullModel_encdec(nets[0], nets[1], nets[2], nets[3], Cr.L1Loss(), Cr.KLLoss(), Cr.lsgan_adversarial_loss(),
+                               cfg.TRAIN.X1RECON_LAMBDA, cfg.TRAIN.X2RECON_LAMBDA, cfg.TRAIN.X3RECON_LAMBDA,
+                               cfg.TRAIN.GAN_LAMBDA).train()
+        d = U.FullModel_D(nets[2], nets[3], Cr.lsgan_adversarial_loss()).train()
+        og = torch.optim.Adam([p for n, p in g.named_parameters() if p.requires_grad and "D_model" not in n], lr=cfg.TRAIN.LR)
+        od = torch.optim.Adam([p for n, p in d.named_parameters() if p.requires_grad and "D_model" in n], lr=cfg.TRAIN.LR)
+
+        def step(xt, x2t, x3t):            # lib/core/function.py:491-512
+            losses, _, x2p, _ = g(xt=xt, x2t=x2t, x3t=x3t, multiplier=1.0, is_baseline=False, baseline_mode="VAE_NATIVE")
+            og.zero_grad()
+            losses[0].backward()
+            og.step()
+            dl = d(x2t=x2t, x2t_predict=x2p.detach())
+            od.zero_grad()
+            dl[0].backward()
+            od.step()
+            return float(losses[0]) + float(dl[0])
+        return "reference", step
+    from oracle import vae2_oracle as O
+    sd, opt = cpu_port_setup(cfg)
+
+    def step(xt, x2t, x3t):
+        B, _, H, W = xt.shape
+        eps_z = [torch.randn(B, Z, h, w) for h, w in O.branch_sizes(H, W)]
+        losses, _, x2p, _ = O.full_encdec_forward(sd, cfg, xt, x2t, x3t, eps_z, torch.randn(B, Z, 1, 1))
+        opt[0].zero_grad()
+        losses[0].backward()
+        opt[0].step()
+        dl = O.full_d_forward(sd, cfg, x2t, x2p.detach())
+        opt[1].zero_grad()
+        dl[0].backward()
+        opt[1].step()
+        return float(losses[0]) + float(dl[0])
+    return "port", step
 
 
 def cpu_port_setup(cfg):
@@ -192,40 +282,57 @@ def cpu_port_setup(cfg):
     return sd, (torch.optim.Adam(pg, lr=1e-4), torch.optim.Adam(pd, lr=1e-4))
 
 
-def cpu_baseline(cfg, H, W, steps=1, warmup=0):
-    """Bounded sample: the same G+D iteration at (H/2, W/2), B=1; frames/s is scaled to the full
-    frame size by the pixel ratio (conv cost is linear in pixels)."""
+def cpu_baseline(cfg, H, W, steps=1, warmup=0, budget_s=420.0):
+    """The reference's CPU implementation of the SAME step at the SAME frame size, B=1 (the bounded sample: one clip
+    triple per step instead of the GPU arm's per-GPU batch; no size extrapolation), all host cores, fp32.  Steps are
+    capped by a wall-clock budget so the run ends within minutes; the line says how many were timed."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    hs, ws = H // 2, W // 2
-    sd, opt = cpu_port_setup(cfg)
+    kind, step = cpu_reference_setup(cfg)
+    mk = lambda: (torch.randn(1, 9, H, W), torch.randn(1, 9, H, W), torch.randn(1, 9, H, W))
+    t_start = time.time()
     for _ in range(warmup):
-        cpu_port_step(cfg, sd, opt, hs, ws, 1, "w")
-    t0 = time.time()
-    for _ in range(steps):
-        cpu_port_step(cfg, sd, opt, hs, ws, 1, "t")
-    dt = (time.time() - t0) / steps
-    scale = (hs * ws) / float(H * W)
-    return {"value": FRAMES_PER_SAMPLE / dt * scale, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "oracle port (torch %s CPU, fp32): %d full G+D iteration(s) at %dx%d B=1, %.1f s each; "
-                      "frames/s scaled x%.2f to %dx%d frames" % (torch.__version__, steps, hs, ws, dt, scale, H, W)}, dt
+        step(*mk())
+    times = []
+    for _ in range(max(1, steps)):
+        x = mk()
+        t0 = time.time()
+        step(*x)
+        times.append(time.time() - t0)
+        if time.time() - t_start > budget_s:
+            break
+    dt = sorted(times)[len(times) // 2]
+    what = ("the UNMODIFIED reference modules (oracle/_ref: FullModel_encdec + FullModel_D + Adam)" if kind == "reference"
+            else "oracle port (functional restatement + torch autograd + Adam)")
+    return {"value": FRAMES_PER_SAMPLE / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": "%s, torch %s CPU fp32, %d thread(s): %d warm-up + %d timed full G+D iteration(s) at %dx%d, B=1 "
+                      "(median %.1f s each); same frame size as the GPU arm, no scaling applied"
+                      % (what, torch.__version__, cores, warmup, len(times), H, W, dt),
+            "same_config": True, "steps_timed": len(times)}, dt
 
 
 def reference_arm(args, cfg, H, W):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_baseline(cfg, H, W, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    base, dt = cpu_baseline(cfg, H, W, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": "train frames/sec", "value": base["value"], "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "n_gpus": args.gpus, "steps": base["steps_timed"], "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "net": "VAE^2 HRNet-W18-small-v2 (encz + encdec + D_seq + D_frm)",
+            "config": {"workload": args.workload, "net": NET_NAMES.get(args.workload, args.workload),
                        "step": "G-step + D-step (fwd, bwd, Adam)", "per_gpu_batch": 1, "global_batch": 1,
                        "frames_per_sample": FRAMES_PER_SAMPLE, "parallelism": "host cores (1 process)",
-                       "sample": base["sample"]},
+                       "steps_requested": args.steps, "sample": base["sample"]},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+NET_NAMES = {"w18_256x512": "VAE^2 HRNet-W18-small-v2 (encz + encdec + D_seq + D_frm)",
+             "w18_1024x2048": "VAE^2 HRNet-W18-small-v2 (encz + encdec + D_seq + D_frm)",
+             "w48_473x473": "VAE^2 HRNet-W48 (encz + encdec + D_seq + D_frm)",
+             "w48_520x520": "VAE^2 HRNet-W48 (encz + encdec + D_seq + D_frm)",
+             "tiny_32x64": "VAE^2 tiny HRNet (test config)"}
 
 
 def main():
@@ -330,37 +437,36 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    hbm, tf_burst, tf_sust, src = peaks()
+    # every rank runs the profiled iteration (SyncBN / DDP collectives need all of them); rank 0 reports its own
+    roof, kernel_table, prof_ms = step_roofline(E, dev, lambda: train_step(g, d, opt_g, opt_d, *resident[0]),
+                                                hbm, tf_sust, src)
+    if args.precision == "fp32":
+        # exact-fp32 convs run on the CUDA cores: the FMA-pipe fraction is the bound such a kernel can actually reach
+        fma_peak = 148 * 128 * 2 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        roof["fma_pipe"] = {"achieved": roof["tensor"]["achieved"], "peak": fma_peak, "unit": "TFLOP/s",
+                            "frac": roof["tensor"]["achieved"] / fma_peak,
+                            "peak_source": "148 SMs x 128 FP32 lanes x 2 x max SM clock"}
     if rank == 0:
-        hbm, tf_burst, tf_sust, src = peaks()
-        tf, kms, desc = conv_microbench(dev, E)
         frames = FRAMES_PER_SAMPLE * B * world * args.steps
         value = frames / (ms * 1e-3)
         line = {
             "metric": "train frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "net": "VAE^2 HRNet-W18-small-v2 (encz + encdec + D_seq + D_frm)",
+            "config": {"workload": args.workload, "net": NET_NAMES.get(args.workload, args.workload),
                        "step": "G-step + D-step (fwd, bwd, Adam)", "per_gpu_batch": B, "global_batch": B * world,
                        "frames_per_sample": FRAMES_PER_SAMPLE, "parallelism": "dp%d" % world,
-                       "l2": "activations per step >> 126 MB L2 (inputs larger than L2); microbench flushes L2",
-                       "cuda_graphs": not args.no_graphs},
+                       "l2": "activations per step >> 126 MB L2 (inputs larger than L2)",
+                       "cuda_graphs": not args.no_graphs, "frame_size": [H, W]},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": 3 * B * 9 * H * W * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
             "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": tf / tf_burst,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
-                         # summarised in profiles/r1_ncu_full_conv_tc_64x64.txt (bf16 kernel; output stays in L2)
-                         "traffic": 16875520 if args.precision == "bf16" else None,
-                         "kernel": desc, "ms_per_launch": kms, "peak_source": src + " (burst, kernel timed alone)"},
+            "roofline": roof,
+            "kernel_shares": kernel_table,
         }
-        if args.precision == "fp32":
-            # the exact-fp32 path runs on the CUDA cores: the tensor roofline above is the contract's yardstick,
-            # the FMA-pipe one is the bound this kernel can actually reach
-            fma_peak = 148 * 128 * 2 * (clk.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
-            line["roofline"]["fma_pipe"] = {"achieved": tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": tf / fma_peak,
-                                            "peak_source": "148 SMs x 128 FP32 lanes x 2 x max SM clock"}
         if flop_per_sample:
             step_tf = flop_per_sample * B / (ms / args.steps * 1e-3) / 1e12
             line["step_conv_tflops"] = {"achieved": step_tf, "peak": tf_sust, "frac": step_tf / tf_sust,
@@ -369,7 +475,7 @@ def main():
         if bf16_path is not None:
             line["bf16_path"] = bf16_path
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline(cfg, H, W)
+            line["cpu_baseline"], _ = cpu_baseline(cfg, H, W, steps=1, warmup=0)
         print(json.dumps(line), flush=True)
     if world > 1:
         # leave without tearing NCCL down: destroying a process group whose collectives live inside captured

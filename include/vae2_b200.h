@@ -37,6 +37,8 @@ int vae2_abi_version(void);
 const char* vae2_status_string(int status);
 /* last CUDA error string seen by this library on the calling thread's device */
 const char* vae2_last_cuda_error(void);
+/* name of the kernel the last convolution launcher on the calling thread dispatched to (profiling introspection) */
+const char* vae2_last_kernel(void);
 
 /* ---- layout: the reference's NCHW fp32 tensors <-> internal channels-last ------------------ */
 /* xs[i].to(device) inputs, lib/core/function.py:487-489; torch.cat inputs, lib/utils/utils.py:77,105 */

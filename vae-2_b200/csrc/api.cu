@@ -5,6 +5,8 @@
 
 using namespace vae2;
 
+namespace vae2 { thread_local const char* g_last_kernel = ""; }
+
 static_assert(sizeof(vae2_pack_desc) == sizeof(PackDesc), "pack desc ABI");
 static_assert(sizeof(vae2_conv_geom) == sizeof(ConvGeom), "conv geom ABI");
 static_assert(sizeof(vae2_fuse_src) == sizeof(FuseSrc), "fuse src ABI");
@@ -31,6 +33,7 @@ const char* vae2_status_string(int status) {
 }
 
 const char* vae2_last_cuda_error(void) { return cudaGetErrorString(cudaPeekAtLastError()); }
+const char* vae2_last_kernel(void) { return g_last_kernel; }
 
 int vae2_nchw_to_act(const float* src, void* dst, int dtype, int B, int C, int Cp, int H, int W, int ld, int src_ctot,
                      int src_coff, vae2_stream_t stream) {

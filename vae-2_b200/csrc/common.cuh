@@ -118,6 +118,11 @@ inline int stream_grid(long long work_items, int per_block, int waves = 8) {
     return (int)(need < cap ? need : cap);
 }
 
+// Name of the kernel the last launcher on this thread picked (introspection for the in-step profiler:
+// vae2_last_kernel() in the C ABI).  Launch sites with several candidate kernels note their choice.
+extern thread_local const char* g_last_kernel;
+inline void note_kernel(const char* name) { g_last_kernel = name; }
+
 inline int check_launch() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? VAE2_OK : VAE2_ERR_CUDA;

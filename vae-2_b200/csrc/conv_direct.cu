@@ -197,6 +197,7 @@ static int launch_t(const Params& p, size_t smem, int grid, cudaStream_t st) {
             return VAE2_ERR_CUDA;
         attr = true;
     }
+    note_kernel("direct::conv_direct_kernel");
     conv_direct_kernel<TN><<<grid, p.groups * p.nsplit, smem, st>>>(p);
     return check_launch();
 }
@@ -406,6 +407,7 @@ static int launch_wg_t(const WgParams& p, size_t smem, int grid, int threads, cu
             return VAE2_ERR_CUDA;
         attr = true;
     }
+    note_kernel("direct::wgrad_direct_kernel");
     wgrad_direct_kernel<TN><<<grid, threads, smem, st>>>(p);
     return check_launch();
 }

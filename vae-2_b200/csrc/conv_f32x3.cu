@@ -398,6 +398,7 @@ static int launch_t32(const t32::Launch& L, cudaStream_t st) {
         attr_set = true;
     }
     int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    note_kernel("t32::conv_f32x3_kernel");
     conv_f32x3_kernel<<<grid, kThreads, smem, st>>>(map_w, p);
     return check_launch();
 }

@@ -368,13 +368,16 @@ static int launch_igemm(const void* A, const void* Bm, const float* bias, void* 
     if (MODE != MODE_WGRAD) {
         if (bn == 64) {
             dim3 grid((unsigned)((M + 127) / 128), (N + 63) / 64);
+            note_kernel("conv_igemm_kernel<128,64>");
             conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, kcls, div_wo, div_ho);
         } else if (((M + 255) / 256) * ((N + 31) / 32) < 2 * kNumSMs) {
             // small layer: half-height tiles (128 threads) so that the grid still covers the GPU about twice
             dim3 grid((unsigned)((M + 127) / 128), (N + 31) / 32);
+            note_kernel("conv_igemm_kernel<128,32>");
             conv_igemm_kernel<TA, 128, 32, MODE><<<grid, 128, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, kcls, div_wo, div_ho);
         } else {
             dim3 grid((unsigned)((M + 255) / 256), (N + 31) / 32);
+            note_kernel("conv_igemm_kernel<256,32>");
             conv_igemm_kernel<TA, 256, 32, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, bias, C, g, accumulate, kcls, div_wo, div_ho);
         }
     } else {
@@ -389,6 +392,7 @@ static int launch_igemm(const void* A, const void* Bm, const float* bias, void* 
         kps = ((kps + BK - 1) / BK) * BK;
         splits = (Ktot + kps - 1) / kps;
         dim3 grid((unsigned)((M + bm - 1) / bm), (N + bn - 1) / bn, (unsigned)splits);
+        note_kernel(bn == 64 ? "conv_igemm_kernel<128,64,wgrad>" : "conv_igemm_kernel<256,32,wgrad>");
         if (bn == 64)
             conv_igemm_kernel<TA, 128, 64, MODE><<<grid, NTHREADS, 0, st>>>((const TA*)A, Bm, nullptr, C, g, 0, (int)kps, div_wo, div_ho);
         else

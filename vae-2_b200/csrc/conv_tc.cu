@@ -786,6 +786,7 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
                 }
                 if (halo) {
                     const int grid = p.total_tiles < ctas * kNumSMs ? p.total_tiles : ctas * kNumSMs;
+                    note_kernel("tc::conv_tc_halo_kernel");
                     conv_tc_halo_kernel<<<grid, kThreads, smem, st>>>(map_a, map_w, p);
                     return check_launch();
                 }
@@ -851,6 +852,7 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
         attr_set = true;
     }
     int grid = p.total_tiles < ctas * kNumSMs ? p.total_tiles : ctas * kNumSMs;
+    note_kernel("tc::conv_tc_kernel");
     conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_w, p);
     return check_launch();
 }
@@ -948,6 +950,7 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
             return VAE2_ERR_CUDA;
         attr_set = true;
     }
+    note_kernel("tc::wgrad_tc_kernel");
     wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
     if (int e = check_launch()) return e;
     const long long n = (long long)p.M_total * g.Cout_p;

@@ -3,3 +3,4 @@ from .module import (EngineModule, set_precision, get_precision, use_cuda_graphs
                      activation_phase, ActArena)
 from .elbo import elbo_terms, check_finite, finite_check_mode  # noqa: F401
 from . import native  # noqa: F401
+from .profiler import KernelProfile  # noqa: F401

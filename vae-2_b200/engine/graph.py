@@ -628,8 +628,10 @@ class ConvOp:
 
     def _geom(self):
         x, y = self.x, self.y
-        return N.ConvGeom(B=x.B, H=x.H, W=x.W, Cin_p=x.Cp, ldx=x.ld, Ho=y.H, Wo=y.W, Cout_p=y.Cp, ldy=y.ld,
-                          k=self.k, stride=self.s, pad=self.k // 2)
+        g = N.ConvGeom(B=x.B, H=x.H, W=x.W, Cin_p=x.Cp, ldx=x.ld, Ho=y.H, Wo=y.W, Cout_p=y.Cp, ldy=y.ld,
+                       k=self.k, stride=self.s, pad=self.k // 2)
+        g.Cin, g.Cout = self.conv.in_channels, self.conv.out_channels   # logical widths (host-side only: profiler)
+        return g
 
     def emit_fwd(self, plan):
         pr = plan.prec

@@ -92,7 +92,7 @@ _PROTOS = {
 _PLAIN_INT = {"vae2_abi_version": [], "vae2_bn_max_partials": [], "vae2_elbo_acc_floats": [],
               "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)], "vae2_conv2d_tf32_supported": [C.POINTER(ConvGeom)]}
 
-EXPORTS = sorted(set(_PROTOS) | set(_PLAIN_INT) | {"vae2_status_string", "vae2_last_cuda_error",
+EXPORTS = sorted(set(_PROTOS) | set(_PLAIN_INT) | {"vae2_status_string", "vae2_last_cuda_error", "vae2_last_kernel",
                                                      "vae2_conv2d_wgrad_tc_workspace", "vae2_conv2d_tf32_dims"})
 
 _lib = None
@@ -123,6 +123,8 @@ def lib():
         h.vae2_status_string.restype = C.c_char_p
         h.vae2_last_cuda_error.argtypes = []
         h.vae2_last_cuda_error.restype = C.c_char_p
+        h.vae2_last_kernel.argtypes = []
+        h.vae2_last_kernel.restype = C.c_char_p
         _lib = h
     return _lib
 
