@@ -194,6 +194,24 @@ int vae2_elbo_terms(const vae2_elbo_seg* segs_dev, int nseg, float* acc, int nsl
                     vae2_stream_t stream);
 int vae2_elbo_terms_bwd(const vae2_elbo_bwd_seg* segs_dev, int nseg, vae2_stream_t stream);
 
+/* ---- callers either side of the path ------------------------------------ */
+/* dataset frame preparation on the device (lib/datasets/cityscapes.py:300-326): uint8 RGB frames [B][L][H][W][3] ->
+ * fp32 nchw [B][3L][H][W], (v/255 - mean)/std with the ImageNet constants the reference uses */
+int vae2_clip_u8_to_nchw(const uint8_t* frames, float* dst, int B, int L, int H, int W, vae2_stream_t stream);
+/* `_to_image(x, is_uint8=False)` of the inference driver (lib/core/function.py:87-98): (x*std+mean)*255 clipped to
+ * [0,255]; x nchw with RGB triplets along channels, n = total elements, HW = pixels per plane */
+int vae2_to_image(const float* x, float* im, int64_t n, int HW, vae2_stream_t stream);
+/* per (row r, frame f): out[(r*F+f)*2] = sum |pred - gt|, [..+1] = sum (pred - gt)^2 over the frame's 3*H*W values
+ * (function.py:262-263 recon loss and PSNR inputs); image planes [R][F][frame_elems], gt row = r % Bg */
+int vae2_frame_metrics(const float* pred_im, const float* gt_im, double* out, int R, int F, int Bg, int frame_elems,
+                       vae2_stream_t stream);
+/* one SSIM level as pytorch_msssim computes it (function.py:244-261; 11-tap Gaussian sigma 1.5, valid, K=(0.01,0.03)):
+ * planes X [N][H][W] vs Y [Ny][H][W] (plane n against n % Ny); out[n*2] = sum ssim_map, out[n*2+1] = sum cs_map */
+int vae2_ssim_level(const float* X, const float* Y, double* out, int N, int Ny, int H, int W, float data_range,
+                    vae2_stream_t stream);
+/* F.avg_pool2d(kernel 2, padding (H%2, W%2)) between MS-SSIM levels; planes [N][H][W] -> [N][Ho][Wo] */
+int vae2_avgpool2(const float* x, float* y, int N, int H, int W, vae2_stream_t stream);
+
 /* ---- optimizer: torch.optim.Adam as configured at tools/train.py:251-261 --------------------- */
 int vae2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, const int64_t* step_dev, float grad_scale, vae2_stream_t stream);

@@ -407,3 +407,68 @@ def test_cuda_graph_capture_applies_bn_side_effects_once():
             assert int(v) == 3 and int(stats[True][k]) == 3, (k, int(v), int(stats[True][k]))
         else:
             assert rel_err(stats[True][k], v) < 1e-6, k
+
+
+# ---- f2: stacked discriminator passes ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_stacked_discriminator_equals_sequential_calls(prec):
+    """forward_groups == the reference's sequential calls: outputs, per-call BN statistics (running stats after the
+    calls, num_batches_tracked), input gradient and parameter gradients (lib/utils/utils.py:114-119, 259-267)."""
+    E.set_precision(prec)
+    name = "tiny_b2_32x64"
+    res = {}
+    for mode in ("seq", "stacked"):
+        gold, cfg, g, d = _load(name)
+        B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+        net = g.D_model_frame.to(DEV).train()
+        real = x2t.to(DEV)
+        fake = (x2t + 0.3 * x3t).to(DEV).requires_grad_(True)
+        srcs = [(t, 3 * f) for f in range(3) for t in (real, fake)]
+        if mode == "seq":
+            outs = [net(t[:, o:o + 3]) for t, o in srcs]
+        else:
+            allo = net.forward_groups(srcs)
+            outs = [allo[i * B:(i + 1) * B] for i in range(len(srcs))]
+        gos = [O.det_normal("sd:go%d" % i, tuple(o.shape)).to(DEV) for i, o in enumerate(outs)]
+        net.zero_grad()
+        sum((o * go).sum() for o, go in zip(outs, gos)).backward()
+        res[mode] = dict(outs=[o.detach().clone() for o in outs], dx=fake.grad.clone(),
+                         grads={k: p.grad.clone() for k, p in net.named_parameters()},
+                         stats={k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k})
+    a, b = res["seq"], res["stacked"]
+    tol = 1e-5 if prec == "fp32" else 2e-2
+    eo = max(rel_err(x, y) for x, y in zip(b["outs"], a["outs"]))
+    edx = rel_err(b["dx"], a["dx"])
+    eg = np.array([rel_err(b["grads"][k], v) for k, v in a["grads"].items() if float(v.norm()) > 1e-8 and ".0.bias" not in k])
+    es = max(rel_err(b["stats"][k], v) for k, v in a["stats"].items() if "running" in k)
+    log_err("stacked_D_" + prec, outs=eo, dx=edx, grads_median=np.median(eg), grads_max=eg.max(), running=es)
+    assert all(int(b["stats"][k]) == int(v) == 6 for k, v in a["stats"].items() if "num_batches" in k)
+    assert eo < tol and es < 1e-5 and edx < 10 * tol, (eo, es, edx)
+    assert np.median(eg) < 10 * tol and eg.max() < (1e-3 if prec == "fp32" else 0.2), (np.median(eg), eg.max())
+
+
+def test_skip_dead_discriminator_grads_in_generator_step():
+    """skip_dead_D_grads: the generator step leaves the discriminators' .grad untouched (the reference's loop zeroes them
+    before they are used, function.py:499-512) and every other gradient is unchanged."""
+    name = "tiny_b2_32x64"
+    out = {}
+    for skip in (False, True):
+        gold, cfg, g, d = _load(name)
+        B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+        g = g.to(DEV).train()
+        g.skip_dead_D_grads = skip
+        losses, _, x2p, _ = _g_step(g, xt.to(DEV), x2t.to(DEV), x3t.to(DEV), eps_z, code)
+        g.zero_grad()
+        losses[0].backward()
+        out[skip] = ({k: (None if p.grad is None else p.grad.clone()) for k, p in g.named_parameters()},
+                     [float(l) for l in losses])
+        assert all(p.requires_grad for p in g.parameters())
+    assert out[True][1] == out[False][1]
+    n_d = 0
+    for k, gr in out[False][0].items():
+        if "D_model" in k:
+            n_d += 1
+            assert out[True][0][k] is None or float(out[True][0][k].abs().sum()) == 0.0, k
+        else:
+            assert torch.equal(out[True][0][k], gr) or rel_err(out[True][0][k], gr) < 1e-5, k
+    assert n_d > 100

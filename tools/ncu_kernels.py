@@ -3,9 +3,10 @@ the target of the `ncu --set full` capture whose summary lives in profiles/ (too
 
     python tools/ncu_kernels.py [bf16|fp32] [B]
 
-    ncu --set full --clock-control none --import-source on \
+    ncu --set full --clock-control none --profile-from-start off \
         -k regex:'conv_tc|wgrad_tc|wgrad_reduce|bn_fwd_fused|bn_bwd_fused|fuse_sum|fuse_bwd_up|elbo_terms|conv_direct|wgrad_direct|conv_igemm|f32x3' \
         -o gpurun_out/ncu_r2_<prec> python tools/ncu_kernels.py <prec>
+    (only the launch bracketed by cudaProfilerStart/Stop is profiled; NCU_ONLY=tag,tag restricts the set)
 """
 import ctypes as C
 import os
@@ -28,12 +29,20 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 p = lambda t: t.data_ptr() if t is not None else None
 
 
+ONLY = os.environ.get("NCU_ONLY", "")      # comma-separated substrings of the tags to run (keeps the report small)
+
+
 def twice(tag, fn):
+    """warm-up launch, L2 flush, then the PROFILED launch (ncu --profile-from-start off sees only this one)."""
+    if ONLY and not any(t in tag for t in ONLY.split(",")):
+        return
     fn()
     flush.zero_()                       # the profiled launch starts from a cold L2, like a launch deep inside the step
     torch.cuda.synchronize()
+    torch.cuda.profiler.start()
     fn()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     print("launched", tag, "->", N.lib().vae2_last_kernel().decode())
 
 
@@ -100,14 +109,9 @@ twice("fuse_bwd_up /2", lambda: N.call.vae2_fuse_bwd_up(p(gout), p(out), p(gsrc)
 Be, Z = 8, 8
 preds = [torch.randn(Be, 9, H, W, device=dev) for _ in range(6)]
 spec = [dict(kind=0, slot=i, a=2 * i, b=2 * i + 1, scale=1.0 / Be, name="l1") for i in range(3)]
-E.elbo_terms(spec, 3, preds)
-flush.zero_(); torch.cuda.synchronize()
-E.elbo_terms(spec, 3, preds)
+twice("elbo L1 x3 B=8", lambda: E.elbo_terms(spec, 3, preds))
 mv = [torch.randn(Be, 2 * Z, H >> i, W >> i, device=dev) * 0.1 for i in range(4)]
 eps = [torch.randn(Be, Z, H >> i, W >> i, device=dev) for i in range(4)]
 spec = [dict(kind=1, slot=0, a=4 + i, b=i, scale=1.0 / Be, want_z=True, name=i) for i in range(4)]
-E.elbo_terms(spec, 1, mv + eps)
-flush.zero_(); torch.cuda.synchronize()
-E.elbo_terms(spec, 1, mv + eps)
-torch.cuda.synchronize()
+twice("elbo reparam+KL x4 B=8", lambda: E.elbo_terms(spec, 1, mv + eps))
 print("done")

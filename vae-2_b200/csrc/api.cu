@@ -190,6 +190,20 @@ int vae2_elbo_terms_bwd(const vae2_elbo_bwd_seg* segs_dev, int nseg, vae2_stream
     return elbo_terms_bwd(reinterpret_cast<const ElboBwdSeg*>(segs_dev), nseg, S(stream));
 }
 
+int vae2_clip_u8_to_nchw(const uint8_t* frames, float* dst, int B, int L, int H, int W, vae2_stream_t stream) {
+    return clip_u8_to_nchw(frames, dst, B, L, H, W, S(stream));
+}
+int vae2_to_image(const float* x, float* im, int64_t n, int HW, vae2_stream_t stream) { return to_image(x, im, n, HW, S(stream)); }
+int vae2_frame_metrics(const float* pred_im, const float* gt_im, double* out, int R, int F, int Bg, int frame_elems,
+                       vae2_stream_t stream) {
+    return frame_metrics(pred_im, gt_im, out, R, F, Bg, frame_elems, S(stream));
+}
+int vae2_ssim_level(const float* X, const float* Y, double* out, int N, int Ny, int H, int W, float data_range,
+                    vae2_stream_t stream) {
+    return ssim_level(X, Y, out, N, Ny, H, W, data_range, S(stream));
+}
+int vae2_avgpool2(const float* x, float* y, int N, int H, int W, vae2_stream_t stream) { return avgpool2(x, y, N, H, W, S(stream)); }
+
 int vae2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, const int64_t* step_dev, float grad_scale, vae2_stream_t stream) {
     return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, reinterpret_cast<const long long*>(step_dev),

@@ -119,6 +119,13 @@ struct ElboBwdSeg {
 };
 int elbo_terms_bwd(const ElboBwdSeg* segs_dev, int nseg, cudaStream_t st);
 
+// metrics.cu (caller-side: device input pipeline, inference metrics)
+int clip_u8_to_nchw(const uint8_t* src, float* dst, int B, int L, int H, int W, cudaStream_t st);
+int to_image(const float* x, float* im, long long n, int HW, cudaStream_t st);
+int frame_metrics(const float* pred, const float* gt, double* out, int R, int F, int Bg, int frame_elems, cudaStream_t st);
+int ssim_level(const float* X, const float* Y, double* out, int N, int Ny, int H, int W, float data_range, cudaStream_t st);
+int avgpool2(const float* x, float* y, int N, int H, int W, cudaStream_t st);
+
 // adam.cu
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
               float weight_decay, const long long* step_dev, float grad_scale, cudaStream_t st);

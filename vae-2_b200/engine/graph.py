@@ -168,22 +168,27 @@ class activation_phase:
 class Act:
     """A channels-last activation [B][H][W][ld] (possibly a channel slice of a wider root)."""
 
-    def __init__(self, plan, C_, H, W, root=None, c_off=0, Cp=None, name=""):
-        self.plan, self.C, self.H, self.W, self.B = plan, C_, H, W, plan.B
+    def __init__(self, plan, C_, H, W, root=None, c_off=0, Cp=None, name="", B=None):
+        self.plan, self.C, self.H, self.W = plan, C_, H, W
+        self.B = (root.B if root is not None else plan.B) if B is None else B   # sub-batch acts: K-sample inference
         self.name = name
         pr = plan.prec
         if root is None:
             self.Cp = pad_to(C_, pr.tot_align) if Cp is None else Cp
-            self.buf = ActArena.alloc(plan.device, pr.tdtype, self.B * H * W * self.Cp, owner=plan)
-            if self.buf is None:
-                self.buf = torch.zeros(self.B * H * W * self.Cp, dtype=pr.tdtype, device=plan.device)
+            self.numel = self.B * H * W * self.Cp
+            if plan.lazy_acts:
+                self._buf = None          # inference plan: assigned by Plan._assign_buffers from buffer liveness
             else:
-                plan.arena_phase = ActArena.phase
+                self._buf = ActArena.alloc(plan.device, pr.tdtype, self.numel, owner=plan)
+                if self._buf is None:
+                    self._buf = torch.zeros(self.numel, dtype=pr.tdtype, device=plan.device)
+                else:
+                    plan.arena_phase = ActArena.phase
             self.ld, self.c_off, self.parent = self.Cp, 0, None
             plan.all_acts.append(self)
         else:
             self.Cp = Cp
-            self.buf, self.ld, self.c_off, self.parent = root.buf, root.ld, root.c_off + c_off, root
+            self._buf, self.ld, self.c_off, self.parent = None, root.ld, root.c_off + c_off, root
         self._grad = None
         self.needs_grad = plan.training
         self.cin_map = None      # logical channel -> physical lane, for concat roots
@@ -192,6 +197,13 @@ class Act:
     @property
     def npix(self):
         return self.B * self.H * self.W
+
+    @property
+    def buf(self):
+        a = self
+        while a.parent is not None:
+            a = a.parent
+        return a._buf
 
     @property
     def ptr(self):
@@ -210,14 +222,14 @@ class Act:
             if self.parent is None:
                 g = Act.__new__(Act)
                 g.__dict__.update(self.__dict__)
-                g.buf = self.plan.grad_alloc(self.buf.numel())
+                g._buf = self.plan.grad_alloc(self.buf.numel())
                 g._grad, g.parent = None, None
                 self._grad = g
             else:
                 pg = self.parent.grad()
                 g = Act.__new__(Act)
                 g.__dict__.update(self.__dict__)
-                g.buf, g.parent, g._grad = pg.buf, pg, None
+                g._buf, g.parent, g._grad = None, pg, None
                 self._grad = g
         return self._grad
 
@@ -230,15 +242,20 @@ class Act:
 
     def to_nchw(self):
         """Debug/test helper: logical NCHW fp32 copy of this activation."""
-        v = self.buf.view(self.B, self.H, self.W, self.ld)[..., self.c_off:self.c_off + self.C]
+        v = self.buf[:self.root.numel].view(self.B, self.H, self.W, self.ld)[..., self.c_off:self.c_off + self.C]
         return v.permute(0, 3, 1, 2).float().contiguous()
 
 
 class Plan:
     """Recorded launch list + buffers for one network call signature."""
 
-    def __init__(self, device, B, prec, training, bn_batch_stats=None, world_size=1, process_group=None):
+    def __init__(self, device, B, prec, training, bn_batch_stats=None, world_size=1, process_group=None, stat_groups=1):
         self.device, self.B, self.prec, self.training = device, B, PRECISIONS[prec], training
+        self.stat_groups = stat_groups        # BN statistics groups along the batch (stacked calls of the reference)
+        # Inference plans (no backward program) keep an activation only while a later op still reads it: buffers are
+        # assigned from a free list after recording (_assign_buffers).  K-sample inference at K=16 would otherwise hold
+        # every intermediate of 16 samples.  VAE2_LAZY_ACTS=0 restores one private buffer per activation.
+        self.lazy_acts = (not training) and os.environ.get("VAE2_LAZY_ACTS", "1") != "0"
         # training: record a backward program.  bn_batch_stats: BN normalises with batch statistics
         # (module.training), which also holds for a train-mode forward under torch.no_grad().
         self.bn_batch_stats = training if bn_batch_stats is None else bn_batch_stats
@@ -279,8 +296,8 @@ class Plan:
             self.params.append(p)
         return self._param_index[key]
 
-    def new_act(self, C_, H, W, name=""):
-        return Act(self, C_, H, W, name=name)
+    def new_act(self, C_, H, W, name="", B=None):
+        return Act(self, C_, H, W, name=name, B=B)
 
     def grad_alloc(self, numel):
         """Bump-allocate an activation-gradient buffer from the shared arena (128-element aligned)."""
@@ -292,12 +309,12 @@ class Plan:
         self._goff += n
         return t
 
-    def concat(self, Cs, H, W, name="cat"):
+    def concat(self, Cs, H, W, name="cat", B=None):
         """A buffer made of padded channel segments; returns (root, [slice acts])."""
         pr = self.prec
         seg_p = [pad_to(c, pr.seg_align) for c in Cs]
         total = pad_to(sum(seg_p), pr.tot_align)
-        root = Act(self, sum(Cs), H, W, Cp=total, name=name)
+        root = Act(self, sum(Cs), H, W, Cp=total, name=name, B=B)
         self.concat_roots.append(root)
         cmap, off, slices = [], 0, []
         for c, cp in zip(Cs, seg_p):
@@ -408,7 +425,10 @@ class Plan:
         self.n_convs = len(convs)
         # forward program
         self.fwd.append(lambda st: N.call.vae2_pack_weights(self.pk_dev.data_ptr(), self.n_convs, st))
-        for o in self.ops:
+        zero_at = self._assign_buffers() if self.lazy_acts else {}
+        for i, o in enumerate(self.ops):
+            for r in zero_at.get(i, ()):        # a recycled concat root: its never-written pad lanes must read as zero
+                self.fwd.append(lambda st, b=r._buf, n=r.numel: b[:n].zero_())
             o.emit_fwd(self)
         if self.arena_phase is not None:
             # shared memory: the lanes of a concat root that no producer writes must not keep another phase's data.
@@ -420,14 +440,64 @@ class Plan:
             if os.environ.get("VAE2_PRIVATE_GRADS", "0") != "1":
                 need = sum(pad_to(a.buf.numel(), 128) for a in self.all_acts)
                 self._garena, self._goff = GradArena.get(dev, self.prec.tdtype, need), 0
-            nbytes = self.dwp_flat.numel() * 4
             dptr = self.dwp_flat
-            self.bwd.append(lambda st: dptr.zero_())
+            any_wgrad = any(o.conv.weight.requires_grad for o in convs)
+            if any_wgrad:
+                self.bwd.append(lambda st: dptr.zero_())
             for o in reversed(self.ops):
                 o.emit_bwd(self)
-            self.bwd.append(lambda st: N.call.vae2_unpack_wgrad(self.up_dev.data_ptr(), self.n_convs, 0, st))
+            if any_wgrad:
+                self.bwd.append(lambda st: N.call.vae2_unpack_wgrad(self.up_dev.data_ptr(), self.n_convs, 0, st))
         self.n_launch_fwd, self.n_launch_bwd = len(self.fwd), len(self.bwd)
         return self
+
+    def _assign_buffers(self):
+        """Liveness-based buffer assignment for inference plans.  Ops run in list order; inputs are written before op 0
+        (eager prologue), outputs are read after the last op (eager epilogue).  A root buffer is taken from the free
+        list (smallest that fits) when its first writer runs and returned after its last reader.  Returns
+        {op index: [concat roots to zero before that op]}.  VAE2_KEEP_TAPS=1 keeps the tap activations private (debugging)."""
+        first, last = {}, {}
+        n = len(self.ops)
+
+        def touch(act, i, write):
+            r = act.root
+            if write:
+                first[id(r)] = min(first.get(id(r), i), i)
+            last[id(r)] = max(last.get(id(r), i), i)
+
+        for i, o in enumerate(self.ops):
+            for a in o.writes():
+                touch(a, -1 if isinstance(o, (InputOp, GroupInputOp, CodeOp)) else i, True)
+            for a in o.reads():
+                touch(a, n if isinstance(o, OutputOp) else i, False)
+        keep = {id(a.root) for a in self.taps.values()} if os.environ.get("VAE2_KEEP_TAPS", "0") == "1" else set()
+        roots = {id(a): a for a in self.all_acts}
+        free, zero_at = [], {}
+        by_first = {}
+        for rid, a in roots.items():
+            by_first.setdefault(first.get(rid, -1), []).append(a)
+        by_last = {}
+        for rid, a in roots.items():
+            by_last.setdefault(last.get(rid, first.get(rid, -1)), []).append(a)
+        tdt, dev = self.prec.tdtype, self.device
+        concat = {id(r) for r in self.concat_roots}
+        self.lazy_bytes = 0
+        for i in range(-1, n + 1):
+            for a in sorted(by_first.get(i, []), key=lambda t: -t.numel):
+                cand = [b for b in free if b.numel() >= a.numel]
+                if cand and id(a) not in keep and i >= 0:
+                    b = min(cand, key=lambda t: t.numel())
+                    free[:] = [t for t in free if t is not b]
+                    if id(a) in concat:
+                        zero_at.setdefault(i, []).append(a)
+                else:
+                    b = torch.zeros(a.numel, dtype=tdt, device=dev)
+                    self.lazy_bytes += a.numel * self.prec.esize
+                a._buf = b
+            for a in by_last.get(i, []):
+                if id(a) not in keep and first.get(id(a), -1) >= 0 and i < n:
+                    free.append(a._buf)
+        return zero_at
 
     def release(self):
         """Drop this plan: its arena extents go back to the phase's free list (the plan must not run again)."""
@@ -529,6 +599,12 @@ Act.root_cp = _root_cp
 class InputOp:
     """External NCHW fp32 tensor (channel window) -> channels-last activation(s).  Eager."""
 
+    def reads(self):
+        return []
+
+    def writes(self):
+        return list(self.dsts)
+
     def __init__(self, plan, slot, C_, H, W, src_ctot, src_coff, dsts, needs_grad):
         self.slot, self.C, self.H, self.W = slot, C_, H, W
         self.src_ctot, self.src_coff, self.dsts, self.needs_grad = src_ctot, src_coff, dsts, needs_grad
@@ -541,7 +617,7 @@ class InputOp:
         def run(st, self=self):
             src = plan.cur_inputs[self.slot]
             for d in self.dsts:
-                N.call.vae2_nchw_to_act(src.data_ptr(), d.ptr, pr.code, plan.B, self.C, d.Cp, self.H, self.W, d.ld,
+                N.call.vae2_nchw_to_act(src.data_ptr(), d.ptr, pr.code, d.B, self.C, d.Cp, self.H, self.W, d.ld,
                                         self.src_ctot, self.src_coff, st)
         plan.pre_fwd.append(run)
 
@@ -553,13 +629,63 @@ class InputOp:
         def run(st, self=self):
             dst = plan.cur_input_grads[self.slot]
             for i, d in enumerate(self.dsts):
-                N.call.vae2_act_to_nchw(d.grad().ptr, dst.data_ptr(), pr.code, plan.B, self.C, self.H, self.W, d.ld,
+                N.call.vae2_act_to_nchw(d.grad().ptr, dst.data_ptr(), pr.code, d.B, self.C, self.H, self.W, d.ld,
                                         self.src_ctot, self.src_coff, 1, st)   # dst starts zero-filled
+        plan.post_bwd.append(run)
+
+
+class GroupInputOp:
+    """Statistics group `gi` of a stacked plan: samples [gi*Bg, (gi+1)*Bg) of `dst` come from a channel window of
+    external NCHW tensor #slot (the reference calls the network once per group, e.g. per frame of the predicted clip,
+    lib/utils/utils.py:116-119, 262-267).  Eager."""
+
+    def reads(self):
+        return []
+
+    def writes(self):
+        return [self.dst]
+
+    def __init__(self, plan, slot, C_, H, W, src_ctot, src_coff, dst, gi, Bg, needs_grad):
+        self.slot, self.C, self.H, self.W = slot, C_, H, W
+        self.src_ctot, self.src_coff, self.dst, self.gi, self.Bg = src_ctot, src_coff, dst, gi, Bg
+        self.needs_grad = needs_grad and plan.training
+        dst.needs_grad = dst.needs_grad if gi else False
+        dst.needs_grad = dst.needs_grad or self.needs_grad
+
+    def _off(self, plan):
+        return self.gi * self.Bg * self.H * self.W * self.dst.ld * plan.prec.esize
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+        d, off = self.dst, self._off(plan)
+
+        def run(st, self=self):
+            src = plan.cur_inputs[self.slot]
+            N.call.vae2_nchw_to_act(src.data_ptr(), d.ptr + off, pr.code, self.Bg, self.C, d.Cp, self.H, self.W, d.ld,
+                                    self.src_ctot, self.src_coff, st)
+        plan.pre_fwd.append(run)
+
+    def emit_bwd(self, plan):
+        if not self.needs_grad:
+            return
+        pr = plan.prec
+        d, off = self.dst, self._off(plan)
+
+        def run(st, self=self):
+            dst = plan.cur_input_grads[self.slot]      # zero-filled by the autograd node; windows / groups accumulate
+            N.call.vae2_act_to_nchw(d.grad().ptr + off, dst.data_ptr(), pr.code, self.Bg, self.C, self.H, self.W, d.ld,
+                                    self.src_ctot, self.src_coff, 1, st)
         plan.post_bwd.append(run)
 
 
 class CodeOp:
     """Per-sample code [B,Z,1,1] broadcast over H x W into a slice (enc_hrnet.py:454-462). Eager."""
+
+    def reads(self):
+        return []
+
+    def writes(self):
+        return [self.dst]
 
     def __init__(self, plan, slot, Z, dst):
         self.slot, self.Z, self.dst = slot, Z, dst
@@ -571,7 +697,7 @@ class CodeOp:
         def run(st, self=self):
             code = plan.cur_inputs[self.slot]
             d = self.dst
-            N.call.vae2_code_broadcast(code.data_ptr(), d.ptr, pr.code, plan.B, self.Z, d.Cp, d.H, d.W, d.ld, st)
+            N.call.vae2_code_broadcast(code.data_ptr(), d.ptr, pr.code, d.B, self.Z, d.Cp, d.H, d.W, d.ld, st)
         plan.pre_fwd.append(run)
 
     def emit_bwd(self, plan):
@@ -580,6 +706,12 @@ class CodeOp:
 
 class OutputOp:
     """Channels-last activation -> channel window of an external NCHW fp32 tensor.  Eager."""
+
+    def reads(self):
+        return [self.act]
+
+    def writes(self):
+        return []
 
     def __init__(self, plan, slot, act, dst_ctot, dst_coff):
         self.slot, self.act, self.dst_ctot, self.dst_coff = slot, act, dst_ctot, dst_coff
@@ -590,7 +722,7 @@ class OutputOp:
         def run(st, self=self):
             a = self.act
             dst = plan.cur_outputs[self.slot]
-            N.call.vae2_act_to_nchw(a.ptr, dst.data_ptr(), pr.code, plan.B, a.C, a.H, a.W, a.ld, self.dst_ctot,
+            N.call.vae2_act_to_nchw(a.ptr, dst.data_ptr(), pr.code, a.B, a.C, a.H, a.W, a.ld, self.dst_ctot,
                                     self.dst_coff, 0, st)
         plan.post_fwd.append(run)
 
@@ -605,7 +737,7 @@ class OutputOp:
             if src is None:           # output unused by the loss: its gradient is zero
                 g.buf.zero_()
                 return
-            N.call.vae2_nchw_to_act(src.data_ptr(), g.ptr, pr.code, plan.B, a.C, a.Cp, a.H, a.W, a.ld, self.dst_ctot,
+            N.call.vae2_nchw_to_act(src.data_ptr(), g.ptr, pr.code, a.B, a.C, a.Cp, a.H, a.W, a.ld, self.dst_ctot,
                                     self.dst_coff, st)
         plan.pre_bwd.append(run)
 
@@ -613,11 +745,18 @@ class OutputOp:
 class ConvOp:
     """nn.Conv2d 3x3 (s1/s2, p1) or 1x1, optional bias."""
 
+    def reads(self):
+        return [self.x]
+
+    def writes(self):
+        return [self.y]
+
     def __init__(self, plan, x, conv, y=None):
         k, s = conv.kernel_size[0], conv.stride[0]
         self.conv, self.x, self.k, self.s, self.taps = conv, x, k, s, k * k
         Ho, Wo = conv_out(x.H, k, s), conv_out(x.W, k, s)
-        self.y = y if y is not None else plan.new_act(conv.out_channels, Ho, Wo, name="conv")
+        self.y = y if y is not None else plan.new_act(conv.out_channels, Ho, Wo, name="conv", B=x.B)
+        assert self.y.B == x.B
         assert (self.y.H, self.y.W) == (Ho, Wo)
         assert conv.in_channels == x.C, (conv.in_channels, x.C)
         plan.param(conv.weight)
@@ -663,12 +802,14 @@ class ConvOp:
         dy = y.grad()
         dyp, xp = dy.ptr, x.ptr
         dwp = plan.dwp_flat.data_ptr() + 4 * self.w_off
-        if getattr(self, "wgrad_tc", False):
+        if not self.conv.weight.requires_grad:
+            pass          # frozen parameter (e.g. a discriminator inside the generator step): no weight gradient
+        elif getattr(self, "wgrad_tc", False):
             wsp = plan.wgrad_ws.data_ptr()
             plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad_tc(xp, dyp, dwp, wsp, gp, st))
         else:
             plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad(xp, dyp, dwp, pr.code, gp, 0, st))
-        if self.conv.bias is not None:
+        if self.conv.bias is not None and self.conv.bias.requires_grad:
             db = plan.grad_ptr(self.conv.bias)
             npix, cb, ldy = y.npix, y.C, y.ld
             plan.bwd.append(lambda st: N.call.vae2_bias_grad(dyp, db, pr.code, npix, cb, ldy, 0, st))
@@ -682,19 +823,35 @@ class ConvOp:
             plan.bwd.append(lambda st: N.call.vae2_conv2d_dgrad(dyp, wpT, dxp, pr.code, gp, acc, eng, st))
 
 
+class _BnPart:
+    """One statistics group of a BN: a contiguous range of samples normalised with its own batch statistics."""
+    pass
+
+
 class BnOp:
     """BatchNorm2d (+residual)(+ReLU) on a raw conv output; training or eval statistics.
 
     Emission is split into sub-steps so that a BnGroupOp can run the members of a SyncBN group through
     ONE collective: stats(+rank-local merge) | all-gather | finalize+apply, and in backward
     reduce | all-reduce | coeffs+elemt.  Without a collective (single rank, batch statistics) each direction
-    is ONE cooperative launch (vae2_bn_fwd_fused / vae2_bn_bwd_fused)."""
+    is ONE cooperative launch (vae2_bn_fwd_fused / vae2_bn_bwd_fused).
+
+    Statistic groups (plan.stat_groups = G > 1): the batch holds G stacked calls of the reference (e.g. the three
+    per-frame discriminator passes, lib/utils/utils.py:116-119) -- samples [g*B/G, (g+1)*B/G) form group g, which is
+    normalised with its OWN batch statistics; running statistics take G momentum updates in group order and
+    num_batches_tracked advances by G, exactly as G sequential module calls do; d(gamma), d(beta) sum over groups."""
 
     _ws = {}
 
+    def reads(self):
+        return [self.y] + ([self.res] if self.res is not None else [])
+
+    def writes(self):
+        return [self.out]
+
     def __init__(self, plan, y, bn, relu, residual=None, out=None):
         self.y, self.bn, self.relu, self.res = y, bn, relu, residual
-        self.out = out if out is not None else plan.new_act(y.C, y.H, y.W, name="bn")
+        self.out = out if out is not None else plan.new_act(y.C, y.H, y.W, name="bn", B=y.B)
         assert self.out.Cp == y.Cp or out is not None
         plan.param(bn.weight)
         plan.param(bn.bias)
@@ -702,20 +859,34 @@ class BnOp:
 
     # ---- forward sub-steps ---------------------------------------------------------------------
     def _fwd_setup(self, plan):
-        y = self.y
+        y, out, res = self.y, self.out, self.res
         f32 = dict(dtype=torch.float32, device=plan.device)
-        self.mean, self.invstd = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
-        self.scale, self.shift = torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
         self.batch_stats = plan.bn_batch_stats or not self.bn.track_running_stats
+        G = plan.stat_groups if self.batch_stats else 1
+        assert y.B % G == 0
+        self.npix_g = y.npix // G
+        es = plan.prec.esize
+        stat = torch.zeros(G, 6, y.Cp, **f32)              # per group: mean, invstd, scale, shift, c1, c2
+        plan.keep.append(stat)
+        self.parts = []
+        for gi in range(G):
+            pt = _BnPart()
+            off = gi * self.npix_g
+            pt.yp, pt.outp = y.ptr + off * y.ld * es, out.ptr + off * out.ld * es
+            pt.resp = (res.ptr + off * res.ld * es) if res is not None else None
+            pt.off, pt.first = off, gi == 0
+            pt.mean, pt.invstd, pt.scale, pt.shift, pt.c1, pt.c2 = (stat[gi, j].data_ptr() for j in range(6))
+            self.parts.append(pt)
         mode = os.environ.get("VAE2_BN_SPLIT", "0")          # "1": split both directions, "fwd" / "bwd": one of them
         fuse_max = int(os.environ.get("VAE2_BN_FUSE_MAX_MB", "1000000")) << 20
-        nbytes = y.npix * y.Cp * (4 if plan.prec.code == 0 else 2)
+        nbytes = self.npix_g * y.Cp * (4 if plan.prec.code == 0 else 2)
         can = self.batch_stats and not self.sync and self.out.Cp >= y.Cp and nbytes <= fuse_max
         self.fused = can and mode not in ("1", "fwd")
         self.fused_bwd = can and mode not in ("1", "bwd")
         if self.batch_stats and not self.fused:
-            self.partials = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * y.Cp, **f32)
-            self.npart = C.c_int(0)
+            for pt in self.parts:
+                pt.partials = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * y.Cp, **f32)
+                pt.npart = C.c_int(0)
 
     @staticmethod
     def _scratch(plan):
@@ -728,88 +899,93 @@ class BnOp:
                                              device=plan.device)
         return ws
 
-    def _emit_fwd_fused(self, plan):
-        """stats | finalize | apply as ONE cooperative launch (single-rank training statistics)."""
-        pr, bn, y, out, res = plan.prec, self.bn, self.y, self.out, self.res
-        lanes = min(y.Cp, out.Cp)
-        ws = self._scratch(plan).data_ptr()
-        yp, op_, rp = y.ptr, out.ptr, (res.ptr if res is not None else None)
-        ldr = res.ld if res is not None else 0
-        npix, ldy, ldo, C_, Cp = y.npix, y.ld, out.ld, y.C, y.Cp
-        eps = float(bn.eps)
-        mom = 0.0 if bn.momentum is None else float(bn.momentum)
-        gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
+    def _bn_ptrs(self):
+        bn = self.bn
         rm = bn.running_mean.data_ptr() if bn.running_mean is not None else None
         rv = bn.running_var.data_ptr() if bn.running_var is not None else None
         nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
-        outs = (self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr())
+        mom = 0.0 if bn.momentum is None else float(bn.momentum)
+        return bn.weight.data_ptr(), bn.bias.data_ptr(), rm, rv, nbt, mom, float(bn.eps)
+
+    def _emit_fwd_fused(self, plan):
+        """stats | finalize | apply as ONE cooperative launch per statistics group (single-rank training statistics)."""
+        pr, y, out, res = plan.prec, self.y, self.out, self.res
+        ws = self._scratch(plan).data_ptr()
+        ldr = res.ld if res is not None else 0
+        npix, ldy, ldo, C_, Cp = self.npix_g, y.ld, out.ld, y.C, y.Cp
+        gp, bp, rm, rv, nbt, mom, eps = self._bn_ptrs()
         relu = 1 if self.relu else 0
-        plan.fwd.append(lambda st: N.call.vae2_bn_fwd_fused(yp, rp, op_, ws, pr.code, npix, C_, Cp, ldy, ldr, ldo, gp, bp,
-                                                            rm, rv, nbt, mom, eps, *outs, relu, st))
+        for pt in self.parts:
+            plan.fwd.append(lambda st, pt=pt: N.call.vae2_bn_fwd_fused(
+                pt.yp, pt.resp, pt.outp, ws, pr.code, npix, C_, Cp, ldy, ldr, ldo, gp, bp, rm, rv, nbt, mom, eps,
+                pt.mean, pt.invstd, pt.scale, pt.shift, relu, st))
 
     def _emit_bwd_fused(self, plan):
         pr = plan.prec
-        y, out, bn, res, g = self.y, self.out, self.bn, self.res, self.g
-        npix, lanes, C_ = y.npix, self.lanes, y.C
+        y, out, res, g = self.y, self.out, self.res, self.g
+        npix, lanes, C_ = self.npix_g, self.lanes, y.C
         ws = self._scratch(plan).data_ptr()
-        dgam, dbet = plan.grad_ptr(bn.weight), plan.grad_ptr(bn.bias)
-        c1p, c2p = self.c1.data_ptr(), self.c2.data_ptr()
+        want_p = self.param_grads
+        dgam = plan.grad_ptr(self.bn.weight) if want_p else None
+        dbet = plan.grad_ptr(self.bn.bias) if want_p else None
         dy = y.grad()
         acc_dy = y.take_acc_flag()
-        dres_p, ld_dres, acc_res = None, 0, 0
+        has_dres, ld_dres, acc_res = False, 0, 0
         if res is not None and res.needs_grad:
             acc_res = res.take_acc_flag()
-            dres_p, ld_dres = res.grad().ptr, res.ld
-        gp_, ap, yp, dyp = g.ptr, out.ptr, y.ptr, dy.ptr
-        mp, ip, scp, shp = self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr()
+            has_dres, ld_dres = True, res.ld
         # ReLU mask: without a residual it is recomputed from y (mode 2) and the stored activation is not read
         relu = 0 if not self.relu else (1 if res is not None else 2)
         gld, old, yld, dld = g.ld, out.ld, y.ld, dy.ld
-        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_fused(gp_, ap, yp, dyp, dres_p, ws, pr.code, npix, C_, lanes, gld,
-                                                            old, yld, dld, ld_dres, mp, ip, scp, shp, dgam, dbet, 0, c1p,
-                                                            c2p, relu, acc_dy, acc_res, st))
+        es = pr.esize
+        for pt in reversed(self.parts):
+            gp_, dyp = g.ptr + pt.off * gld * es, dy.ptr + pt.off * dld * es
+            dres_p = (res.grad().ptr + pt.off * ld_dres * es) if has_dres else None
+            accp = 0 if pt is self.parts[-1] else 1          # groups run last-to-first: the last group writes, the rest add
+            plan.bwd.append(lambda st, pt=pt, gp_=gp_, dyp=dyp, dres_p=dres_p, accp=accp: N.call.vae2_bn_bwd_fused(
+                gp_, pt.outp, pt.yp, dyp, dres_p, ws, pr.code, npix, C_, lanes, gld, old, yld, dld, ld_dres, pt.mean,
+                pt.invstd, pt.scale, pt.shift, dgam, dbet, accp, pt.c1, pt.c2, relu, acc_dy, acc_res, st))
 
-    def _emit_stats(self, plan, merged_ptr=None):
+    def _emit_stats(self, plan, merged_ptrs=None):
         """Per-CTA partials (and, for SyncBN, the rank-local merge into the group message)."""
         pr, y = plan.prec, self.y
-        pp, yp, npart, Cp, npix, ld = self.partials.data_ptr(), y.ptr, self.npart, y.Cp, y.npix, y.ld
-        plan.fwd.append(lambda st: N.call.vae2_bn_stats(yp, pp, C.byref(npart), pr.code, npix, Cp, ld, st))
-        if merged_ptr is not None:
-            plan.fwd.append(lambda st: N.call.vae2_bn_merge(pp, npart.value, Cp, merged_ptr, st))
+        Cp, npix, ld = y.Cp, self.npix_g, y.ld
+        for i, pt in enumerate(self.parts):
+            pp = pt.partials.data_ptr()
+            plan.fwd.append(lambda st, pt=pt, pp=pp: N.call.vae2_bn_stats(pt.yp, pp, C.byref(pt.npart), pr.code, npix, Cp, ld, st))
+            if merged_ptrs is not None:
+                mp = merged_ptrs[i]
+                plan.fwd.append(lambda st, pt=pt, pp=pp, mp=mp: N.call.vae2_bn_merge(pp, pt.npart.value, Cp, mp, st))
 
-    def _emit_finalize(self, plan, parts_ptr=None, n_parts=None, stride=0):
-        bn, y = self.bn, self.y
+    def _emit_finalize(self, plan, parts_ptrs=None, n_parts=None, stride=0):
+        y = self.y
         Cp, C_ = y.Cp, y.C
-        eps = float(bn.eps)
-        mom = 0.0 if bn.momentum is None else float(bn.momentum)
-        gp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
+        gp, bp, rm, rv, nbt, mom, eps = self._bn_ptrs()
         if self.batch_stats:
-            rm = bn.running_mean.data_ptr() if bn.running_mean is not None else None
-            rv = bn.running_var.data_ptr() if bn.running_var is not None else None
-            nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
-            outs = (self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr())
-            if parts_ptr is None:
-                pp, npart = self.partials.data_ptr(), self.npart
-                plan.fwd.append(lambda st: N.call.vae2_bn_finalize(pp, npart.value, C_, Cp, gp, bp, rm, rv, nbt, mom,
-                                                                   eps, *outs, st))
-            else:
-                plan.fwd.append(lambda st: N.call.vae2_bn_finalize_strided(parts_ptr, n_parts, stride, C_, Cp, gp, bp,
-                                                                           rm, rv, nbt, mom, eps, *outs, st))
+            for i, pt in enumerate(self.parts):      # group order = the reference's call order (running-stat updates)
+                outs = (pt.mean, pt.invstd, pt.scale, pt.shift)
+                if parts_ptrs is None:
+                    pp = pt.partials.data_ptr()
+                    plan.fwd.append(lambda st, pt=pt, pp=pp, outs=outs: N.call.vae2_bn_finalize(
+                        pp, pt.npart.value, C_, Cp, gp, bp, rm, rv, nbt, mom, eps, *outs, st))
+                else:
+                    src = parts_ptrs[i]
+                    plan.fwd.append(lambda st, src=src, outs=outs: N.call.vae2_bn_finalize_strided(
+                        src, n_parts, stride, C_, Cp, gp, bp, rm, rv, nbt, mom, eps, *outs, st))
         else:
-            rm, rv = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
-            sp, hp = self.scale.data_ptr(), self.shift.data_ptr()
-            plan.fwd.append(lambda st: N.call.vae2_bn_eval_coeffs(C_, Cp, gp, bp, rm, rv, eps, sp, hp, st))
+            pt = self.parts[0]
+            plan.fwd.append(lambda st: N.call.vae2_bn_eval_coeffs(C_, Cp, gp, bp, rm, rv, eps, pt.scale, pt.shift, st))
 
     def _emit_apply(self, plan):
         pr = plan.prec
         y, out, res = self.y, self.out, self.res
         lanes = min(y.Cp, out.Cp)
-        yp, op_, rp = y.ptr, out.ptr, (res.ptr if res is not None else None)
         ldr = res.ld if res is not None else 0
-        sp, hp, relu = self.scale.data_ptr(), self.shift.data_ptr(), 1 if self.relu else 0
-        npix, ldy, ldo = y.npix, y.ld, out.ld
-        plan.fwd.append(lambda st: N.call.vae2_bn_apply(yp, rp, op_, pr.code, npix, lanes, ldy, ldr, ldo, sp, hp,
-                                                        relu, st))
+        relu = 1 if self.relu else 0
+        npix, ldy, ldo = (self.npix_g if self.batch_stats else y.npix), y.ld, out.ld
+        for pt in self.parts:
+            plan.fwd.append(lambda st, pt=pt: N.call.vae2_bn_apply(pt.yp, pt.resp, pt.outp, pr.code, npix, lanes, ldy, ldr,
+                                                                  ldo, pt.scale, pt.shift, relu, st))
 
     def emit_fwd(self, plan):
         """Stand-alone BN (its own collective under SyncBN)."""
@@ -819,47 +995,59 @@ class BnOp:
     def _bwd_setup(self, plan):
         y = self.y
         f32 = dict(dtype=torch.float32, device=plan.device)
-        if not self.fused_bwd:
-            self.bparts = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * y.Cp, **f32)
-        self.sums, self.c1, self.c2 = torch.zeros(2 * y.Cp, **f32), torch.zeros(y.Cp, **f32), torch.zeros(y.Cp, **f32)
-        self.bnpart = C.c_int(0)
+        # d(gamma), d(beta) are skipped when neither is trainable (e.g. the discriminators inside the generator step)
+        self.param_grads = self.bn.weight.requires_grad or self.bn.bias.requires_grad
+        for pt in self.parts:
+            if not self.fused_bwd:
+                pt.bparts = torch.zeros(N.lib().vae2_bn_max_partials() * 2 * y.Cp, **f32)
+            pt.sums = torch.zeros(2 * y.Cp, **f32)
+            pt.bnpart = C.c_int(0)
         self.lanes = min(y.Cp, self.out.Cp)
         self.g = self.out.grad()
 
     def _emit_bwd_reduce(self, plan):
         pr = plan.prec
         y, out, g = self.y, self.out, self.g
-        gp_, ap, yp, pp, sp = g.ptr, out.ptr, y.ptr, self.bparts.data_ptr(), self.sums.data_ptr()
-        npart, npix, lanes, C_ = self.bnpart, y.npix, self.lanes, y.C
-        mp, ip, relu = self.mean.data_ptr(), self.invstd.data_ptr(), 1 if self.relu else 0
+        npix, lanes, C_ = self.npix_g, self.lanes, y.C
+        relu = 1 if self.relu else 0
         gld, old, yld = g.ld, out.ld, y.ld
-        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_reduce(gp_, ap, yp, pp, C.byref(npart), pr.code, npix, lanes,
-                                                             gld, old, yld, mp, ip, relu, st))
-        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_finalize(pp, npart.value, C_, lanes, sp, st))
+        es = pr.esize
+        for pt in self.parts:
+            gp_ = g.ptr + pt.off * gld * es
+            pp, sp = pt.bparts.data_ptr(), pt.sums.data_ptr()
+            plan.bwd.append(lambda st, pt=pt, gp_=gp_, pp=pp: N.call.vae2_bn_bwd_reduce(
+                gp_, pt.outp, pt.yp, pp, C.byref(pt.bnpart), pr.code, npix, lanes, gld, old, yld, pt.mean, pt.invstd, relu, st))
+            plan.bwd.append(lambda st, pt=pt, pp=pp, sp=sp: N.call.vae2_bn_bwd_finalize(pp, pt.bnpart.value, C_, lanes, sp, st))
 
-    def _emit_bwd_apply(self, plan, gsum_ptr=None):
+    def _emit_bwd_apply(self, plan, gsum_ptrs=None):
         """coefficients (from the global sums) + elementwise pass; parameter grads from the LOCAL sums."""
         pr = plan.prec
-        y, out, bn, res, g = self.y, self.out, self.bn, self.res, self.g
-        npix, lanes, C_ = y.npix, self.lanes, y.C
-        sp = self.sums.data_ptr()
-        dgam, dbet = plan.grad_ptr(bn.weight), plan.grad_ptr(bn.bias)
-        c1p, c2p = self.c1.data_ptr(), self.c2.data_ptr()
-        count = npix * (plan.world_size if gsum_ptr is not None else 1)
-        gs = gsum_ptr if gsum_ptr is not None else sp
-        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_coeffs(gs, C_, lanes, 1.0 / count, dgam, dbet, 0, sp, c1p, c2p, st))
+        y, out, res, g = self.y, self.out, self.res, self.g
+        npix, lanes, C_ = self.npix_g, self.lanes, y.C
+        want_p = self.param_grads
+        dgam = plan.grad_ptr(self.bn.weight) if want_p else None
+        dbet = plan.grad_ptr(self.bn.bias) if want_p else None
+        count = npix * (plan.world_size if gsum_ptrs is not None else 1)
         dy = y.grad()
         acc_dy = y.take_acc_flag()
-        dres_p, ld_dres, acc_res = None, 0, 0
+        has_dres, ld_dres, acc_res = False, 0, 0
         if res is not None and res.needs_grad:
             acc_res = res.take_acc_flag()
-            dres_p, ld_dres = res.grad().ptr, res.ld
-        gp_, ap, yp, dyp = g.ptr, out.ptr, y.ptr, dy.ptr
-        mp, ip, scp, relu = self.mean.data_ptr(), self.invstd.data_ptr(), self.scale.data_ptr(), 1 if self.relu else 0
+            has_dres, ld_dres = True, res.ld
+        relu = 1 if self.relu else 0
         gld, old, yld, dld = g.ld, out.ld, y.ld, dy.ld
-        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_elemt(gp_, ap, yp, dyp, dres_p, pr.code, npix, lanes, gld, old,
-                                                            yld, dld, ld_dres, mp, ip, scp, c1p, c2p, relu, acc_dy,
-                                                            acc_res, st))
+        es = pr.esize
+        for i, pt in enumerate(self.parts):
+            sp = pt.sums.data_ptr()
+            gs = gsum_ptrs[i] if gsum_ptrs is not None else sp
+            accp = 0 if i == 0 else 1
+            plan.bwd.append(lambda st, pt=pt, gs=gs, sp=sp, accp=accp: N.call.vae2_bn_bwd_coeffs(
+                gs, C_, lanes, 1.0 / count, dgam, dbet, accp, sp, pt.c1, pt.c2, st))
+            gp_, dyp = g.ptr + pt.off * gld * es, dy.ptr + pt.off * dld * es
+            dres_p = (res.grad().ptr + pt.off * ld_dres * es) if has_dres else None
+            plan.bwd.append(lambda st, pt=pt, gp_=gp_, dyp=dyp, dres_p=dres_p: N.call.vae2_bn_bwd_elemt(
+                gp_, pt.outp, pt.yp, dyp, dres_p, pr.code, npix, lanes, gld, old, yld, dld, ld_dres, pt.mean, pt.invstd,
+                pt.scale, pt.c1, pt.c2, relu, acc_dy, acc_res, st))
 
     def emit_bwd(self, plan):
         BnGroupOp(plan, [self]).emit_bwd(plan)
@@ -869,7 +1057,13 @@ class BnGroupOp:
     """BNs at the same depth of independent branches.  Single rank: the members simply run one after the
     other.  SyncBN: their (count, mean, M2) messages are concatenated and travel in ONE all-gather, their
     backward sums in ONE all-reduce -- the reference's per-BN collectives (1177 + 1160 per iteration,
-    SURVEY.md §2.2) shrink by the branch count."""
+    SURVEY.md §2.2) shrink by the branch count (and by the statistics-group count of a stacked plan)."""
+
+    def reads(self):
+        return [a for m in self.members for a in m.reads()]
+
+    def writes(self):
+        return [a for m in self.members for a in m.writes()]
 
     def __init__(self, plan, members):
         self.members = members
@@ -892,17 +1086,20 @@ class BnGroupOp:
         f32 = dict(dtype=torch.float32, device=plan.device)
         offs, total = [], 0
         for m in ms:
-            offs.append(total)
-            total += 3 * m.y.Cp
+            o = []
+            for _ in m.parts:
+                o.append(total)
+                total += 3 * m.y.Cp
+            offs.append(o)
         msg, gathered = torch.zeros(total, **f32), torch.zeros(plan.world_size * total, **f32)
         plan.keep += [msg, gathered]
-        for m, off in zip(ms, offs):
-            m._emit_stats(plan, merged_ptr=msg.data_ptr() + 4 * off)
+        for m, o in zip(ms, offs):
+            m._emit_stats(plan, merged_ptrs=[msg.data_ptr() + 4 * x for x in o])
         grp = plan.group
         plan.fwd.append(lambda st: dist.all_gather_into_tensor(gathered, msg, group=grp))
         plan.n_collectives_fwd += 1
-        for m, off in zip(ms, offs):
-            m._emit_finalize(plan, parts_ptr=gathered.data_ptr() + 4 * off, n_parts=plan.world_size, stride=total)
+        for m, o in zip(ms, offs):
+            m._emit_finalize(plan, parts_ptrs=[gathered.data_ptr() + 4 * x for x in o], n_parts=plan.world_size, stride=total)
             m._emit_apply(plan)
 
     def emit_bwd(self, plan):
@@ -920,29 +1117,39 @@ class BnGroupOp:
         f32 = dict(dtype=torch.float32, device=plan.device)
         offs, total = [], 0
         for m in ms:
-            offs.append(total)
-            total += 2 * m.y.Cp
+            o = []
+            for _ in m.parts:
+                o.append(total)
+                total += 2 * m.y.Cp
+            offs.append(o)
         gsum = torch.zeros(total, **f32)
         plan.keep.append(gsum)
-        for m, off in zip(ms, offs):
+        for m, o in zip(ms, offs):
             m._emit_bwd_reduce(plan)
-            dst, src, n = gsum[off:off + 2 * m.lanes], m.sums, 2 * m.lanes
-            plan.bwd.append(lambda st, dst=dst, src=src, n=n: dst.copy_(src[:n]))
+            for pt, off in zip(m.parts, o):
+                dst, src, n = gsum[off:off + 2 * m.lanes], pt.sums, 2 * m.lanes
+                plan.bwd.append(lambda st, dst=dst, src=src, n=n: dst.copy_(src[:n]))
         grp = plan.group
         plan.bwd.append(lambda st: dist.all_reduce(gsum, group=grp))
         plan.n_collectives_bwd += 1
-        for m, off in zip(ms, offs):
-            m._emit_bwd_apply(plan, gsum_ptr=gsum.data_ptr() + 4 * off)
+        for m, o in zip(ms, offs):
+            m._emit_bwd_apply(plan, gsum_ptrs=[gsum.data_ptr() + 4 * x for x in o])
 
 
 class FuseOp:
     """out = [relu](sum_j resize(src_j)); sources at the output size are added as they are,
     others are bilinearly resized (align_corners=False).  enc_hrnet.py:233-248 / :833-839."""
 
+    def reads(self):
+        return list(self.srcs)
+
+    def writes(self):
+        return [self.out]
+
     def __init__(self, plan, srcs, H, W, relu, out=None):
         self.srcs, self.relu = srcs, relu
         C_ = srcs[0].C
-        self.out = out if out is not None else plan.new_act(C_, H, W, name="fuse")
+        self.out = out if out is not None else plan.new_act(C_, H, W, name="fuse", B=srcs[0].B)
         self.lanes = min([s.Cp for s in srcs] + [self.out.Cp])
 
     def emit_fwd(self, plan):
@@ -982,6 +1189,12 @@ class FuseOp:
 class CopyOp:
     """dst slice (=) src   (channel concat done as a slice write)."""
 
+    def reads(self):
+        return [self.src]
+
+    def writes(self):
+        return [self.dst]
+
     def __init__(self, plan, src, dst):
         self.src, self.dst = src, dst
 
@@ -1002,6 +1215,35 @@ class CopyOp:
         plan.bwd.append(lambda st: N.call.vae2_slice_copy(gd, gs, pr.code, s.npix, lanes, d.ld, s.ld, acc, st))
 
 
+class TileOp:
+    """dst[k*Bs + b] = src[b] for k < K: a feature computed once per context clip feeds all K latent draws stacked along
+    the batch axis (K-sample inference, SURVEY.md §8 f1: the encoder trunk does not depend on z).  Forward only."""
+
+    def reads(self):
+        return [self.src]
+
+    def writes(self):
+        return [self.dst]
+
+    def __init__(self, plan, src, dst, K):
+        assert dst.B == K * src.B and (src.H, src.W) == (dst.H, dst.W)
+        self.src, self.dst, self.K = src, dst, K
+        dst.needs_grad = False
+
+    def emit_fwd(self, plan):
+        pr = plan.prec
+        s, d = self.src, self.dst
+        lanes = min(s.Cp, d.Cp)
+        step = s.npix * d.ld * pr.esize
+        for k in range(self.K):
+            dp = d.ptr + k * step
+            plan.fwd.append(lambda st, dp=dp: N.call.vae2_slice_copy(s.ptr, dp, pr.code, s.npix, lanes, s.ld, d.ld, 0, st))
+
+    def emit_bwd(self, plan):
+        if plan.training:
+            raise RuntimeError("vae2_b200: TileOp (K-sample inference) has no backward")
+
+
 # =============================================================================================
 # recording front-end used by the nn.Module mirrors
 # =============================================================================================
@@ -1012,15 +1254,18 @@ class Recorder:
         self.n_out = 0
 
     # inputs / outputs ---------------------------------------------------------------------
-    def input(self, C_, H, W, needs_grad, src_ctot=None, src_coff=0, slot=None, into=None):
+    def input(self, C_, H, W, needs_grad, src_ctot=None, src_coff=0, slot=None, into=None, B=None):
         """Declare (a channel window of) external input #slot; `into` lists slice acts to fill."""
         p = self.plan
         if slot is None:
             slot = self.n_in
             self.n_in += 1
-        dsts = into if into is not None else [p.new_act(C_, H, W, name="in%d" % slot)]
+        dsts = into if into is not None else [p.new_act(C_, H, W, name="in%d" % slot, B=B)]
         p.add(InputOp(p, slot, C_, H, W, src_ctot if src_ctot is not None else C_, src_coff, dsts, needs_grad))
         return dsts[0] if into is None else dsts
+
+    def group_input(self, slot, C_, H, W, src_ctot, src_coff, dst, gi, Bg, needs_grad):
+        self.plan.add(GroupInputOp(self.plan, slot, C_, H, W, src_ctot, src_coff, dst, gi, Bg, needs_grad))
 
     def new_input_slot(self):
         s = self.n_in
@@ -1071,5 +1316,9 @@ class Recorder:
         self.plan.add(CopyOp(self.plan, src, dst))
         return dst
 
-    def concat(self, Cs, H, W, name="cat"):
-        return self.plan.concat(Cs, H, W, name)
+    def concat(self, Cs, H, W, name="cat", B=None):
+        return self.plan.concat(Cs, H, W, name, B=B)
+
+    def tile(self, src, dst, K):
+        self.plan.add(TileOp(self.plan, src, dst, K))
+        return dst

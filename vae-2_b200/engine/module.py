@@ -127,7 +127,9 @@ class EngineModule(nn.Module):
                 return dist.get_world_size()
         return 1
 
-    def _run(self, inputs, tag=""):
+    def _run(self, inputs, tag="", batch=None, stat_groups=1):
+        """``batch`` / ``stat_groups``: a stacked plan holds ``stat_groups`` calls of the reference along the batch
+        axis (``batch`` samples in total), each normalised with its own BatchNorm statistics (graph.BnOp)."""
         dev = inputs[0].device
         if dev.type != "cuda":
             raise RuntimeError("vae2_b200: this path runs on CUDA devices only (got %s); there is no CPU fallback"
@@ -137,7 +139,9 @@ class EngineModule(nn.Module):
         needs = tuple(bool(t.requires_grad) and grad_on for t in inputs)
         shapes = tuple(tuple(t.shape) for t in inputs)
         world = self._sync_world() if training else 1
-        key = (tag, shapes, needs, training, grad_on, _STATE["precision"], dev.index, world)
+        frozen = tuple(not p.requires_grad for p in self.parameters()) if (training and grad_on) else ()
+        frozen = hash(frozen) if any(frozen) else 0
+        key = (tag, shapes, needs, training, grad_on, _STATE["precision"], dev.index, world, frozen, stat_groups)
         pool = self._plans().setdefault(key, [])
         plan = next((p for p in pool if not p.busy), None)
         if plan is not None and plan.param_ptrs != tuple(p.data_ptr() for p in plan.params):
@@ -148,8 +152,8 @@ class EngineModule(nn.Module):
             plan = None
         if plan is None:
             with torch.cuda.device(dev):
-                plan = Plan(dev, shapes[0][0], _STATE["precision"], training and grad_on, bn_batch_stats=training,
-                            world_size=world)
+                plan = Plan(dev, batch or shapes[0][0], _STATE["precision"], training and grad_on, bn_batch_stats=training,
+                            world_size=world, stat_groups=stat_groups)
                 rec = Recorder(plan)
                 plan.out_shapes = self._record(rec, shapes, needs, tag)
                 plan.finalize()

@@ -88,6 +88,11 @@ _PROTOS = {
     "vae2_elbo_terms": [vp, i32, vp, i32, vp, vp],
     "vae2_elbo_terms_bwd": [vp, i32, vp],
     "vae2_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, f32, vp],
+    "vae2_clip_u8_to_nchw": [vp, vp, i32, i32, i32, i32, vp],
+    "vae2_to_image": [vp, vp, i64, i32, vp],
+    "vae2_frame_metrics": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "vae2_ssim_level": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
+    "vae2_avgpool2": [vp, vp, i32, i32, i32, vp],
 }
 _PLAIN_INT = {"vae2_abi_version": [], "vae2_bn_max_partials": [], "vae2_elbo_acc_floats": [],
               "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)], "vae2_conv2d_tf32_supported": [C.POINTER(ConvGeom)]}

@@ -346,10 +346,13 @@ class HighResolutionNet(EngineModule):
         return pre
 
     # ---- recording -----------------------------------------------------------------------
-    def _emit_trunk(self, rec, p, x, code_maps=None, head_cat=True):
+    def _emit_trunk(self, rec, p, x, code_maps=None, head_cat=True, tile=1):
         """stem -> layer1 -> stage2..4.  ``code_maps(b, H, W, C)`` (optional) returns the concat
         root and feature slice for branch b in front of transition3_e.  Returns the stage-4
-        outputs; with head_cat they are laid out inside the head's concat buffer."""
+        outputs; with head_cat they are laid out inside the head's concat buffer.
+        ``tile`` = K > 1 (K-sample inference): x holds B context clips, everything up to transition3 runs once per
+        clip and its result is replicated K times into the concat buffers, which (like all that follows) hold K*B
+        samples -- the K latent draws of every clip."""
         g = lambda n: getattr(self, p + n)
         x = rec.conv_bn(x, g("conv1"), g("bn1"), relu=True)
         x = rec.conv_bn(x, g("conv2"), g("bn2"), relu=True)
@@ -369,11 +372,16 @@ class HighResolutionNet(EngineModule):
             t3 = g("transition3")
             sizes = self._branch_sizes(ys, len(t3))
             cats = [code_maps(b, h, w, c) for b, (c, h, w) in enumerate(sizes)]
-            _emit_transition(rec, t3, ys, len(ys), outs=[feat for _, feat in cats])
+            if tile > 1:
+                feats = _emit_transition(rec, t3, ys, len(ys))
+                for f, (_, dst) in zip(feats, cats):
+                    rec.tile(f, dst, tile)
+            else:
+                _emit_transition(rec, t3, ys, len(ys), outs=[feat for _, feat in cats])
             xs = _emit_transition(rec, g("transition3_e"), [root for root, _ in cats], len(cats))
         outs = None
         if head_cat:
-            cat, slices = rec.concat([a.C for a in xs], xs[0].H, xs[0].W, name=p + "headcat")
+            cat, slices = rec.concat([a.C for a in xs], xs[0].H, xs[0].W, name=p + "headcat", B=xs[0].B)
             outs = [slices[0]] + [None] * (len(xs) - 1)
         ys = self._emit_stage(rec, g("stage4"), xs, outs)
         for i, t in enumerate(ys):
@@ -462,7 +470,9 @@ class HighResolutionNetED(HighResolutionNet):
     def _record(self, rec, shapes, needs, tag):
         B, Cx, H, W = shapes[0]
         Z, coded = self.z_dim, self.enable_random_code
-        x = rec.input(Cx, H, W, needs[0])
+        K = tag[1] if isinstance(tag, tuple) and tag[0] == "ksample" else 1
+        KB = K * B                                  # plan.B; the context clips (and the encoder trunk) have B samples
+        x = rec.input(Cx, H, W, needs[0], B=B)
         z_slots = [rec.new_input_slot() for _ in range(4)] if coded else []
         code_slot = rec.new_input_slot() if (coded and not self.is_baseline) else None
         z_needs = needs[1:5] if coded else []
@@ -472,7 +482,7 @@ class HighResolutionNetED(HighResolutionNet):
 
             def code_maps(b, h, w, c):
                 segs = ([Z] if (first and not self.is_baseline) else []) + [Z, c]
-                root, sl = rec.concat(segs, h, w, name="zcat%d" % b)
+                root, sl = rec.concat(segs, h, w, name="zcat%d" % b, B=KB)
                 if len(segs) == 3:
                     rec.code(code_slot, Z, sl[0])
                 pending[b] = sl[-2]
@@ -484,10 +494,10 @@ class HighResolutionNetED(HighResolutionNet):
         cur = x
         for p, first in (("", True), ("decf_", False), ("decp_", False)):
             cm, pending = maps_for(first) if coded else (None, {})
-            _, cat = self._emit_trunk(rec, p, cur if first else preds[0][0], cm)
+            _, cat = self._emit_trunk(rec, p, cur if first else preds[0][0], cm, tile=K if first else 1)
             for b, sl in pending.items():
                 z_dsts[b].append(sl)
-            root, sl = rec.concat([3, 3, 3], H, W, name=p + "pred")
+            root, sl = rec.concat([3, 3, 3], H, W, name=p + "pred", B=KB)
             heads = [getattr(self, "%slast_layer_%d" % (p, h + 1)) for h in range(3)]
             mids = rec.conv_bn_multi([dict(x=cat, conv=hd[0], bn=hd[1], relu=True) for hd in heads])
             for h in range(3):
@@ -515,6 +525,18 @@ class HighResolutionNetED(HighResolutionNet):
             inputs += list(z) + [code]
         x1, x2, x3 = self._run(inputs)
         return x1, x2, x3
+
+    def sample_k(self, x, z, code):
+        """K latent draws per context clip in ONE pass (reference: lib/core/function.py:124-146 runs the
+        whole wrapper once per draw).  x: [B, 3L, H, W] context clips; z: 4 maps [K*B, Z, H_i, W_i]; code: [K*B, Z, 1, 1];
+        draw k of clip b sits at row k*B + b.  The encoder trunk up to transition3 does not depend on z: it runs once per
+        clip and is replicated; returns (x1, x2, x3) of shape [K*B, 3L, H, W].  Inference only (eval or no_grad)."""
+        if torch.is_grad_enabled() and self.training:
+            raise RuntimeError("vae2_b200: sample_k is an inference path (call under torch.no_grad() or in eval mode)")
+        KB, B = z[0].shape[0], x.shape[0]
+        assert KB % B == 0 and code.shape[0] == KB and len(z) == 4
+        with torch.no_grad():
+            return self._run([x] + list(z) + [code], tag=("ksample", KB // B), batch=KB)
 
 
 class HighResolutionNetEDz(HighResolutionNet):
@@ -565,14 +587,43 @@ class HighResolutionNetDsc(HighResolutionNet):
         return {"": self.clip_length} if self.is_sequence else None
 
     def _record(self, rec, shapes, needs, tag):
-        _, Cx, H, W = shapes[0]
-        _, cat = self._emit_trunk(rec, "", rec.input(Cx, H, W, needs[0]))
+        if isinstance(tag, tuple) and tag[0] == "groups":
+            # stacked calls: group gi = channel window [coff, coff + Cin) of input #slot, samples gi*Bg .. (gi+1)*Bg
+            _, Cin, groups = tag
+            Bg, _, H, W = shapes[0]
+            x = rec.plan.new_act(Cin, H, W, name="in_groups")
+            for gi, (slot, coff) in enumerate(groups):
+                rec.group_input(slot, Cin, H, W, shapes[slot][1], coff, x, gi, Bg, needs[slot])
+            rec.n_in = len(shapes)
+        else:
+            _, Cx, H, W = shapes[0]
+            x = rec.input(Cx, H, W, needs[0])
+        _, cat = self._emit_trunk(rec, "", x)
         o = self._emit_head(rec, self.last_layer, cat)
         rec.output(o)
         return [(1, H, W)]
 
     def forward(self, x, *args, **kwargs):
         return self._run([x])[0]
+
+    def forward_groups(self, sources):
+        """Several calls of this discriminator as ONE stacked pass.  ``sources`` lists, in the
+        reference's call order, (tensor [B, C, H, W], channel offset): call i sees channels [off, off + Cin) of its
+        tensor, exactly what ``D(x[:, off:off + Cin])`` would.  Returns [len(sources) * B, 1, H, W]; rows
+        [i*B, (i+1)*B) are call i's output.  Each call keeps its own BatchNorm batch statistics, running statistics
+        are updated call by call and num_batches_tracked advances by len(sources) -- bit-for-bit the statistics
+        grouping of the reference's sequential calls (lib/utils/utils.py:114-119, 259-267)."""
+        cin = self.conv1.in_channels
+        tensors, groups = [], []
+        for t, off in sources:
+            slot = next((i for i, u in enumerate(tensors) if u is t), None)
+            if slot is None:
+                tensors.append(t)
+                slot = len(tensors) - 1
+            assert t.shape == tensors[0].shape and off + cin <= t.shape[1]
+            groups.append((slot, int(off)))
+        B = tensors[0].shape[0]
+        return self._run(tensors, tag=("groups", cin, tuple(groups)), batch=B * len(groups), stat_groups=len(groups))[0]
 
 
 def get_encdec_model(cfg, **kwargs):

@@ -38,6 +38,29 @@ def __getattr__(name):
     return _fallthrough.reference_attr("utils.utils", name)
 
 
+def _stack_D():
+    """Run the discriminator calls of a step as stacked passes (models.enc_hrnet.HighResolutionNetDsc.forward_groups);
+    VAE2_STACK_D=0 restores one pass per call."""
+    return os.environ.get("VAE2_STACK_D", "1") != "0"
+
+
+class _frozen:
+    """Parameters of `modules` do not require grad inside the block (the plan recorder then emits no weight /
+    gamma / beta gradient for them)."""
+
+    def __init__(self, modules, on):
+        self.ps = [p for m in modules for p in m.parameters() if p.requires_grad] if on else []
+
+    def __enter__(self):
+        for p in self.ps:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p in self.ps:
+            p.requires_grad_(True)
+        return False
+
+
 def _fast_losses(*crits):
     """True when the criteria are this package's fused ones (otherwise call them as given)."""
     from core import criterion as C_
@@ -55,6 +78,10 @@ class FullModel_encdec(nn.Module):
         self.criterion_recon, self.criterion_KL, self.criterion_gan = criterion_recon, criterion_KL, criterion_gan
         self.x1recon_lambda, self.x2recon_lambda = x1recon_lambda, x2recon_lambda
         self.x3recon_lambda, self.gan_lambda = x3recon_lambda, gan_lambda
+        # The reference's loop zeroes the discriminators' gradients right after this wrapper's backward
+        # (lib/core/function.py:499-512: optimizer_D.zero_grad() precedes loss_D.backward()), so the D weight / gamma /
+        # beta gradients of the generator step are dead.  True = do not compute them (their .grad stays as it was).
+        self.skip_dead_D_grads = os.environ.get("VAE2_SKIP_DEAD_D_GRADS", "0") == "1"
 
     def _anomoly_detection(self, tensor_dict=None):
         """Reference semantics (:63-65) without the per-tensor host sync: raises for any earlier
@@ -96,8 +123,14 @@ class FullModel_encdec(nn.Module):
         xt_predict, x2t_predict, x3t_predict = self.encdec_model(x=xt, z=z, is_baseline=False)   # :105
 
         L = self.D_model_sequence.clip_length
-        d_seq = self.D_model_sequence(x2t_predict)
-        d_frm = [self.D_model_frame(x2t_predict[:, f * 3: f * 3 + 3, :, :]) for f in range(x2t.shape[1] // L)]
+        nf = x2t.shape[1] // L
+        with _frozen([self.D_model_sequence, self.D_model_frame], self.skip_dead_D_grads and torch.is_grad_enabled()):
+            d_seq = self.D_model_sequence(x2t_predict)
+            if _stack_D() and hasattr(self.D_model_frame, "forward_groups"):
+                allf = self.D_model_frame.forward_groups([(x2t_predict, 3 * f) for f in range(nf)])     # :116-119
+                d_frm = [allf[f * B:(f + 1) * B] for f in range(nf)]
+            else:
+                d_frm = [self.D_model_frame(x2t_predict[:, f * 3: f * 3 + 3, :, :]) for f in range(nf)]
         if _fast_losses(self.criterion_recon, self.criterion_KL, self.criterion_gan):
             tensors = [xt_predict, xt, x2t_predict, x2t, x3t_predict, x3t, d_seq] + d_frm
             spec = [dict(kind=0, slot=0, a=0, b=1, scale=1.0 / B, name="xt_predict"),
@@ -143,11 +176,16 @@ class FullModel_D(nn.Module):
         B = real.shape[0]
         L = self.D_model_sequence.clip_length
         # call order as the reference (:260-267): seq(real), seq(fake), then per frame real, fake
-        outs = [self.D_model_sequence(real), self.D_model_sequence(fake)]
         nf = x2t.shape[1] // L
-        for f in range(nf):
-            outs.append(self.D_model_frame(real[:, f * 3: f * 3 + 3, :, :]))
-            outs.append(self.D_model_frame(fake[:, f * 3: f * 3 + 3, :, :]))
+        if _stack_D() and hasattr(self.D_model_frame, "forward_groups"):
+            seq = self.D_model_sequence.forward_groups([(real, 0), (fake, 0)])
+            frm = self.D_model_frame.forward_groups([(t, 3 * f) for f in range(nf) for t in (real, fake)])
+            outs = [seq[:B], seq[B:]] + [frm[i * B:(i + 1) * B] for i in range(2 * nf)]
+        else:
+            outs = [self.D_model_sequence(real), self.D_model_sequence(fake)]
+            for f in range(nf):
+                outs.append(self.D_model_frame(real[:, f * 3: f * 3 + 3, :, :]))
+                outs.append(self.D_model_frame(fake[:, f * 3: f * 3 + 3, :, :]))
         spec = [dict(kind=2, slot=0, a=0, b=None, scale=0.5 / B, target=1.0, name="d_seq_real"),
                 dict(kind=2, slot=0, a=1, b=None, scale=0.5 / B, target=0.0, name="d_seq_fake")]
         for f in range(nf):
