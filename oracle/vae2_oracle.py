@@ -263,6 +263,27 @@ def _code_maps(code, xs):
     return [code.repeat(1, 1, t.shape[-2], t.shape[-1]) for t in xs]
 
 
+class bf16_storage:
+    """Context manager: emulate bf16 ACTIVATION STORAGE inside this oracle -- every conv and BN output is rounded to
+    bf16 (straight-through for autograd), arithmetic stays in the tensors' own dtype (use fp64).  This is the noise
+    model of the tensor-core path (bf16 tensors in HBM, fp32 accumulation): tests use it as the yardstick that tells
+    bf16 rounding noise, amplified by a deep random-weight net, apart from a wrong kernel."""
+
+    def __enter__(self):
+        global _conv, _bn
+        self._c, self._b = _conv, _bn
+        q = lambda x: x + (x.bfloat16().to(x.dtype) - x).detach()
+        oc, ob = _conv, _bn
+        _conv = lambda c, name, x, stride=1: q(oc(c, name, x, stride))
+        _bn = lambda c, name, x: q(ob(c, name, x))
+        return self
+
+    def __exit__(self, *exc):
+        global _conv, _bn
+        _conv, _bn = self._c, self._b
+        return False
+
+
 # ---------------------------------------------------------------------------
 # the four networks
 # ---------------------------------------------------------------------------

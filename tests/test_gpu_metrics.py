@@ -1,0 +1,120 @@
+"""GPU: the callers either side of the path against the CPU oracle (oracle/metrics_oracle.py):
+device input pipeline, K-sample inference driver, un-normalise / L1 / PSNR / SSIM / MS-SSIM kernels."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import E, O, RandnQueue, build_product, case_inputs, cfg_of, golden, log_err, rel_err
+from oracle import metrics_oracle as MO
+
+import core.sampling as S
+import utils.device_pipeline as DP
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_device_input_pipeline_matches_dataset_transform():
+    rs = np.random.RandomState(3)
+    B, T, H, W = 2, 9, 37, 53
+    frames = rs.randint(0, 256, size=(B, T, H, W, 3)).astype(np.uint8)
+    frames[0, 0, 0, :8] = [[0, 0, 0], [255, 255, 255], [1, 2, 3], [254, 0, 255], [128, 128, 128], [7, 77, 177], [0, 255, 0], [9, 9, 9]]
+    ref = [np.stack(c) for c in zip(*[MO.clips_from_frames(list(frames[b])) for b in range(B)])]
+    got = DP.clips_from_u8(torch.from_numpy(frames).to(DEV))
+    assert len(got) == 3
+    for a, r in zip(got, ref):
+        assert tuple(a.shape) == (B, 9, H, W)
+        assert float((a.cpu() - torch.from_numpy(r)).abs().max()) < 1e-6      # <= 1 ulp of values of magnitude ~2
+    # the staged loader yields the same clips, in order, for ragged batch sizes
+    batches = [torch.from_numpy(frames), torch.from_numpy(frames[:1]), torch.from_numpy(frames[::-1].copy())]
+    out = list(DP.DeviceClipLoader(batches, DEV))
+    assert len(out) == 3 and tuple(out[1][0].shape) == (1, 9, H, W)
+    assert torch.equal(out[0][1], got[1]) and torch.equal(out[2][2][0], got[2][1]) and torch.equal(out[1][0][0], got[0][0])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DP.clips_from_u8(torch.from_numpy(frames))
+
+
+def test_image_metrics_match_oracle_and_closed_forms():
+    g = torch.Generator().manual_seed(5)
+    R, B, H, W = 4, 2, 67, 90                 # odd sizes: MS-SSIM pooling pads
+    gt = torch.randn(B, 9, H, W, generator=g)
+    pred = gt.repeat(R // B, 1, 1, 1) + 0.2 * torch.randn(R, 9, H, W, generator=g)
+    pred[0, :3] = 5.0                          # saturates the clip at 255
+    im, im_gt = S.to_image(pred.to(DEV)), S.to_image(gt.to(DEV))
+    recon, psnr = S.frame_metrics(im, im_gt)
+    worst = dict(to_image=0.0, recon=0.0, psnr=0.0, ssim=0.0, msssim=0.0)
+    for r in range(R):
+        for f in range(3):
+            a, b = MO.to_image(pred[r, 3 * f:3 * f + 3].numpy()), MO.to_image(gt[r % B, 3 * f:3 * f + 3].numpy())
+            worst["to_image"] = max(worst["to_image"], float(np.abs(im[r, 3 * f:3 * f + 3].permute(1, 2, 0).cpu().numpy() - a).max()))
+            rc, ps = MO.recon_and_psnr(a, b)
+            worst["recon"] = max(worst["recon"], abs(float(recon[r, f]) - rc) / rc)
+            worst["psnr"] = max(worst["psnr"], abs(float(psnr[r, f]) - ps) / abs(ps))
+    fr = im.view(-1, 3, H, W)
+    gsel = im_gt.view(B, 3, 3, H, W)[torch.arange(R) % B].reshape(-1, 3, H, W)
+    s_ref, ms_ref = MO.ssim(fr.cpu(), gsel.cpu()), MO.ms_ssim(fr.cpu(), gsel.cpu())
+    s_got, ms_got = S.ssim(fr, gsel, 255, size_average=False), S.ms_ssim(fr, gsel, 255, size_average=False)
+    worst["ssim"] = float(((s_got.cpu() - s_ref.double()).abs() / s_ref.double().abs()).max())
+    worst["msssim"] = float(((ms_got.cpu() - ms_ref.double()).abs() / ms_ref.double().abs()).max())
+    log_err("image_metrics", **worst)
+    assert worst["to_image"] < 1e-4 and worst["recon"] < 1e-5 and worst["psnr"] < 1e-5, worst
+    assert worst["ssim"] < 1e-4 and worst["msssim"] < 1e-4, worst
+    assert abs(float(S.ssim(fr, gsel)) - float(s_ref.mean())) < 1e-5          # size_average=True, as the reference calls it
+    # closed forms: identical images -> 1; constant images a, b -> (2ab + C1)/(a^2 + b^2 + C1)
+    assert abs(float(S.ssim(fr, fr)) - 1.0) < 1e-6 and abs(float(S.ms_ssim(fr, fr)) - 1.0) < 1e-6
+    a, b = 60.0, 200.0
+    ca, cb = torch.full((1, 3, 40, 50), a, device=DEV), torch.full((1, 3, 40, 50), b, device=DEV)
+    C1 = (0.01 * 255) ** 2
+    assert abs(float(S.ssim(ca, cb)) - (2 * a * b + C1) / (a * a + b * b + C1)) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_k_sample_inference_equals_sequential_draws(prec):
+    """K stacked draws == K calls of the eval-mode wrapper in prior_sampling mode (the reference's loop,
+    function.py:124-146), same eps; draw 0 also equals the golden eval arrays of the unmodified reference."""
+    E.set_precision(prec)
+    try:
+        name = "tiny_b2_32x64"
+        gold = golden(name)
+        cfg = cfg_of(str(gold["cfg"]))
+        g, d = build_product(cfg)
+        O.fill_state_dict(g.state_dict(), seed_tag=name, mode="trained")
+        B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
+        g = g.to(DEV).eval()
+        K = 3
+        draws = [(eps_z, code)] + [([O.det_normal("ks%d:%d" % (k, i), tuple(e.shape)) for i, e in enumerate(eps_z)],
+                                    O.det_normal("ks%d:c" % k, tuple(code.shape))) for k in range(1, K)]
+        xd, x2d, x3d = xt.to(DEV), x2t.to(DEV), x3t.to(DEV)
+        seq = []
+        with torch.no_grad():
+            for ez, cd in draws:
+                with RandnQueue([cd]):
+                    _, x1p, x2p, x3p = g(xt=xd, x2t=x2d, x3t=x3d, multiplier=1.0, eps=[e.to(DEV) for e in ez],
+                                         sampling_mode="prior_sampling")
+                seq.append((x1p.clone(), x2p.clone(), x3p.clone()))
+        z = [torch.cat([draws[k][0][i] for k in range(K)], 0).to(DEV) for i in range(4)]
+        cds = torch.cat([draws[k][1] for k in range(K)], 0).to(DEV)
+        out = S.KSampleInference(g, K=K)(xd, x2d, x3d, eps=(z, cds))
+        tol = 1e-5 if prec == "fp32" else 3e-2
+        worst = 0.0
+        for k in range(K):
+            for j, key in enumerate(("xt_predict", "x2t_predict", "x3t_predict")):
+                worst = max(worst, rel_err(out[key][k], seq[k][j]))
+        e_gold = max(rel_err(out[key][0], gold[gk]) for key, gk in (("xt_predict", "eval_x1p"), ("x2t_predict", "eval_x2p"),
+                                                                   ("x3t_predict", "eval_x3p")))
+        # scores against the oracle on the sequential predictions
+        im, gt = MO.to_image(seq[1][1][0, 3:6].cpu().numpy()), MO.to_image(x2t[0, 3:6].numpy())
+        rc, ps = MO.recon_and_psnr(im, gt)
+        e_rc = abs(float(out["x2t_recon"][1, 0, 1]) - rc) / rc
+        e_ps = abs(float(out["x2t_psnr"][1, 0, 1]) - ps) / abs(ps)
+        log_err("ksample_" + prec, stacked_vs_sequential=worst, draw0_vs_reference_golden=e_gold, recon=e_rc, psnr=e_ps)
+        assert worst < tol, worst
+        assert e_gold < (1e-4 if prec == "fp32" else 5e-2), e_gold
+        assert e_rc < 10 * tol and e_ps < 10 * tol
+        assert out["x3t_ssim"].shape == (K, B, 3) and bool(torch.isfinite(out["x3t_msssim"]).all())
+        if prec == "fp32":      # inference plans recycle activation buffers: the resident footprint is far below the sum
+            plan = [p for pool in g.encdec_model._plans().values() for p in pool if not p.training][-1]
+            total = sum(a.numel for a in plan.all_acts) * plan.prec.esize
+            assert plan.lazy_bytes < 0.4 * total, (plan.lazy_bytes, total)
+    finally:
+        E.set_precision("fp32")

@@ -331,8 +331,12 @@ def test_activation_arena_matches_private_memory(graphs):
                 hist.append([float(l.mean()) for l in losses] + [float(dl[0].mean())])
             if arena:
                 losses, _, x2p, _ = _run_g_step(g, xd, x2d, x3d, eps_z, code)     # G backward left pending ...
-                with pytest.raises(RuntimeError, match="share activation memory"):
-                    d(x2d, x2p.detach())                                             # ... so phase D must refuse
+                os.environ["VAE2_EAGER_GAN"] = "0"    # (the eager D step lives in the scratch region and would not collide)
+                try:
+                    with pytest.raises(RuntimeError, match="share activation memory"):
+                        d(x2d, x2p.detach())                                         # ... so phase D must refuse
+                finally:
+                    os.environ.pop("VAE2_EAGER_GAN", None)
                 del losses
         finally:
             E.use_cuda_graphs(False)

@@ -81,6 +81,13 @@ class ActArena:
     live = {}
     _pools = {}
 
+    @staticmethod
+    def region(phase):
+        """Phases named 'region:name' live in their own pool: 'scratch:*' holds the transient discriminator passes whose
+        backward runs right after their forward (utils.utils._EagerGan*), next to -- not on top of -- the 'main' pool
+        in which the generator networks wait for their backward."""
+        return phase.split(":", 1)[0] if (phase is not None and ":" in phase) else "main"
+
     @classmethod
     def enabled(cls):
         return os.environ.get("VAE2_ACT_ARENA", "1") != "0"
@@ -93,7 +100,7 @@ class ActArena:
         if cls.phase is None or not cls.enabled():
             return None
         esize = torch.empty(0, dtype=tdtype).element_size()
-        key = (str(device), tdtype)
+        key = (str(device), tdtype, cls.region(cls.phase))
         pool = cls._pools.setdefault(key, {"chunks": [], "cur": {}, "free": {}})
         n = pad_to(numel, 128)
         free = pool["free"].setdefault(cls.phase, [])
@@ -165,6 +172,22 @@ class activation_phase:
         return False
 
 
+class _FakeBuf:
+    """Stand-in for a gradient buffer during the sizing pass of Plan._emit_backward (only addresses are taken)."""
+
+    def __init__(self, byte_off, numel):
+        self._p, self._n = 4096 + byte_off, numel
+
+    def data_ptr(self):
+        return self._p
+
+    def numel(self):
+        return self._n
+
+    def zero_(self):
+        return self
+
+
 class Act:
     """A channels-last activation [B][H][W][ld] (possibly a channel slice of a wider root)."""
 
@@ -222,7 +245,7 @@ class Act:
             if self.parent is None:
                 g = Act.__new__(Act)
                 g.__dict__.update(self.__dict__)
-                g._buf = self.plan.grad_alloc(self.buf.numel())
+                g._buf, g._gext = self.plan.grad_alloc(self.numel)
                 g._grad, g.parent = None, None
                 self._grad = g
             else:
@@ -275,7 +298,7 @@ class Plan:
         self.keep = []                        # keep-alive for ctypes arrays / tensors
         self.busy = False
         self.n_collectives_fwd = self.n_collectives_bwd = 0
-        self._garena, self._goff = None, 0
+        self._garena, self._goff, self._gsim, self._gfree, self._gpeak = None, 0, False, [], 0
         self.all_acts = []
         self.arena_phase = None               # set when an activation buffer comes from the phase-shared ActArena
         self.arena_extents = []               # (pool key, phase, chunk, offset, size) of those buffers
@@ -300,14 +323,73 @@ class Plan:
         return Act(self, C_, H, W, name=name, B=B)
 
     def grad_alloc(self, numel):
-        """Bump-allocate an activation-gradient buffer from the shared arena (128-element aligned)."""
-        if self._garena is None:      # finalize() sizes the arena; a stray early request gets private memory
-            return torch.zeros(numel, dtype=self.prec.tdtype, device=self.device)
+        """An activation-gradient buffer from the shared arena (128-element aligned): first fit among the extents that
+        finished gradients gave back (_release_grads), else the bump cursor.  Returns (buffer, extent).  During the
+        sizing pass (_gsim) the buffer is a stand-in that only knows its offset."""
+        if self._garena is None and not self._gsim:      # VAE2_PRIVATE_GRADS=1 / a stray early request: private memory
+            return torch.zeros(numel, dtype=self.prec.tdtype, device=self.device), None
         n = pad_to(numel, 128)
-        assert self._goff + n <= self._garena.numel(), "gradient arena under-sized"
-        t = self._garena[self._goff:self._goff + numel]
-        self._goff += n
-        return t
+        off = None
+        for i, (o, sz) in enumerate(self._gfree):
+            if sz >= n:
+                off = o
+                if sz == n:
+                    self._gfree.pop(i)
+                else:
+                    self._gfree[i] = (o + n, sz - n)
+                break
+        if off is None:
+            off = self._goff
+            self._goff += n
+            self._gpeak = max(self._gpeak, self._goff)
+        if self._gsim:
+            return _FakeBuf(off * self.prec.esize, numel), (off, n)
+        assert off + n <= self._garena.numel(), "gradient arena under-sized"
+        return self._garena[off:off + numel], (off, n)
+
+    def _release_grads(self, op):
+        """After op's backward has been emitted: the gradient of every buffer whose producers are all done is dead."""
+        for a in op.writes():
+            r = a.root
+            r._nw -= 1
+            g = r._grad
+            if r._nw == 0 and g is not None and getattr(g, "_gext", None) is not None:
+                self._gfree.append(g._gext)
+                g._gext = None
+                self._gfree.sort()
+                out = []
+                for e in self._gfree:           # coalesce neighbours
+                    if out and out[-1][0] + out[-1][1] == e[0]:
+                        out[-1] = (out[-1][0], out[-1][1] + e[1])
+                    else:
+                        out.append(e)
+                self._gfree = out
+
+    def _emit_backward(self, convs):
+        """(Re)build the backward program.  Gradient buffers are recycled: a gradient lives from the backward of the
+        buffer's last consumer to the backward of its first producer, so the arena holds the peak over the program,
+        not one buffer per activation (63 GB -> a few GB for a stacked discriminator pass at B=4)."""
+        self.bwd, self.pre_bwd, self.post_bwd = [], [], []
+        self.n_collectives_bwd = 0
+        self._gfree, self._goff, self._gpeak = [], 0, 0
+        acts = {id(a): a for a in self.all_acts}
+        for o in self.ops:
+            for a in list(o.reads()) + list(o.writes()):
+                acts[id(a)] = a
+        for a in acts.values():
+            a._grad, a.grad_written, a._nw = None, False, 0
+        for o in self.ops:
+            for a in o.writes():
+                a.root._nw += 1
+        dptr = self.dwp_flat
+        any_wgrad = any(o.conv.weight.requires_grad for o in convs)
+        if any_wgrad:
+            self.bwd.append(lambda st: dptr.zero_())
+        for o in reversed(self.ops):
+            o.emit_bwd(self)
+            self._release_grads(o)
+        if any_wgrad:
+            self.bwd.append(lambda st: N.call.vae2_unpack_wgrad(self.up_dev.data_ptr(), self.n_convs, 0, st))
 
     def concat(self, Cs, H, W, name="cat", B=None):
         """A buffer made of padded channel segments; returns (root, [slice acts])."""
@@ -437,17 +519,14 @@ class Plan:
                 self.pre_fwd.insert(0, lambda st, b=r.buf: b.zero_())
         # backward program (reverse order; accumulate flags resolved statically)
         if self.training:
+            self._garena, self._gsim = None, False
             if os.environ.get("VAE2_PRIVATE_GRADS", "0") != "1":
-                need = sum(pad_to(a.buf.numel(), 128) for a in self.all_acts)
-                self._garena, self._goff = GradArena.get(dev, self.prec.tdtype, need), 0
-            dptr = self.dwp_flat
-            any_wgrad = any(o.conv.weight.requires_grad for o in convs)
-            if any_wgrad:
-                self.bwd.append(lambda st: dptr.zero_())
-            for o in reversed(self.ops):
-                o.emit_bwd(self)
-            if any_wgrad:
-                self.bwd.append(lambda st: N.call.vae2_unpack_wgrad(self.up_dev.data_ptr(), self.n_convs, 0, st))
+                self._gsim = True                    # sizing pass: same emission, stand-in buffers, measures the peak
+                self._emit_backward(convs)
+                self._gsim = False
+                self.grad_arena_elems = self._gpeak
+                self._garena = GradArena.get(dev, self.prec.tdtype, max(self._gpeak, 128))
+            self._emit_backward(convs)
         self.n_launch_fwd, self.n_launch_bwd = len(self.fwd), len(self.bwd)
         return self
 

@@ -161,7 +161,7 @@ class EngineModule(nn.Module):
             pool.append(plan)
         if plan.arena_phase is not None:
             for other, n in ActArena.live.items():
-                if other != plan.arena_phase and n > 0:
+                if other != plan.arena_phase and n > 0 and ActArena.region(other) == ActArena.region(plan.arena_phase):
                     raise RuntimeError("vae2_b200: a network of phase %r still waits for its backward while phase %r runs; "
                                        "the phases share activation memory (set VAE2_ACT_ARENA=0 to interleave them)"
                                        % (other, plan.arena_phase))

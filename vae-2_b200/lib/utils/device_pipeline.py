@@ -52,27 +52,32 @@ class DeviceClipLoader:
         def stage(host, slot):
             if ring[slot] is None or ring[slot][0].shape != host.shape:
                 ring[slot] = (torch.empty(host.shape, dtype=torch.uint8).pin_memory(),
-                              torch.empty(host.shape, dtype=torch.uint8, device=self.device), torch.cuda.Event())
-            pin, dev, ev = ring[slot]
+                              torch.empty(host.shape, dtype=torch.uint8, device=self.device), torch.cuda.Event(),
+                              torch.cuda.Event())
+            pin, dev, ev, consumed = ring[slot]
             ev.synchronize()                       # the device copy that last used this pinned buffer has finished
             pin.copy_(host)
             with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(consumed)   # the normalise kernel that last read this device buffer is done
                 dev.copy_(pin, non_blocking=True)
                 ev.record(self.copy_stream)
             self.bytes_per_batch = host.numel()
-            return dev, ev
+            return dev, ev, consumed
 
         try:
             pending = stage(next(it), 0)
         except StopIteration:
             return
         while pending is not None:
-            dev, ev = pending
+            dev, ev, consumed = pending
             i += 1
             try:
                 nxt = stage(next(it), i % 2)
             except StopIteration:
                 nxt = None
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            yield tuple(clips_from_u8(dev, self.clip_num))
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            clips = tuple(clips_from_u8(dev, self.clip_num))
+            consumed.record(cur)
+            yield clips
             pending = nxt

@@ -61,6 +61,114 @@ class _frozen:
         return False
 
 
+def _eager_gan():
+    """Evaluate the GAN terms eagerly (forward AND backward of every discriminator pass inside the wrapper's forward):
+    a discriminator's activations then live only for the duration of its own pass (engine scratch region) instead of
+    until the caller's backward().  VAE2_EAGER_GAN=0 restores plain autograd ordering."""
+    return os.environ.get("VAE2_EAGER_GAN", "1") != "0"
+
+
+def _d_stack():
+    """Most discriminator calls stacked into one pass (memory of a stacked pass grows with the count)."""
+    return max(1, int(os.environ.get("VAE2_D_STACK", "6")))
+
+
+class _EagerGanG(torch.autograd.Function):
+    """GAN terms of the generator step (reference lib/utils/utils.py:114-119) with the discriminators' parameters
+    frozen: d(term)/d(x2t_predict) is computed right away -- the terms are linear in the upstream gradient, so the
+    caller's backward() only scales the two stored gradients."""
+
+    @staticmethod
+    def forward(ctx, wrapper, x2p):
+        B = x2p.shape[0]
+        L = wrapper.D_model_sequence.clip_length
+        nf = x2p.shape[1] // L
+        vals, grads = [], []
+        for which in ("seq", "frm"):
+            with torch.enable_grad():
+                xd = x2p.detach().requires_grad_(True)
+                with _E.activation_phase("scratch:G" + which), _frozen([wrapper.D_model_sequence, wrapper.D_model_frame], True):
+                    if which == "seq":
+                        outs = [wrapper.D_model_sequence(xd)]
+                    elif _stack_D() and hasattr(wrapper.D_model_frame, "forward_groups"):
+                        allf = wrapper.D_model_frame.forward_groups([(xd, 3 * f) for f in range(nf)])
+                        outs = [allf[f * B:(f + 1) * B] for f in range(nf)]
+                    else:
+                        outs = [wrapper.D_model_frame(xd[:, f * 3: f * 3 + 3, :, :]) for f in range(nf)]
+                    spec = [dict(kind=2, slot=0, a=i, b=None, scale=0.5 / B, target=1.0, name="d_%s%d" % (which, i))
+                            for i in range(len(outs))]
+                    v = _E.elbo_terms(spec, 1, outs)[0][0]
+                    (g,) = torch.autograd.grad(v, xd)
+            vals.append(v.detach())
+            grads.append(g)
+        ctx.save_for_backward(*grads)
+        return vals[0], vals[1]
+
+    @staticmethod
+    def backward(ctx, g_seq, g_frm):
+        a, b = ctx.saved_tensors
+        out = None
+        for g, t in ((g_seq, a), (g_frm, b)):
+            if g is not None:
+                out = g * t if out is None else out + g * t
+        return None, out
+
+
+class _EagerGanD(torch.autograd.Function):
+    """Discriminator step (reference lib/utils/utils.py:259-276): every (stacked) pass runs forward, its LSGAN terms
+    and backward at once; parameter gradients for a unit upstream gradient are kept (a few MB) and scaled in backward()."""
+
+    @staticmethod
+    def forward(ctx, wrapper, real, fake, n_seq, *params):
+        B = real.shape[0]
+        L = wrapper.D_model_sequence.clip_length
+        nf = real.shape[1] // L
+        seq_p, frm_p = params[:n_seq], params[n_seq:]
+        half = lambda t: dict(kind=2, slot=0, b=None, scale=0.5 / B, target=t)
+        with torch.enable_grad():
+            with _E.activation_phase("scratch:Dseq"):
+                seq = wrapper.D_model_sequence.forward_groups([(real, 0), (fake, 0)])
+                v_seq = _E.elbo_terms([dict(half(1.0), a=0, name="d_seq_real"), dict(half(0.0), a=1, name="d_seq_fake")], 1,
+                                      [seq[:B], seq[B:]])[0][0]
+                g_seq = torch.autograd.grad(v_seq, [p for p in seq_p if p.requires_grad], allow_unused=True)
+            per = max(1, _d_stack() // 2)                    # frames per stacked pass (each frame = real + fake)
+            v_frm, g_frm = None, None
+            for f0 in range(0, nf, per):
+                fr = range(f0, min(nf, f0 + per))
+                with _E.activation_phase("scratch:Dfrm"):
+                    # channel windows are cut here (offset 0 in the plan) so that every chunk replays ONE plan
+                    srcs = [(t[:, 3 * f:3 * f + 3].contiguous(), 0) for f in fr for t in (real, fake)]
+                    out = wrapper.D_model_frame.forward_groups(srcs)
+                    spec = [dict(half(1.0 if i % 2 == 0 else 0.0), a=i, name="d_frm_%s" % ("real" if i % 2 == 0 else "fake"))
+                            for i in range(len(srcs))]
+                    v = _E.elbo_terms(spec, 1, [out[i * B:(i + 1) * B] for i in range(len(srcs))])[0][0]
+                    g = torch.autograd.grad(v, [p for p in frm_p if p.requires_grad], allow_unused=True)
+                v_frm = v.detach() if v_frm is None else v_frm + v.detach()
+                g_frm = list(g) if g_frm is None else [a if b is None else (b if a is None else a + b) for a, b in zip(g_frm, g)]
+        ctx.n_seq, ctx.req = n_seq, [p.requires_grad for p in params]
+        ctx.grads = list(g_seq) + list(g_frm)
+        return v_seq.detach(), v_frm
+
+    @staticmethod
+    def backward(ctx, up_seq, up_frm):
+        out, it = [], iter(ctx.grads)
+        n_seq_req = sum(ctx.req[:ctx.n_seq])
+        for i, need in enumerate(ctx.req):
+            if not need:
+                out.append(None)
+                continue
+            g = next(it)
+            up = up_seq if i < ctx.n_seq else up_frm
+            out.append(None if (g is None or up is None) else g * up)
+        ctx.grads = None
+        return (None, None, None, None) + tuple(out)
+
+
+def _crit():
+    from core import criterion as C_
+    return C_
+
+
 def _fast_losses(*crits):
     """True when the criteria are this package's fused ones (otherwise call them as given)."""
     from core import criterion as C_
@@ -124,31 +232,40 @@ class FullModel_encdec(nn.Module):
 
         L = self.D_model_sequence.clip_length
         nf = x2t.shape[1] // L
-        with _frozen([self.D_model_sequence, self.D_model_frame], self.skip_dead_D_grads and torch.is_grad_enabled()):
-            d_seq = self.D_model_sequence(x2t_predict)
-            if _stack_D() and hasattr(self.D_model_frame, "forward_groups"):
-                allf = self.D_model_frame.forward_groups([(x2t_predict, 3 * f) for f in range(nf)])     # :116-119
-                d_frm = [allf[f * B:(f + 1) * B] for f in range(nf)]
-            else:
-                d_frm = [self.D_model_frame(x2t_predict[:, f * 3: f * 3 + 3, :, :]) for f in range(nf)]
-        if _fast_losses(self.criterion_recon, self.criterion_KL, self.criterion_gan):
-            tensors = [xt_predict, xt, x2t_predict, x2t, x3t_predict, x3t, d_seq] + d_frm
-            spec = [dict(kind=0, slot=0, a=0, b=1, scale=1.0 / B, name="xt_predict"),
-                    dict(kind=0, slot=1, a=2, b=3, scale=1.0 / B, name="x2t_predict"),
-                    dict(kind=0, slot=2, a=4, b=5, scale=1.0 / B, name="x3t_predict"),
-                    dict(kind=2, slot=3, a=6, b=None, scale=0.5 / B, target=1.0, name="d_seq")]
-            spec += [dict(kind=2, slot=4, a=7 + f, b=None, scale=0.5 / B, target=1.0, name="d_frm%d" % f)
-                     for f in range(len(d_frm))]
-            vals = _E.elbo_terms(spec, 5, [t if i % 2 == 0 or i > 5 else t.detach() for i, t in enumerate(tensors)])[0]
+        fast = _fast_losses(self.criterion_recon, self.criterion_KL, self.criterion_gan)
+        l1_spec = [dict(kind=0, slot=0, a=0, b=1, scale=1.0 / B, name="xt_predict"),
+                   dict(kind=0, slot=1, a=2, b=3, scale=1.0 / B, name="x2t_predict"),
+                   dict(kind=0, slot=2, a=4, b=5, scale=1.0 / B, name="x3t_predict")]
+        l1_in = [xt_predict, xt.detach(), x2t_predict, x2t.detach(), x3t_predict, x3t.detach()]
+        eager = (fast and self.skip_dead_D_grads and _eager_gan() and _stack_D() and torch.is_grad_enabled()
+                 and x2t_predict.requires_grad and hasattr(self.D_model_frame, "forward_groups"))
+        if eager:
+            # discriminators frozen (their gradients are dead, see __init__) and evaluated forward+backward right here
+            x2t_gan_sequence_loss, x2t_gan_frame_loss = _EagerGanG.apply(self, x2t_predict)
+            vals = _E.elbo_terms(l1_spec, 3, l1_in)[0]
             xt_recon_loss, x2t_recon_loss, x3t_recon_loss = vals[0], vals[1], vals[2]
-            x2t_gan_sequence_loss, x2t_gan_frame_loss = vals[3], vals[4]
         else:
-            xt_recon_loss = self.criterion_recon(predict=xt_predict, target=xt)
-            x2t_recon_loss = self.criterion_recon(predict=x2t_predict, target=x2t)
-            x3t_recon_loss = self.criterion_recon(predict=x3t_predict, target=x3t)
-            x2t_gan_sequence_loss = 0.5 * self.criterion_gan(sample=d_seq, mode="real")
-            x2t_gan_frame_loss = torch.sum(torch.stack(
-                [0.5 * self.criterion_gan(sample=d, mode="real") for d in d_frm], 0), 0)
+            with _frozen([self.D_model_sequence, self.D_model_frame], self.skip_dead_D_grads and torch.is_grad_enabled()):
+                d_seq = self.D_model_sequence(x2t_predict)
+                if _stack_D() and hasattr(self.D_model_frame, "forward_groups"):
+                    allf = self.D_model_frame.forward_groups([(x2t_predict, 3 * f) for f in range(nf)])     # :116-119
+                    d_frm = [allf[f * B:(f + 1) * B] for f in range(nf)]
+                else:
+                    d_frm = [self.D_model_frame(x2t_predict[:, f * 3: f * 3 + 3, :, :]) for f in range(nf)]
+            if fast:
+                spec = l1_spec + [dict(kind=2, slot=3, a=6, b=None, scale=0.5 / B, target=1.0, name="d_seq")]
+                spec += [dict(kind=2, slot=4, a=7 + f, b=None, scale=0.5 / B, target=1.0, name="d_frm%d" % f)
+                         for f in range(len(d_frm))]
+                vals = _E.elbo_terms(spec, 5, l1_in + [d_seq] + d_frm)[0]
+                xt_recon_loss, x2t_recon_loss, x3t_recon_loss = vals[0], vals[1], vals[2]
+                x2t_gan_sequence_loss, x2t_gan_frame_loss = vals[3], vals[4]
+            else:
+                xt_recon_loss = self.criterion_recon(predict=xt_predict, target=xt)
+                x2t_recon_loss = self.criterion_recon(predict=x2t_predict, target=x2t)
+                x3t_recon_loss = self.criterion_recon(predict=x3t_predict, target=x3t)
+                x2t_gan_sequence_loss = 0.5 * self.criterion_gan(sample=d_seq, mode="real")
+                x2t_gan_frame_loss = torch.sum(torch.stack(
+                    [0.5 * self.criterion_gan(sample=d, mode="real") for d in d_frm], 0), 0)
 
         losses_all = self.x1recon_lambda * xt_recon_loss + self.x2recon_lambda * x2t_recon_loss + \
             self.x3recon_lambda * x3t_recon_loss + kl_w * z_KL_loss + \
@@ -177,6 +294,12 @@ class FullModel_D(nn.Module):
         L = self.D_model_sequence.clip_length
         # call order as the reference (:260-267): seq(real), seq(fake), then per frame real, fake
         nf = x2t.shape[1] // L
+        if (_eager_gan() and _stack_D() and torch.is_grad_enabled() and hasattr(self.D_model_frame, "forward_groups")
+                and isinstance(self.criterion_gan, _crit().lsgan_adversarial_loss)):
+            ps, pf = list(self.D_model_sequence.parameters()), list(self.D_model_frame.parameters())
+            D_losses_sequence, D_losses_frame = _EagerGanD.apply(self, real, fake, len(ps), *ps, *pf)
+            D_losses = self.gan_lambda * (D_losses_sequence + D_losses_frame)
+            return [torch.unsqueeze(D_losses, 0), D_losses_sequence, D_losses_frame]
         if _stack_D() and hasattr(self.D_model_frame, "forward_groups"):
             seq = self.D_model_sequence.forward_groups([(real, 0), (fake, 0)])
             frm = self.D_model_frame.forward_groups([(t, 3 * f) for f in range(nf) for t in (real, fake)])
