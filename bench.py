@@ -97,6 +97,9 @@ def build_models(cfg, dev, world, local_rank):
                            cfg.TRAIN.X1RECON_LAMBDA, cfg.TRAIN.X2RECON_LAMBDA, cfg.TRAIN.X3RECON_LAMBDA,
                            cfg.TRAIN.GAN_LAMBDA)
     d = U.FullModel_D(nets[2], nets[3], Cr.lsgan_adversarial_loss())
+    # The loop below is the reference's adversarial_train: optimizer_D.zero_grad() wipes whatever the generator step left
+    # in the discriminators' .grad (function.py:499-512), so those gradients are not computed (config.skip_dead_D_grads)
+    g.skip_dead_D_grads = True
     # trained-scale BN/conv init would need a checkpoint; the reference's own init is used (enc_hrnet.py:753-760)
     if world > 1:   # tools/train.py:216-229
         g = torch.nn.SyncBatchNorm.convert_sync_batchnorm(g)
@@ -458,11 +461,14 @@ def main():
                        "step": "G-step + D-step (fwd, bwd, Adam)", "per_gpu_batch": B, "global_batch": B * world,
                        "frames_per_sample": FRAMES_PER_SAMPLE, "parallelism": "dp%d" % world,
                        "l2": "activations per step >> 126 MB L2 (inputs larger than L2)",
-                       "cuda_graphs": not args.no_graphs, "frame_size": [H, W]},
+                       "cuda_graphs": not args.no_graphs, "frame_size": [H, W], "skip_dead_D_grads": True,
+                       "stacked_discriminator_passes": os.environ.get("VAE2_STACK_D", "1") != "0",
+                       "d_stack": int(os.environ.get("VAE2_D_STACK", "6"))},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": 3 * B * 9 * H * W * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
             "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
+            "arena_gb": E.ActArena.summary(),
             "clocks": clk,
             "roofline": roof,
             "kernel_shares": kernel_table,

@@ -157,6 +157,8 @@ def test_conv_f32x3_fwd_dgrad(case):
     torch.cuda.synchronize()
     y = from_act(ya, "fp32", B, Cout, Ho, Wo, Cout_p)
     e_mine, e_ref = rel_err(y, yr.detach()), rel_err(y32, yr.detach())
+    from helpers import log_err
+    log_err("f32x3_conv_%s" % (case,), f32x3_vs_fp64=e_mine, torch_fp32_vs_fp64=e_ref)
     assert e_mine < 3e-5, "f32x3 fwd err %.2e vs torch-fp32 err %.2e" % (e_mine, e_ref)
     assert float(ya.view(-1, Cout_p)[:, Cout:].abs().sum()) == 0.0
     gya, _ = to_act(gy, "fp32", Cout_p)

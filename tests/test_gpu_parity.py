@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import (E, O, M, RandnQueue, build_product, case_inputs, cfg_of, golden, rel_err)
+from helpers import (E, O, M, RandnQueue, build_product, case_inputs, cfg_of, golden, log_err, rel_err)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -162,6 +162,12 @@ def test_g_and_d_step_match_reference_golden_fp32(name, wmode):
     # 1.6e-2 apart, which leaves 8e-4 / 1e-3 on the x1-L1 and GAN terms while the x3-L1 term happens to agree to
     # 2e-6 -- so the yardstick is the worst term of the case, not each term's own luck)
     ltol = max(FP32_TOL, 3.0 * float(np.max(np.abs(gold["g_losses"] - gold["g_losses64"]) / np.abs(gold["g_losses64"]))))
+    import os as _os
+    log_err("golden_fp32_" + name + ("_fp32tc" if _os.environ.get("VAE2_FP32_TC") == "1" else ""),
+            losses_vs_ref64=(np.abs(got - gold["g_losses64"]) / np.abs(gold["g_losses64"])).tolist(),
+            losses_vs_ref32=(np.abs(got - gold["g_losses"]) / np.abs(gold["g_losses"])).tolist(), ltol=ltol,
+            acts_vs_ref64={k: rel_err(a, gold[k + "64"]) for a, k in ((x1p, "x1p"), (x2p, "x2p"), (x3p, "x3p"))},
+            ref32_vs_ref64_acts={k: rel_err(gold[k], gold[k + "64"]) for k in ("x1p", "x2p", "x3p")})
     assert np.all(np.abs(got - gold["g_losses64"]) <= ltol * np.abs(gold["g_losses64"])), \
         ("G losses vs reference fp64", got, gold["g_losses64"], ltol)
     assert np.all(np.abs(got - gold["g_losses"]) <= 2 * ltol * np.abs(gold["g_losses"])), \

@@ -13,7 +13,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 tag = sys.argv[2] if len(sys.argv) > 2 else os.path.splitext(os.path.basename(rep))[0]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+if rep.endswith(".csv"):       # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): the report itself was too big to bring back
+    raw = open(rep).read()
+    raw = raw[raw.index('"ID"'):]
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}

@@ -5,8 +5,13 @@
 // (measured 4e-6 per conv, 20x the error of an fp32 FMA loop).  Every fp32 operand is therefore split EXACTLY
 // into three bf16 terms,  x = x1 + x2 + x3  (8 + 8 + 8 significand bits), and the product is accumulated as
 //     x1*w1 + x1*w2 + x2*w1 + x2*w2 + x1*w3 + x3*w1          (dropped terms <= 2^-24 relative)
-// in the fp32 TMEM accumulator; bf16 x bf16 products are exact in fp32.  Six bf16 MMAs with K=16 cost the same
-// number of tcgen05.mma instructions as three TF32 MMAs with K=8.  Same implicit GEMM as conv_tc.cu (M tile =
+// in fp32 TMEM accumulators; bf16 x bf16 products are exact in fp32.  Six bf16 MMAs with K=16 cost the same
+// number of tcgen05.mma instructions as three TF32 MMAs with K=8.
+// TWO accumulators per tile: tensor-core accumulation truncates (about half an ulp of the running sum, biased, per
+// tcgen05.mma), and with all six products in one accumulator that bias grows with 6 x (taps x K/16) instructions --
+// measured 1e-6..1.5e-5 per conv in round 1, which pushed the encoder prediction to 1.35e-4.  Here the leading product
+// x1*w1 accumulates in D_main, the five correction products (<= 2^-8 of it) in D_corr, whose truncation is 2^-8 smaller
+// in absolute terms; the epilogue adds the two with one rounded fp32 add.  D_main sees a sixth of the instructions.  Same implicit GEMM as conv_tc.cu (M tile =
 // TH x TW pixel patch, taps x 32-channel chunks on K, N tile <= 256), different operand plumbing:
 //   * activations stay plain fp32 in HBM; four PRODUCER warps (one pixel row per thread) gather the shifted
 //     pixel's 32 channels with 16-byte loads (bounds / padding by predicate, stride-2 by address), split them
@@ -182,26 +187,27 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
                 mbar_wait(&acc_empty[as], (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NT);
+                const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * NT), d_corr = d_main + (uint32_t)NT;
                 uint32_t accum = 0;
                 for (int ks = 0; ks < nks; ++ks) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a1 = a_lo0 + (uint32_t)stage * stage_step, a2 = a1 + a_step, a3 = a2 + a_step;
                     const uint32_t w1 = a1 + w_off, w2 = w1 + w_step, w3 = w2 + w_step;
-                    // smallest terms first, x1*w1 last (keeps the tiny products from being absorbed early)
+                    // correction products (smallest first) into D_corr, the leading product into D_main
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) { umma_bf16_lohi(d_tmem, a3 + 2 * k, hi, w1 + 2 * k, hi, idesc, accum); accum = 1; }
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a1 + 2 * k, hi, w3 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w3 + 2 * k, hi, idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a2 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a2 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a1 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a1 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
+                    accum = 1;
                     umma_commit(&empty[stage]);
                     if (++stage == nstage) { stage = 0; phase ^= 1; }
                 }
@@ -228,11 +234,12 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             const int h = gi * p.sO + p.oh_off, w = gj * p.sO + p.ow_off;
             mbar_wait(&acc_full[as], use & 1);
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * NT);
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * NT);
             float* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
             for (int c0 = 0; c0 < NT; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t0 + c0, v);
+                uint32_t v[16], u[16];
+                tmem_ld16(t0 + c0, v);               // D_main
+                tmem_ld16(t0 + NT + c0, u);          // D_corr
                 tmem_ld_wait();
                 const int n = nt * NT + c0;
                 if (in_img) {
@@ -240,8 +247,10 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     for (int i = 0; i < 4; ++i) {
                         const int nn = n + 4 * i;
                         if (nn < Cn) {                      // Cn is a multiple of 4
-                            float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                            float4 f = make_float4(__uint_as_float(v[4 * i]) + __uint_as_float(u[4 * i]),
+                                                   __uint_as_float(v[4 * i + 1]) + __uint_as_float(u[4 * i + 1]),
+                                                   __uint_as_float(v[4 * i + 2]) + __uint_as_float(u[4 * i + 2]),
+                                                   __uint_as_float(v[4 * i + 3]) + __uint_as_float(u[4 * i + 3]));
                             if (bias != nullptr) {
                                 const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + nn));
                                 f.x += bb.x; f.y += bb.y; f.z += bb.z; f.w += bb.w;
@@ -373,9 +382,10 @@ static int launch_t32(const t32::Launch& L, cudaStream_t st) {
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return VAE2_ERR_UNSUPPORTED;
     p.stages = stages;
-    p.acc_stages = (2 * p.NT <= 512) ? 2 : 1;
+    p.acc_stages = (4 * p.NT <= 512) ? 2 : 1;          // two accumulators (main + correction) per stage
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.acc_stages * p.NT) p.tmem_cols <<= 1;
+    while (p.tmem_cols < p.acc_stages * 2 * p.NT) p.tmem_cols <<= 1;
+    if (p.tmem_cols > 512) return VAE2_ERR_UNSUPPORTED;
     p.accumulate = L.accumulate;
     p.a = L.a; p.bias = L.bias; p.out = L.out;
 

@@ -67,11 +67,48 @@ elbo_terms_kernel(const ElboSeg* __restrict__ segs, int nseg, float* __restrict_
                 for (long long i = tid; i < s.n; i += nthreads) acc += l1_term(s.a[i], s.b[i], bad);
             }
         } else if (s.kind == 1) {     // reparam + KL
-            for (long long i = tid; i < s.n; i += nthreads) acc += kl_elem(s, i, bad);
+            // rows r = (b, z) of HW contiguous elements: eps / z at r*HW, mu at (b*2Z + z)*HW, logvar Z planes further on
+            const bool vec = (s.HW % 4 == 0) && (s.n / 4 < 0x7fffffffLL) &&
+                             ((((uintptr_t)s.a | (uintptr_t)s.b | (uintptr_t)s.out) & 15) == 0);
+            if (vec) {
+                const unsigned hw4 = (unsigned)(s.HW / 4), n4 = (unsigned)(s.n / 4), Zu = (unsigned)s.Z;
+                const float4* e4 = reinterpret_cast<const float4*>(s.a);
+                const float4* m4 = reinterpret_cast<const float4*>(s.b);
+                float4* o4 = reinterpret_cast<float4*>(s.out);
+                for (unsigned i = (unsigned)tid; i < n4; i += (unsigned)nthreads) {
+                    const unsigned r = i / hw4, c = i - r * hw4;
+                    const unsigned b = r / Zu, z = r - b * Zu;
+                    const size_t im = (size_t)(b * 2 * Zu + z) * hw4 + c;
+                    const float4 mu = m4[im], lv = m4[im + (size_t)Zu * hw4];
+                    if (o4 != nullptr) {
+                        const float4 ep = e4 != nullptr ? e4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 zz;
+                        zz.x = s.prior ? ep.x : fmaf(expf(0.5f * lv.x), ep.x, mu.x);
+                        zz.y = s.prior ? ep.y : fmaf(expf(0.5f * lv.y), ep.y, mu.y);
+                        zz.z = s.prior ? ep.z : fmaf(expf(0.5f * lv.z), ep.z, mu.z);
+                        zz.w = s.prior ? ep.w : fmaf(expf(0.5f * lv.w), ep.w, mu.w);
+                        bad += (!finite_f(zz.x)) + (!finite_f(zz.y)) + (!finite_f(zz.z)) + (!finite_f(zz.w));
+                        o4[i] = zz;
+                    }
+                    acc += 0.5f * (mu.x * mu.x + (expm1f(lv.x) - lv.x)) + 0.5f * (mu.y * mu.y + (expm1f(lv.y) - lv.y)) +
+                           0.5f * (mu.z * mu.z + (expm1f(lv.z) - lv.z)) + 0.5f * (mu.w * mu.w + (expm1f(lv.w) - lv.w));
+                }
+            } else {
+                for (long long i = tid; i < s.n; i += nthreads) acc += kl_elem(s, i, bad);
+            }
         } else {                      // LSGAN: sum (a - target)^2
-            for (long long i = tid; i < s.n; i += nthreads) {
-                const float d = s.a[i] - s.target;
-                acc = fmaf(d, d, acc);
+            if ((s.n % 4 == 0) && (((uintptr_t)s.a & 15) == 0)) {
+                const float4* a4 = reinterpret_cast<const float4*>(s.a);
+                for (long long i = tid; i < s.n / 4; i += nthreads) {
+                    const float4 a = a4[i];
+                    const float d0 = a.x - s.target, d1 = a.y - s.target, d2 = a.z - s.target, d3 = a.w - s.target;
+                    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                }
+            } else {
+                for (long long i = tid; i < s.n; i += nthreads) {
+                    const float d = s.a[i] - s.target;
+                    acc = fmaf(d, d, acc);
+                }
             }
         }
         acc = block_sum(acc * s.scale, red);
@@ -116,6 +153,22 @@ elbo_terms_bwd_kernel(const ElboBwdSeg* __restrict__ segs, int nseg) {
         const ElboBwdSeg s = segs[si];
         const float go = (s.gout != nullptr ? *s.gout : 1.f) * s.scale;
         if (s.kind == 0) {
+            if ((s.n % 4 == 0) && ((((uintptr_t)s.a | (uintptr_t)s.b | (uintptr_t)s.grad) & 15) == 0)) {
+                const float4* a4 = reinterpret_cast<const float4*>(s.a);
+                const float4* b4 = reinterpret_cast<const float4*>(s.b);
+                float4* g4 = reinterpret_cast<float4*>(s.grad);
+                for (long long i = tid; i < s.n / 4; i += nthreads) {
+                    const float4 a = a4[i], b = b4[i];
+                    float4 gr;
+                    gr.x = a.x > b.x ? go : (a.x < b.x ? -go : 0.f);
+                    gr.y = a.y > b.y ? go : (a.y < b.y ? -go : 0.f);
+                    gr.z = a.z > b.z ? go : (a.z < b.z ? -go : 0.f);
+                    gr.w = a.w > b.w ? go : (a.w < b.w ? -go : 0.f);
+                    if (s.accumulate) { const float4 o = g4[i]; gr.x += o.x; gr.y += o.y; gr.z += o.z; gr.w += o.w; }
+                    g4[i] = gr;
+                }
+                continue;
+            }
             for (long long i = tid; i < s.n; i += nthreads) {
                 const float d = s.a[i] - s.b[i];
                 const float gr = d > 0.f ? go : (d < 0.f ? -go : 0.f);
@@ -123,6 +176,41 @@ elbo_terms_bwd_kernel(const ElboBwdSeg* __restrict__ segs, int nseg) {
             }
         } else if (s.kind == 1) {
             const long long zhw = (long long)s.Z * s.HW;
+            const bool vec = (s.HW % 4 == 0) && (s.n / 4 < 0x7fffffffLL) &&
+                             ((((uintptr_t)s.a | (uintptr_t)s.b | (uintptr_t)s.gz | (uintptr_t)s.grad) & 15) == 0);
+            if (vec) {
+                const unsigned hw4 = (unsigned)(s.HW / 4), n4 = (unsigned)(s.n / 4), Zu = (unsigned)s.Z;
+                const float4* e4 = reinterpret_cast<const float4*>(s.a);
+                const float4* m4 = reinterpret_cast<const float4*>(s.b);
+                const float4* z4 = reinterpret_cast<const float4*>(s.gz);
+                float4* g4 = reinterpret_cast<float4*>(s.grad);
+                const bool use_gz = s.gz != nullptr && !s.prior;
+                for (unsigned i = (unsigned)tid; i < n4; i += (unsigned)nthreads) {
+                    const unsigned r = i / hw4, c = i - r * hw4;
+                    const unsigned b = r / Zu, z = r - b * Zu;
+                    const size_t im = (size_t)(b * 2 * Zu + z) * hw4 + c, iv = im + (size_t)Zu * hw4;
+                    const float4 mu = m4[im], lv = m4[iv];
+                    float4 dmu = make_float4(go * mu.x, go * mu.y, go * mu.z, go * mu.w);
+                    float4 dlv = make_float4(go * 0.5f * expm1f(lv.x), go * 0.5f * expm1f(lv.y), go * 0.5f * expm1f(lv.z),
+                                             go * 0.5f * expm1f(lv.w));
+                    if (use_gz) {
+                        const float4 gz = z4[i], ep = e4[i];
+                        dmu.x += gz.x; dmu.y += gz.y; dmu.z += gz.z; dmu.w += gz.w;
+                        dlv.x = fmaf(gz.x * 0.5f * expf(0.5f * lv.x), ep.x, dlv.x);
+                        dlv.y = fmaf(gz.y * 0.5f * expf(0.5f * lv.y), ep.y, dlv.y);
+                        dlv.z = fmaf(gz.z * 0.5f * expf(0.5f * lv.z), ep.z, dlv.z);
+                        dlv.w = fmaf(gz.w * 0.5f * expf(0.5f * lv.w), ep.w, dlv.w);
+                    }
+                    if (s.accumulate) {
+                        const float4 a = g4[im], v = g4[iv];
+                        dmu.x += a.x; dmu.y += a.y; dmu.z += a.z; dmu.w += a.w;
+                        dlv.x += v.x; dlv.y += v.y; dlv.z += v.z; dlv.w += v.w;
+                    }
+                    g4[im] = dmu;
+                    g4[iv] = dlv;
+                }
+                continue;
+            }
             for (long long e = tid; e < s.n; e += nthreads) {
                 const long long b = e / zhw, rem = e - b * zhw;
                 const long long im = b * 2 * zhw + rem, iv = im + zhw;

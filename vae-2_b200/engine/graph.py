@@ -156,6 +156,15 @@ class ActArena:
         cls._pools.clear()
         cls.live.clear()
 
+    @classmethod
+    def summary(cls):
+        """{region: GiB held} plus the gradient arenas -- where a step's resident memory sits (bench.py reports it)."""
+        out = {}
+        for (dev, tdt, region), pool in cls._pools.items():
+            out[region] = out.get(region, 0.0) + sum(c.numel() * c.element_size() for c in pool["chunks"]) / 2**30
+        out["grad_arena"] = sum(t.numel() * t.element_size() for t in GradArena._arenas.values()) / 2**30
+        return {k: round(v, 2) for k, v in out.items()}
+
 
 class activation_phase:
     """Context manager used by the wrapper modules: plans recorded inside share activation memory across phases."""
@@ -353,7 +362,7 @@ class Plan:
             r = a.root
             r._nw -= 1
             g = r._grad
-            if r._nw == 0 and g is not None and getattr(g, "_gext", None) is not None:
+            if r._nw == 0 and g is not None and getattr(g, "_gext", None) is not None and not r._pin:
                 self._gfree.append(g._gext)
                 g._gext = None
                 self._gfree.sort()
@@ -377,10 +386,15 @@ class Plan:
             for a in list(o.reads()) + list(o.writes()):
                 acts[id(a)] = a
         for a in acts.values():
-            a._grad, a.grad_written, a._nw = None, False, 0
+            a._grad, a.grad_written, a._nw, a._pin = None, False, 0, False
         for o in self.ops:
             for a in o.writes():
                 a.root._nw += 1
+            if isinstance(o, (InputOp, GroupInputOp)) and o.needs_grad:
+                for a in o.writes():
+                    a.root._pin = True      # read by the eager epilogue AFTER the whole program: never recycled
+            if isinstance(o, OutputOp):
+                o.act.grad()                # written by the eager prologue BEFORE the program: allocated first
         dptr = self.dwp_flat
         any_wgrad = any(o.conv.weight.requires_grad for o in convs)
         if any_wgrad:

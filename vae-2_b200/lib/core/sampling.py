@@ -156,7 +156,8 @@ class KSampleInference:
                 gidx = (torch.arange(fr.shape[0], device=im.device) // F_ % B) * F_ + torch.arange(fr.shape[0], device=im.device) % F_
                 gsel = gf[gidx]
                 out[name + "_ssim"] = ssim(fr, gsel, 255, size_average=False).view(self.K, B, F_)
-                out[name + "_msssim"] = ms_ssim(fr, gsel, 255, size_average=False).view(self.K, B, F_)
+                if min(H, W) > (11 - 1) * 2 ** 2:          # pytorch_msssim's size requirement for the 3 levels used
+                    out[name + "_msssim"] = ms_ssim(fr, gsel, 255, size_average=False).view(self.K, B, F_)
         if self.keep:
             out["xt_predict"], out["x2t_predict"], out["x3t_predict"] = (t.view(self.K, B, *t.shape[1:]) for t in (x1p, x2p, x3p))
         return out

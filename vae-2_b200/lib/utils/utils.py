@@ -73,86 +73,91 @@ def _d_stack():
     return max(1, int(os.environ.get("VAE2_D_STACK", "6")))
 
 
+def _eager_pass(net, srcs, targets, B, phase, grad_wrt):
+    """One stacked discriminator pass evaluated forward AND backward: srcs = [(tensor, channel offset)], targets = LSGAN
+    targets per call.  Returns (sum of the 0.5/B-scaled terms, gradients w.r.t. ``grad_wrt``)."""
+    with _E.activation_phase("scratch:" + phase):
+        out = net.forward_groups(srcs) if len(srcs) > 1 or srcs[0][1] != 0 else net(srcs[0][0])
+        spec = [dict(kind=2, slot=0, a=i, b=None, scale=0.5 / B, target=t, name="%s%d" % (phase, i)) for i, t in enumerate(targets)]
+        v = _E.elbo_terms(spec, 1, [out[i * B:(i + 1) * B] for i in range(len(srcs))])[0][0]
+        g = torch.autograd.grad(v, grad_wrt, allow_unused=True)
+    return v.detach(), g
+
+
+def _add(a, b):
+    return b if a is None else (a if b is None else a + b)
+
+
 class _EagerGanG(torch.autograd.Function):
     """GAN terms of the generator step (reference lib/utils/utils.py:114-119) with the discriminators' parameters
     frozen: d(term)/d(x2t_predict) is computed right away -- the terms are linear in the upstream gradient, so the
-    caller's backward() only scales the two stored gradients."""
+    caller's backward() only scales the two stored gradients.  At most VAE2_D_STACK frames share a stacked pass."""
 
     @staticmethod
     def forward(ctx, wrapper, x2p):
         B = x2p.shape[0]
         L = wrapper.D_model_sequence.clip_length
         nf = x2p.shape[1] // L
-        vals, grads = [], []
-        for which in ("seq", "frm"):
-            with torch.enable_grad():
-                xd = x2p.detach().requires_grad_(True)
-                with _E.activation_phase("scratch:G" + which), _frozen([wrapper.D_model_sequence, wrapper.D_model_frame], True):
-                    if which == "seq":
-                        outs = [wrapper.D_model_sequence(xd)]
-                    elif _stack_D() and hasattr(wrapper.D_model_frame, "forward_groups"):
-                        allf = wrapper.D_model_frame.forward_groups([(xd, 3 * f) for f in range(nf)])
-                        outs = [allf[f * B:(f + 1) * B] for f in range(nf)]
-                    else:
-                        outs = [wrapper.D_model_frame(xd[:, f * 3: f * 3 + 3, :, :]) for f in range(nf)]
-                    spec = [dict(kind=2, slot=0, a=i, b=None, scale=0.5 / B, target=1.0, name="d_%s%d" % (which, i))
-                            for i in range(len(outs))]
-                    v = _E.elbo_terms(spec, 1, outs)[0][0]
-                    (g,) = torch.autograd.grad(v, xd)
-            vals.append(v.detach())
-            grads.append(g)
-        ctx.save_for_backward(*grads)
-        return vals[0], vals[1]
+        with torch.enable_grad(), _frozen([wrapper.D_model_sequence, wrapper.D_model_frame], True):
+            xd = x2p.detach().requires_grad_(True)
+            v_seq, (g_seq,) = _eager_pass(wrapper.D_model_sequence, [(xd, 0)], [1.0], B, "Gseq", [xd])
+            per, v_frm, g_frm = min(nf, _d_stack()), None, None
+            for f0 in range(0, nf, per):
+                fr = list(range(f0, min(nf, f0 + per)))
+                if per == nf:
+                    srcs = [(xd, 3 * f) for f in fr]                  # one plan reads all windows of x2t_predict
+                else:                                                 # chunks replay ONE plan: windows cut here
+                    srcs = [(xd[:, 3 * f:3 * f + 3].contiguous(), 0) for f in fr]
+                v, (g,) = _eager_pass(wrapper.D_model_frame, srcs, [1.0] * len(fr), B, "Gfrm", [xd])
+                v_frm, g_frm = _add(v_frm, v), _add(g_frm, g)
+        ctx.save_for_backward(g_seq, g_frm)
+        return v_seq, v_frm
 
     @staticmethod
-    def backward(ctx, g_seq, g_frm):
+    def backward(ctx, up_seq, up_frm):
         a, b = ctx.saved_tensors
         out = None
-        for g, t in ((g_seq, a), (g_frm, b)):
-            if g is not None:
-                out = g * t if out is None else out + g * t
+        for up, t in ((up_seq, a), (up_frm, b)):
+            if up is not None:
+                out = _add(out, up * t)
         return None, out
 
 
 class _EagerGanD(torch.autograd.Function):
     """Discriminator step (reference lib/utils/utils.py:259-276): every (stacked) pass runs forward, its LSGAN terms
-    and backward at once; parameter gradients for a unit upstream gradient are kept (a few MB) and scaled in backward()."""
+    and backward at once; parameter gradients for a unit upstream gradient are kept (a few MB) and scaled in backward().
+    Calls are stacked in the reference's order (seq: real, fake; frames: real_f, fake_f, ...), at most VAE2_D_STACK per
+    pass, so BN running statistics see the same update sequence."""
 
     @staticmethod
     def forward(ctx, wrapper, real, fake, n_seq, *params):
         B = real.shape[0]
         L = wrapper.D_model_sequence.clip_length
         nf = real.shape[1] // L
-        seq_p, frm_p = params[:n_seq], params[n_seq:]
-        half = lambda t: dict(kind=2, slot=0, b=None, scale=0.5 / B, target=t)
+        seq_p = [p for p in params[:n_seq] if p.requires_grad]
+        frm_p = [p for p in params[n_seq:] if p.requires_grad]
+        stack = _d_stack()
         with torch.enable_grad():
-            with _E.activation_phase("scratch:Dseq"):
-                seq = wrapper.D_model_sequence.forward_groups([(real, 0), (fake, 0)])
-                v_seq = _E.elbo_terms([dict(half(1.0), a=0, name="d_seq_real"), dict(half(0.0), a=1, name="d_seq_fake")], 1,
-                                      [seq[:B], seq[B:]])[0][0]
-                g_seq = torch.autograd.grad(v_seq, [p for p in seq_p if p.requires_grad], allow_unused=True)
-            per = max(1, _d_stack() // 2)                    # frames per stacked pass (each frame = real + fake)
-            v_frm, g_frm = None, None
-            for f0 in range(0, nf, per):
-                fr = range(f0, min(nf, f0 + per))
-                with _E.activation_phase("scratch:Dfrm"):
-                    # channel windows are cut here (offset 0 in the plan) so that every chunk replays ONE plan
-                    srcs = [(t[:, 3 * f:3 * f + 3].contiguous(), 0) for f in fr for t in (real, fake)]
-                    out = wrapper.D_model_frame.forward_groups(srcs)
-                    spec = [dict(half(1.0 if i % 2 == 0 else 0.0), a=i, name="d_frm_%s" % ("real" if i % 2 == 0 else "fake"))
-                            for i in range(len(srcs))]
-                    v = _E.elbo_terms(spec, 1, [out[i * B:(i + 1) * B] for i in range(len(srcs))])[0][0]
-                    g = torch.autograd.grad(v, [p for p in frm_p if p.requires_grad], allow_unused=True)
-                v_frm = v.detach() if v_frm is None else v_frm + v.detach()
-                g_frm = list(g) if g_frm is None else [a if b is None else (b if a is None else a + b) for a, b in zip(g_frm, g)]
+            calls = [(real, 1.0), (fake, 0.0)]
+            v_seq, g_seq = None, [None] * len(seq_p)
+            for c0 in range(0, 2, min(2, stack)):
+                ch = calls[c0:c0 + min(2, stack)]
+                v, g = _eager_pass(wrapper.D_model_sequence, [(t, 0) for t, _ in ch], [tg for _, tg in ch], B, "Dseq", seq_p)
+                v_seq, g_seq = _add(v_seq, v), [_add(a, b) for a, b in zip(g_seq, g)]
+            # frame calls: windows are cut here (offset 0 in the plan) so that every chunk replays ONE plan
+            calls = [(t[:, 3 * f:3 * f + 3].contiguous(), tg) for f in range(nf) for t, tg in ((real, 1.0), (fake, 0.0))]
+            v_frm, g_frm = None, [None] * len(frm_p)
+            for c0 in range(0, len(calls), stack):
+                ch = calls[c0:c0 + stack]
+                v, g = _eager_pass(wrapper.D_model_frame, [(t, 0) for t, _ in ch], [tg for _, tg in ch], B, "Dfrm", frm_p)
+                v_frm, g_frm = _add(v_frm, v), [_add(a, b) for a, b in zip(g_frm, g)]
         ctx.n_seq, ctx.req = n_seq, [p.requires_grad for p in params]
         ctx.grads = list(g_seq) + list(g_frm)
-        return v_seq.detach(), v_frm
+        return v_seq, v_frm
 
     @staticmethod
     def backward(ctx, up_seq, up_frm):
         out, it = [], iter(ctx.grads)
-        n_seq_req = sum(ctx.req[:ctx.n_seq])
         for i, need in enumerate(ctx.req):
             if not need:
                 out.append(None)
