@@ -353,6 +353,9 @@ def main():
     args = ap.parse_args()
 
     from config import load_config
+    # discriminator calls stacked per pass: all of them at the small frame sizes, one at a time at 1024x2048 / W48 where a
+    # stacked pass would not fit beside the generator networks (engine scratch region)
+    os.environ.setdefault("VAE2_D_STACK", "1" if args.workload in ("w18_1024x2048", "w48_473x473", "w48_520x520") else "6")
     yaml_name, H, W, B, flop_per_sample = WORKLOADS[args.workload]
     if isinstance(B, dict):      # largest per-GPU batch that fits 180 GB with this precision's activation footprint
         B = B[args.precision]

@@ -67,7 +67,7 @@ def test_image_metrics_match_oracle_and_closed_forms():
     a, b = 60.0, 200.0
     ca, cb = torch.full((1, 3, 40, 50), a, device=DEV), torch.full((1, 3, 40, 50), b, device=DEV)
     C1 = (0.01 * 255) ** 2
-    assert abs(float(S.ssim(ca, cb)) - (2 * a * b + C1) / (a * a + b * b + C1)) < 1e-5
+    assert abs(float(S.ssim(ca, cb)) - (2 * a * b + C1) / (a * a + b * b + C1)) < 1e-4      # fp32 E[x^2]-mu^2 at 200^2
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

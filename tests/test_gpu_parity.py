@@ -163,7 +163,7 @@ def test_g_and_d_step_match_reference_golden_fp32(name, wmode):
     # 2e-6 -- so the yardstick is the worst term of the case, not each term's own luck)
     ltol = max(FP32_TOL, 3.0 * float(np.max(np.abs(gold["g_losses"] - gold["g_losses64"]) / np.abs(gold["g_losses64"]))))
     import os as _os
-    log_err("golden_fp32_" + name + ("_fp32tc" if _os.environ.get("VAE2_FP32_TC") == "1" else ""),
+    log_err("golden_fp32_" + name + {"0": "_cudacores", "1": "", "all": "_tcall"}.get(_os.environ.get("VAE2_FP32_TC", "1"), ""),
             losses_vs_ref64=(np.abs(got - gold["g_losses64"]) / np.abs(gold["g_losses64"])).tolist(),
             losses_vs_ref32=(np.abs(got - gold["g_losses"]) / np.abs(gold["g_losses"])).tolist(), ltol=ltol,
             acts_vs_ref64={k: rel_err(a, gold[k + "64"]) for a, k in ((x1p, "x1p"), (x2p, "x2p"), (x3p, "x3p"))},

@@ -203,7 +203,7 @@ def test_bf16_module_fwd_bwd_vs_oracle(kind):
     backward, up-sampling fuse backward.  Reference = the fp64 oracle.  Bounds: output <= 1e-2 outright; gradients against
     the oracle's own bf16-storage noise model (O.bf16_storage: ReLU masks flip where |pre-activation| is below the 4e-3
     storage noise, which alone costs a few % in L2 -- measured 4-6e-2 on dx for both): error <= 2x the emulated error
-    + 5e-3, cosine >= 0.995."""
+    + 5e-3, cosine >= min(0.995, emulated - 0.003)."""
     E.set_precision("bf16")
     mod, shapes, fn = _bf16_module_case(kind)
     sd = mod.state_dict()
@@ -234,7 +234,7 @@ def test_bf16_module_fwd_bwd_vs_oracle(kind):
     sum((y * g.to(DEV)).sum() for y, g in zip(ys, gos)).backward()
     e_out = max(rel_err(a, b) for a, b in zip(ys, ys_r))
     e_dx, em_dx = max(rel_err(a.grad, b.grad) for a, b in zip(xd, xr)), max(rel_err(a.grad, b.grad) for a, b in zip(xe, xr))
-    eg, em, cs = [], [], []
+    eg, em, cs, cem = [], [], [], []
     for k, p in mod.named_parameters():
         r = sdr["b." + k].grad
         if r is None or float(r.norm()) < 1e-7 or k.endswith("downsample.0.bias"):
@@ -242,13 +242,14 @@ def test_bf16_module_fwd_bwd_vs_oracle(kind):
         eg.append(rel_err(p.grad, r))
         em.append(rel_err(sde["b." + k].grad, r))
         cs.append(_cos(p.grad, r))
-    eg, em, cs = np.array(eg), np.array(em), np.array(cs)
+        cem.append(_cos(sde["b." + k].grad, r))
+    eg, em, cs, cem = np.array(eg), np.array(em), np.array(cs), np.array(cem)
     log_err("bf16_module_" + kind, out=e_out, dx=e_dx, emulated_dx=em_dx, n=len(eg), grads_median=np.median(eg),
             emulated_grads_median=np.median(em), grads_max=eg.max(), emulated_grads_max=em.max(), cos_min=cs.min())
     assert e_out < 1e-2, e_out
     assert e_dx <= 2.0 * em_dx + 5e-3, (e_dx, em_dx)
     assert np.median(eg) <= 2.0 * np.median(em) + 5e-3 and eg.max() <= 2.0 * em.max() + 1e-2, (np.median(eg), np.median(em), eg.max(), em.max())
-    assert cs.min() > 0.995, cs.min()
+    assert cs.min() > min(0.995, cem.min() - 0.003), (cs.min(), cem.min())
 
 
 def _oracle_g_grads(sd, cfg, inputs, dtype, bf16_storage=False):

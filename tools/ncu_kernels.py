@@ -68,6 +68,18 @@ for name, H, W, Cin, Cout, k, s_ in CONVS:
         twice("wgrad " + name, lambda: N.call.vae2_conv2d_wgrad_tc(p(x), p(dy), p(dwp), p(ws), C.byref(g), st))
     else:
         twice("wgrad " + name, lambda: N.call.vae2_conv2d_wgrad(p(x), p(dy), p(dwp), code, C.byref(g), 0, st))
+    if prec == "fp32" and max(Cip, Cop) >= 40 and N.lib().vae2_conv2d_tf32_supported(C.byref(g)):
+        # the fp32 path's tensor-core route for the >= 40-lane layers: exact 3-way bf16 split, split accumulators
+        Nf, Kf, NfT, KfT = N.tf32_dims(g)
+        wsrc = torch.randn(Cout, Cin, k, k, device=dev) * 0.05
+        wf = torch.zeros(3 * k * k * Nf * Kf, dtype=torch.bfloat16, device=dev)
+        wb = torch.zeros(3 * k * k * NfT * KfT, dtype=torch.bfloat16, device=dev)
+        d = (N.Tf32PackDesc * 1)()
+        d[0] = N.Tf32PackDesc(w=p(wsrc), fwd=p(wf), bwd=p(wb), Cout=Cout, Cin=Cin, k=k, Nf=Nf, Kf=Kf, NfT=NfT, KfT=KfT)
+        tab = torch.frombuffer(bytearray(bytes(d)), dtype=torch.uint8).to(dev)
+        N.call.vae2_pack_weights_tf32(tab.data_ptr(), 1, st)
+        twice("f32x3 fwd " + name, lambda: N.call.vae2_conv2d_fwd(p(x), p(wf), None, p(y), 0, C.byref(g), 2, st))
+        twice("f32x3 dgrad " + name, lambda: N.call.vae2_conv2d_dgrad(p(dy), p(wb), p(dx), 0, C.byref(g), 0, 2, st))
     del x, y, dy, dx, w, dwp
     torch.cuda.empty_cache()
 

@@ -29,17 +29,22 @@ struct FuseArgs {
 template <typename T>
 __global__ void __launch_bounds__(256)
 fuse_sum_kernel(FuseArgs a, T* __restrict__ out, int B, int H, int W, int Cp, int ld_out, int relu) {
+    // one image row per blockIdx.y step, (pixel, lane vector) pairs along x: the per-element index math is 32-bit and
+    // the row's vertical interpolation coefficients are computed once per thread and row (ncu r2a: the flat 64-bit
+    // div/mod version was issue-bound at 72 % of the issue slots and 12 % of HBM)
     constexpr int V = Vec<T>::N;
-    const int lanes = Cp / V;
-    const long long total = (long long)B * H * W * lanes;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / lanes;
-        const int c0 = (int)(i - p * lanes) * V;
-        const int x = (int)(p % W);
-        const long long t = p / W;
-        const int y = (int)(t % H);
-        const int b = (int)(t / H);
+    const unsigned lanes = (unsigned)(Cp / V);
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)W * lanes) return;
+    const int x = (int)(idx / lanes);
+    const int c0 = (int)(idx - (unsigned)x * lanes) * V;
+    int x0s[MAX_SRC], x1s[MAX_SRC];
+    float lxs[MAX_SRC];
+#pragma unroll
+    for (int j = 0; j < MAX_SRC; ++j) bilinear_src(x, a.sw[j], a.W[j], x0s[j], x1s[j], lxs[j]);
+    for (int row = blockIdx.y; row < B * H; row += gridDim.y) {
+        const int b = row / H, y = row - b * H;
+        const long long p = (long long)row * W + x;
         float acc[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -52,10 +57,11 @@ fuse_sum_kernel(FuseArgs a, T* __restrict__ out, int B, int H, int W, int Cp, in
 #pragma unroll
                 for (int k = 0; k < V; ++k) acc[k] += v.v[k];
             } else {
-                int y0, y1, x0, x1;
-                float ly, lx;
+                int y0, y1;
+                float ly;
                 bilinear_src(y, a.sh[j], a.H[j], y0, y1, ly);
-                bilinear_src(x, a.sw[j], a.W[j], x0, x1, lx);
+                const int x0 = x0s[j], x1 = x1s[j];
+                const float lx = lxs[j];
                 const long long base = (long long)b * a.H[j];
                 const Vec<T> v00 = Vec<T>::load(s + ((base + y0) * a.W[j] + x0) * a.ld[j] + c0);
                 const Vec<T> v01 = Vec<T>::load(s + ((base + y0) * a.W[j] + x1) * a.ld[j] + c0);
@@ -120,22 +126,23 @@ fuse_bwd_up_kernel(const T* __restrict__ g, const T* __restrict__ out, T* __rest
                    int Hs, int Ws, int Cp, int ld_g, int ld_out, int ld_gsrc, float sh, float sw, int relu,
                    int accumulate) {
     constexpr int V = Vec<T>::N;
-    const int lanes = Cp / V;
-    const long long total = (long long)B * Hs * Ws * lanes;
+    const unsigned lanes = (unsigned)(Cp / V);
     const float rh = 1.f / sh, rw = 1.f / sw;   // output pixels per source pixel
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / lanes;
-        const int c0 = (int)(i - p * lanes) * V;
-        const int xs = (int)(p % Ws);
-        const long long t = p / Ws;
-        const int ys = (int)(t % Hs);
-        const int b = (int)(t / Hs);
-        // candidate output rows/cols whose source coordinate can fall in (ys-1, ys+1)
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)Ws * lanes) return;
+    const int xs = (int)(idx / lanes);
+    const int c0 = (int)(idx - (unsigned)xs * lanes) * V;
+    int ox_lo = (int)floorf((xs - 0.5f) * rw - 0.5f) - 1, ox_hi = (int)ceilf((xs + 1.5f) * rw - 0.5f) + 1;
+    ox_lo = max(ox_lo, 0); ox_hi = min(ox_hi, W - 1);
+    // trim the conservative column range to the columns that really touch xs (their weights do not depend on the row)
+    while (ox_lo <= ox_hi) { int x0, x1; float lx; bilinear_src(ox_lo, sw, Ws, x0, x1, lx); if (x0 == xs || x1 == xs) break; ++ox_lo; }
+    while (ox_hi >= ox_lo) { int x0, x1; float lx; bilinear_src(ox_hi, sw, Ws, x0, x1, lx); if (x0 == xs || x1 == xs) break; --ox_hi; }
+    for (int row = blockIdx.y; row < B * Hs; row += gridDim.y) {
+        const int b = row / Hs, ys = row - b * Hs;
+        const long long p = (long long)row * Ws + xs;
+        // candidate output rows whose source coordinate can fall in (ys-1, ys+1)
         int oy_lo = (int)floorf((ys - 0.5f) * rh - 0.5f) - 1, oy_hi = (int)ceilf((ys + 1.5f) * rh - 0.5f) + 1;
-        int ox_lo = (int)floorf((xs - 0.5f) * rw - 0.5f) - 1, ox_hi = (int)ceilf((xs + 1.5f) * rw - 0.5f) + 1;
         oy_lo = max(oy_lo, 0); oy_hi = min(oy_hi, H - 1);
-        ox_lo = max(ox_lo, 0); ox_hi = min(ox_hi, W - 1);
         float acc[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -193,12 +200,17 @@ int fuse_sum(const FuseSrc* srcs, int nsrc, void* out, int dtype, int B, int H, 
         a.sw[j] = (float)srcs[k].W / (float)W;
         if (srcs[k].ld % V) return VAE2_ERR_ARG;
     }
-    const long long work = (long long)B * H * W * (Cp / V);
-    const int grid = stream_grid(work, 256 * 2);
+    const int per_row = W * (Cp / V);
+    const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32 * 32);
+    const long long rows = (long long)B * H;
+    const int gx = (per_row + threads - 1) / threads;
+    long long gy = (16LL * kNumSMs * 256 / threads + gx - 1) / gx;      // ~16 CTAs per SM; threads walk rows gy apart
+    if (gy > rows) gy = rows;
+    dim3 grid(gx, (unsigned)(gy < 1 ? 1 : gy));
     if (dtype == VAE2_DT_F32)
-        fuse_sum_kernel<float><<<grid, 256, 0, st>>>(a, (float*)out, B, H, W, Cp, ld_out, relu);
+        fuse_sum_kernel<float><<<grid, threads, 0, st>>>(a, (float*)out, B, H, W, Cp, ld_out, relu);
     else
-        fuse_sum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, (__nv_bfloat16*)out, B, H, W, Cp, ld_out, relu);
+        fuse_sum_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(a, (__nv_bfloat16*)out, B, H, W, Cp, ld_out, relu);
     return check_launch();
 }
 
@@ -226,12 +238,17 @@ int fuse_bwd_up(const void* g, const void* out, void* gsrc, int dtype, int B, in
     const int V = dtype == VAE2_DT_F32 ? 4 : 8;
     if (Cp % V || ld_g % V || ld_gsrc % V) return VAE2_ERR_ARG;
     const float sh = (float)Hs / (float)H, sw = (float)Ws / (float)W;
-    const long long work = (long long)B * Hs * Ws * (Cp / V);
-    const int grid = stream_grid(work, 256);
+    const int per_row = Ws * (Cp / V);
+    const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32 * 32);
+    const long long rows = (long long)B * Hs;
+    const int gx = (per_row + threads - 1) / threads;
+    long long gy = (16LL * kNumSMs * 256 / threads + gx - 1) / gx;
+    if (gy > rows) gy = rows;
+    dim3 grid(gx, (unsigned)(gy < 1 ? 1 : gy));
     if (dtype == VAE2_DT_F32)
-        fuse_bwd_up_kernel<float><<<grid, 256, 0, st>>>((const float*)g, (const float*)out, (float*)gsrc, B, H, W, Hs, Ws, Cp, ld_g, ld_out, ld_gsrc, sh, sw, relu, accumulate);
+        fuse_bwd_up_kernel<float><<<grid, threads, 0, st>>>((const float*)g, (const float*)out, (float*)gsrc, B, H, W, Hs, Ws, Cp, ld_g, ld_out, ld_gsrc, sh, sw, relu, accumulate);
     else
-        fuse_bwd_up_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)gsrc, B, H, W, Hs, Ws, Cp, ld_g, ld_out, ld_gsrc, sh, sw, relu, accumulate);
+        fuse_bwd_up_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)gsrc, B, H, W, Hs, Ws, Cp, ld_g, ld_out, ld_gsrc, sh, sw, relu, accumulate);
     return check_launch();
 }
 

@@ -315,7 +315,12 @@ class Plan:
         self.taps = {}                        # name -> Act at module boundaries (debug / parity tests: Act.to_nchw)
         self.concat_roots = []
         self.use_tc = os.environ.get("VAE2_DISABLE_TC", "0") != "1"
-        self.fp32_tc = os.environ.get("VAE2_FP32_TC", "0") == "1"
+        # fp32 storage, forward / data-gradient GEMMs of the >= 40-lane layers on tcgen05 through the exact 3-way bf16 split
+        # with split accumulators (csrc/conv_f32x3.cu): measured MORE accurate than the CUDA-core FMA loops inside the
+        # full nets (profiles/r2_parity_errors.jsonl: x2p 1.6e-6 vs 2.8e-6 on tiny, 7.2e-5 vs 1.06e-4 on W48).
+        # "0" = CUDA cores only, "all" = every supported conv (the narrow 20/36-lane layers are faster on conv_direct).
+        self.fp32_tc = os.environ.get("VAE2_FP32_TC", "1")
+        self.fp32_tc_min_lanes = int(os.environ.get("VAE2_FP32_TC_MIN_LANES", "40"))
         self.use_tc_wgrad = os.environ.get("VAE2_DISABLE_TC_WGRAD", "0") != "1"
         self.graph_fwd = self.graph_bwd = None
         self.n_launch_fwd = self.n_launch_bwd = 0
@@ -446,7 +451,8 @@ class Plan:
                 o.engine = 1 if N.lib().vae2_conv2d_tc_supported(C.byref(g)) else 0
         # fp32 storage with the fwd/dgrad GEMMs on tensor cores through the exact 3-way bf16 split (opt-in:
         # its truncating fp32 accumulation is ~1e-6..1e-5 per conv)
-        x3 = [o for o in convs if self.prec.code == 0 and self.fp32_tc and dev.type == "cuda"
+        x3 = [o for o in convs if self.prec.code == 0 and self.fp32_tc not in ("0", "") and dev.type == "cuda"
+              and (self.fp32_tc == "all" or max(o.x.root_cp(), o.y.Cp) >= self.fp32_tc_min_lanes)
               and N.lib().vae2_conv2d_tf32_supported(C.byref(o._geom()))]
         tot3f = tot3b = 0
         for o in x3:
