@@ -155,6 +155,23 @@ int vae2_bn_bwd_fused(const void* g, const void* a, const void* y, void* dy, voi
                       float* dbeta, int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres,
                       vae2_stream_t stream);
 
+/* The same with `groups` statistics groups stacked along the batch axis (the reference calls a discriminator once per
+ * frame / per real-fake input, lib/utils/utils.py:114-119, 259-267; here those calls are one stacked pass): group g covers
+ * npix pixels, tensors of consecutive groups follow each other in memory, statistic outputs (mean, invstd, scale, shift,
+ * c1, c2) of group g sit g*stat_stride floats after group 0's.  Each group is normalised with its own batch statistics;
+ * running statistics receive the `groups` momentum updates in group order, num_batches_tracked advances by `groups`,
+ * d(gamma) / d(beta) are summed over the groups -- exactly what `groups` sequential module calls produce. */
+int vae2_bn_fwd_fused_groups(const void* y, const void* res, void* out, float* partials, int dtype, int64_t npix, int C,
+                             int Cp, int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                             float eps, float* mean, float* invstd, float* scale, float* shift, int relu, int groups,
+                             int stat_stride, vae2_stream_t stream);
+int vae2_bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                             int64_t npix, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres,
+                             const float* mean, const float* invstd, const float* scale, const float* shift, float* dgamma,
+                             float* dbeta, int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres,
+                             int groups, int stat_stride, vae2_stream_t stream);
+
 /* ---- branch fusion / upsampling: HighResolutionModule.forward enc_hrnet.py:233-248, :833-839 -- */
 typedef struct { const void* ptr; int32_t H, W, ld; } vae2_fuse_src;        /* HOST array */
 typedef struct { void* ptr; int32_t ld, accumulate; } vae2_fuse_dst;         /* HOST array */

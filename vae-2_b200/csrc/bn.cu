@@ -38,13 +38,16 @@ template <typename T>
 struct Lay {
     static constexpr int V = Vec<T>::N;
     int lanes, R, lane, r;
+    int bid, nb;      // this CTA's index / the CTA count WITHIN ITS STATISTICS GROUP (the whole grid when there is one group)
     bool active;
-    __device__ __forceinline__ explicit Lay(int Cp) {
+    __device__ __forceinline__ explicit Lay(int Cp, int bid_ = -1, int nb_ = 0) {
         lanes = Cp / V;
         R = blockDim.x / lanes;
         lane = threadIdx.x % lanes;
         r = threadIdx.x / lanes;
         active = r < R;
+        bid = bid_ < 0 ? (int)blockIdx.x : bid_;
+        nb = bid_ < 0 ? (int)gridDim.x : nb_;
     }
 };
 
@@ -78,8 +81,8 @@ __device__ __forceinline__ void stream_pixels(float* sm, const Lay<T>& L, long l
     constexpr int V = Vec<T>::N;
     constexpr int D = kPipeSlots / NTENS;
     if (!L.active) return;
-    const long long stride = (long long)gridDim.x * L.R;
-    const long long first = (long long)blockIdx.x * L.R + L.r;
+    const long long stride = (long long)L.nb * L.R;
+    const long long first = (long long)L.bid * L.R + L.r;
     const long long n = first < P ? (P - first + stride - 1) / stride : 0;
     const int c0 = L.lane * V;
     uint4* mine = reinterpret_cast<uint4*>(sm) + threadIdx.x;     // slot s, tensor t: mine[(s*NTENS + t) * BN_THREADS]
@@ -174,9 +177,9 @@ __device__ __forceinline__ void cta_merge_welford(float* sm, int lanes, int R, i
 
 template <typename T>
 __device__ __forceinline__ void stats_to_partials(const T* __restrict__ y, float* __restrict__ partials, long long P,
-                                                  int Cp, int ld, float* sm) {
+                                                  int Cp, int ld, float* sm, int bid = -1, int nb = 0) {
     constexpr int V = Vec<T>::N;
-    const Lay<T> L(Cp);
+    const Lay<T> L(Cp, bid, nb);
     float mean[V], m2[V], n;
     stats_pass<T>(y, P, ld, L, sm, mean, m2, n);
     cta_merge_welford<V>(sm, L.lanes, L.R, L.lane, L.r, L.active, mean, m2, n);
@@ -383,13 +386,13 @@ __device__ __forceinline__ void bwd_reduce_to_partials_t(const T* __restrict__ g
                                                        long long P, int Cp, int ld_g, int ld_a, int ld_y,
                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                                        float* sm, const float* __restrict__ scale = nullptr,
-                                                       const float* __restrict__ shift = nullptr) {
+                                                       const float* __restrict__ shift = nullptr, int bid = -1, int nb = 0) {
     constexpr int relu = RELU;
     // relu: 0 none | 1 mask = [a > 0] read from the stored activation | 2 mask recomputed as
     // [fma(y, scale, shift) > 0] -- the very expression the forward pass rounded into `a` (no residual), so the
     // activation is not read at all
     constexpr int V = Vec<T>::N;
-    const Lay<T> L(Cp);
+    const Lay<T> L(Cp, bid, nb);
     // s2 accumulates sum(dyb * (y - mu)); the factor invstd is applied once at the end.  Centring on mu keeps
     // the sum free of the cancellation a raw sum(dyb * y) would have.
     float s1[V], s2[V], mu[V], sc[V], sh[V];
@@ -609,6 +612,12 @@ struct BnFwdArgs {
     long long* nbt;
     float momentum, eps;
     float *mean, *invstd, *scale, *shift;
+    // statistics groups (stacked calls of the reference along the batch axis): group g covers P pixels starting
+    // gs_* elements after group g-1, its statistics outputs sit stat_stride floats after the previous group's.  The
+    // grid is G x (gridDim.x / G) CTAs; running statistics take the G momentum updates in group order.
+    int G;
+    long long gs_y, gs_res, gs_out;
+    int stat_stride;
 };
 
 template <typename T>
@@ -617,85 +626,94 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
     extern __shared__ __align__(16) float sm[];
     cg::grid_group grid = cg::this_grid();
     prof_mark(A.prof, 0);
+    const int nbpg = gridDim.x / A.G;                 // CTAs per statistics group
+    const int grp = blockIdx.x / nbpg, lb = blockIdx.x - grp * nbpg;
     // parameters of the channel this CTA will finalize: cold in HBM, so fetched under the statistics pass
     float gm0 = 0.f, bt0 = 0.f, rm00 = 0.f, rv00 = 0.f;
     if (threadIdx.x == 0 && (int)blockIdx.x < A.C) {
         gm0 = A.gamma[blockIdx.x]; bt0 = A.beta[blockIdx.x];
         if (A.running_mean != nullptr) { rm00 = A.running_mean[blockIdx.x]; rv00 = A.running_var[blockIdx.x]; }
     }
-    stats_to_partials<T>((const T*)A.y, A.partials, A.P, A.Cp, A.ld_y, sm);
+    stats_to_partials<T>((const T*)A.y + grp * A.gs_y, A.partials, A.P, A.Cp, A.ld_y, sm, lb, nbpg);
     prof_mark(A.prof, 1);
     grid.sync();
     prof_mark(A.prof, 2);
     // One CTA per channel: every thread fetches <= 3 partials at once (one L2 round trip for the whole merge),
-    // warp butterflies, then the 8 warp results meet in shared memory.
+    // warp butterflies, then the 8 warp results meet in shared memory.  Groups are finalized one after the other by
+    // the same CTA so that the running statistics see their momentum updates in the reference's call order.
     for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {
-        const int n_parts = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int n_parts = nbpg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         float gm = gm0, bt = bt0, rm0 = rm00, rv0 = rv00;      // first channel: fetched before the statistics pass
         if (threadIdx.x == 0 && c < A.C && c != blockIdx.x) {
             gm = A.gamma[c]; bt = A.beta[c];
             if (A.running_mean != nullptr) { rm0 = A.running_mean[c]; rv0 = A.running_var[c]; }
         }
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        if (c < A.C) {
-            float a[3][3];
+        for (int gq = 0; gq < A.G; ++gq) {
+            const float* parts = A.partials + (long long)gq * nbpg * 3 * A.Cp;
+            float n = 0.f, mean = 0.f, m2 = 0.f;
+            if (c < A.C) {
+                float a[3][3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int k = threadIdx.x + j * BN_THREADS;
-                const bool valid = k < n_parts;
-                const float* p = A.partials + (long long)(valid ? k : 0) * 3 * A.Cp;
-                a[j][0] = valid ? __ldcg(p + c) : 0.f;
-                a[j][1] = __ldcg(p + A.Cp + c);
-                a[j][2] = __ldcg(p + 2 * A.Cp + c);
-            }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) chan_merge(n, mean, m2, a[j][0], a[j][1], a[j][2]);
-            warp_tree_merge(n, mean, m2);
-        }
-        __syncthreads();
-        if (lane == 0) { sm[warp * 3] = n; sm[warp * 3 + 1] = mean; sm[warp * 3 + 2] = m2; }
-        __syncthreads();
-        if (warp == 0) {
-            const int w = lane & 7;
-            n = sm[w * 3]; mean = sm[w * 3 + 1]; m2 = sm[w * 3 + 2];
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {      // butterfly over the 8 warp results (lanes 8.. mirror lanes 0..7)
-                const float nb = __shfl_xor_sync(0xffffffffu, n, o);
-                const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
-                const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
-                const float nn = n + nb;
-                if (nn > 0.f) {
-                    const float d = mb - mean;
-                    const float f = nb / nn;
-                    mean = (nb > 0.f && n > 0.f) ? mean + d * f : (nb > 0.f ? mb : mean);
-                    m2 = m2 + m2b + ((nb > 0.f && n > 0.f) ? d * d * n * f : 0.f);
+                for (int j = 0; j < 3; ++j) {
+                    const int k = threadIdx.x + j * BN_THREADS;
+                    const bool valid = k < n_parts;
+                    const float* p = parts + (long long)(valid ? k : 0) * 3 * A.Cp;
+                    a[j][0] = valid ? __ldcg(p + c) : 0.f;
+                    a[j][1] = __ldcg(p + A.Cp + c);
+                    a[j][2] = __ldcg(p + 2 * A.Cp + c);
                 }
-                n = nn;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) chan_merge(n, mean, m2, a[j][0], a[j][1], a[j][2]);
+                warp_tree_merge(n, mean, m2);
             }
-            if (lane == 0) {
-                if (c >= A.C) {
-                    A.mean[c] = 0.f; A.invstd[c] = 0.f; A.scale[c] = 0.f; A.shift[c] = 0.f;
-                } else {
-                    const float var = m2 / n;
-                    const float invstd = rsqrtf(var + A.eps);
-                    const float sc = gm * invstd;
-                    A.mean[c] = mean; A.invstd[c] = invstd; A.scale[c] = sc; A.shift[c] = bt - mean * sc;
-                    if (A.running_mean != nullptr) {
-                        const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
-                        A.running_mean[c] = (1.f - A.momentum) * rm0 + A.momentum * mean;
-                        A.running_var[c] = (1.f - A.momentum) * rv0 + A.momentum * unbiased;
+            __syncthreads();
+            if (lane == 0) { sm[warp * 3] = n; sm[warp * 3 + 1] = mean; sm[warp * 3 + 2] = m2; }
+            __syncthreads();
+            if (warp == 0) {
+                const int w = lane & 7;
+                n = sm[w * 3]; mean = sm[w * 3 + 1]; m2 = sm[w * 3 + 2];
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {      // butterfly over the 8 warp results (lanes 8.. mirror lanes 0..7)
+                    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+                    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+                    const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+                    const float nn = n + nb;
+                    if (nn > 0.f) {
+                        const float d = mb - mean;
+                        const float f = nb / nn;
+                        mean = (nb > 0.f && n > 0.f) ? mean + d * f : (nb > 0.f ? mb : mean);
+                        m2 = m2 + m2b + ((nb > 0.f && n > 0.f) ? d * d * n * f : 0.f);
+                    }
+                    n = nn;
+                }
+                if (lane == 0) {
+                    const int so = gq * A.stat_stride + c;
+                    if (c >= A.C) {
+                        A.mean[so] = 0.f; A.invstd[so] = 0.f; A.scale[so] = 0.f; A.shift[so] = 0.f;
+                    } else {
+                        const float var = m2 / n;
+                        const float invstd = rsqrtf(var + A.eps);
+                        const float sc = gm * invstd;
+                        A.mean[so] = mean; A.invstd[so] = invstd; A.scale[so] = sc; A.shift[so] = bt - mean * sc;
+                        if (A.running_mean != nullptr) {
+                            const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
+                            rm0 = (1.f - A.momentum) * rm0 + A.momentum * mean;
+                            rv0 = (1.f - A.momentum) * rv0 + A.momentum * unbiased;
+                            if (gq == A.G - 1) { A.running_mean[c] = rm0; A.running_var[c] = rv0; }
+                        }
                     }
                 }
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && A.nbt != nullptr) *A.nbt += 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.nbt != nullptr) *A.nbt += A.G;
     prof_mark(A.prof, 3);
     grid.sync();
     prof_mark(A.prof, 4);
-    const Lay<T> L(A.Cp);
-    apply_pass<T>((const T*)A.y, (const T*)A.res, (T*)A.out, A.P, A.ld_y, A.ld_res, A.ld_out, A.scale, A.shift, A.relu, L,
-                  sm, true);
+    const Lay<T> L(A.Cp, lb, nbpg);
+    apply_pass<T>((const T*)A.y + grp * A.gs_y, A.res != nullptr ? (const T*)A.res + grp * A.gs_res : nullptr,
+                  (T*)A.out + grp * A.gs_out, A.P, A.ld_y, A.ld_res, A.ld_out, A.scale + grp * A.stat_stride,
+                  A.shift + grp * A.stat_stride, A.relu, L, sm, true);
     prof_mark(A.prof, 5);
 }
 
@@ -709,6 +727,9 @@ struct BnBwdArgs {
     const float *mean, *invstd, *scale, *shift;
     float *dgamma, *dbeta, *c1, *c2;
     float inv_count;
+    int G;                                         // statistics groups, as in BnFwdArgs; d(gamma), d(beta) sum over them
+    long long gs_g, gs_a, gs_y, gs_dy, gs_dres;
+    int stat_stride;
 };
 
 template <typename T, int RELU, bool DRES>
@@ -717,47 +738,60 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
     extern __shared__ __align__(16) float sm[];
     cg::grid_group grid = cg::this_grid();
     prof_mark(A.prof, 0);
-    bwd_reduce_to_partials_t<T, RELU>((const T*)A.g, (const T*)A.a, (const T*)A.y, A.partials, A.P, A.Cp, A.ld_g, A.ld_a,
-                                      A.ld_y, A.mean, A.invstd, sm, A.scale, A.shift);
+    const int nbpg = gridDim.x / A.G;
+    const int grp = blockIdx.x / nbpg, lb = blockIdx.x - grp * nbpg;
+    const int so_g = grp * A.stat_stride;
+    const T* gp = (const T*)A.g + grp * A.gs_g;
+    const T* ap = A.a != nullptr ? (const T*)A.a + grp * A.gs_a : nullptr;
+    const T* yp = (const T*)A.y + grp * A.gs_y;
+    bwd_reduce_to_partials_t<T, RELU>(gp, ap, yp, A.partials, A.P, A.Cp, A.ld_g, A.ld_a, A.ld_y, A.mean + so_g,
+                                      A.invstd + so_g, sm, A.scale + so_g, A.shift != nullptr ? A.shift + so_g : nullptr, lb,
+                                      nbpg);
     prof_mark(A.prof, 1);
     grid.sync();
     prof_mark(A.prof, 2);
-    for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {      // one CTA per channel, one L2 round trip
-        const int n_parts = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        float s1 = 0.f, s2 = 0.f;
-        if (c < A.C) {
+    for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {      // one CTA per channel, one L2 round trip per group
+        const int n_parts = nbpg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float t1 = 0.f, t2 = 0.f;                              // sums over the groups: parameter gradients
+        for (int gq = 0; gq < A.G; ++gq) {
+            const float* parts = A.partials + (long long)gq * nbpg * 2 * A.Cp;
+            float s1 = 0.f, s2 = 0.f;
+            if (c < A.C) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int k = threadIdx.x + j * BN_THREADS;
-                if (k < n_parts) {
-                    s1 += __ldcg(A.partials + (long long)k * 2 * A.Cp + c);
-                    s2 += __ldcg(A.partials + (long long)k * 2 * A.Cp + A.Cp + c);
+                for (int j = 0; j < 3; ++j) {
+                    const int k = threadIdx.x + j * BN_THREADS;
+                    if (k < n_parts) {
+                        s1 += __ldcg(parts + (long long)k * 2 * A.Cp + c);
+                        s2 += __ldcg(parts + (long long)k * 2 * A.Cp + A.Cp + c);
+                    }
                 }
             }
-        }
-        s1 = warp_sum(s1); s2 = warp_sum(s2);
-        __syncthreads();
-        if (lane == 0) { sm[warp * 2] = s1; sm[warp * 2 + 1] = s2; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s1 = 0.f; s2 = 0.f;
+            s1 = warp_sum(s1); s2 = warp_sum(s2);
+            __syncthreads();
+            if (lane == 0) { sm[warp * 2] = s1; sm[warp * 2 + 1] = s2; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s1 = 0.f; s2 = 0.f;
 #pragma unroll
-            for (int w = 0; w < BN_THREADS / 32; ++w) { s1 += sm[w * 2]; s2 += sm[w * 2 + 1]; }
-            A.c1[c] = s1 * A.inv_count;
-            A.c2[c] = s2 * A.inv_count;
-            if (c < A.C) {
-                if (A.dbeta != nullptr) A.dbeta[c] = A.acc_param ? A.dbeta[c] + s1 : s1;
-                if (A.dgamma != nullptr) A.dgamma[c] = A.acc_param ? A.dgamma[c] + s2 : s2;
+                for (int w = 0; w < BN_THREADS / 32; ++w) { s1 += sm[w * 2]; s2 += sm[w * 2 + 1]; }
+                A.c1[gq * A.stat_stride + c] = s1 * A.inv_count;
+                A.c2[gq * A.stat_stride + c] = s2 * A.inv_count;
+                t1 += s1; t2 += s2;
             }
+        }
+        if (threadIdx.x == 0 && c < A.C) {
+            if (A.dbeta != nullptr) A.dbeta[c] = A.acc_param ? A.dbeta[c] + t1 : t1;
+            if (A.dgamma != nullptr) A.dgamma[c] = A.acc_param ? A.dgamma[c] + t2 : t2;
         }
     }
     prof_mark(A.prof, 3);
     grid.sync();
     prof_mark(A.prof, 4);
-    const Lay<T> L(A.Cp);
-    bwd_elemt_pass_t<T, RELU, DRES>((const T*)A.g, (const T*)A.a, (const T*)A.y, (T*)A.dy, (T*)A.dres, A.P, A.ld_g, A.ld_a,
-                                    A.ld_y, A.ld_dy, A.ld_dres, A.mean, A.invstd, A.scale, A.c1, A.c2, A.acc_dy, A.acc_dres,
-                                    L, sm, true, A.shift);
+    const Lay<T> L(A.Cp, lb, nbpg);
+    bwd_elemt_pass_t<T, RELU, DRES>(gp, ap, yp, (T*)A.dy + grp * A.gs_dy, A.dres != nullptr ? (T*)A.dres + grp * A.gs_dres : nullptr,
+                                    A.P, A.ld_g, A.ld_a, A.ld_y, A.ld_dy, A.ld_dres, A.mean + so_g, A.invstd + so_g,
+                                    A.scale + so_g, A.c1 + so_g, A.c2 + so_g, A.acc_dy, A.acc_dres, L, sm, true,
+                                    A.shift != nullptr ? A.shift + so_g : nullptr);
     prof_mark(A.prof, 5);
 }
 
@@ -811,8 +845,9 @@ static int launch_fwd_fused(BnFwdArgs& A, cudaStream_t st) {
     constexpr int V = Vec<T>::N;
     static int cap = 0;
     const size_t smem = kPipeBytes;   // streaming slots; the merge scratch aliases them
-    const int grid = coop_grid(bn_fwd_fused_kernel<T>, smem, A.P, A.Cp, V, &cap);
+    int grid = coop_grid(bn_fwd_fused_kernel<T>, smem, A.P * A.G, A.Cp, V, &cap);
     if (grid < 1) return VAE2_ERR_CUDA;
+    grid = grid < A.G ? A.G : grid / A.G * A.G;      // the same CTA count for every statistics group (cap >= 148 > G)
     void* args[] = {(void*)&A};
     if (cudaLaunchCooperativeKernel((const void*)bn_fwd_fused_kernel<T>, dim3(grid), dim3(BN_THREADS), args, smem, st) !=
         cudaSuccess)
@@ -825,8 +860,9 @@ static int launch_bwd_fused_t(BnBwdArgs& A, cudaStream_t st) {
     constexpr int V = Vec<T>::N;
     static int cap = 0;
     const size_t smem = kPipeBytes;   // streaming slots; the merge scratch aliases them
-    const int grid = coop_grid(bn_bwd_fused_kernel<T, RELU, DRES>, smem, A.P, A.Cp, V, &cap);
+    int grid = coop_grid(bn_bwd_fused_kernel<T, RELU, DRES>, smem, A.P * A.G, A.Cp, V, &cap);
     if (grid < 1) return VAE2_ERR_CUDA;
+    grid = grid < A.G ? A.G : grid / A.G * A.G;
     void* args[] = {(void*)&A};
     if (cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel<T, RELU, DRES>, dim3(grid), dim3(BN_THREADS), args,
                                     smem, st) != cudaSuccess)
@@ -853,8 +889,20 @@ int bn_fwd_fused(const void* y, const void* res, void* out, float* partials, int
                  float* shift, int relu, cudaStream_t st) {
     const int V = vec_of(dtype);
     if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V) || Cp / V > BN_THREADS || P < 1) return VAE2_ERR_ARG;
+    return bn_fwd_fused_groups(y, res, out, partials, dtype, P, C, Cp, ld_y, ld_res, ld_out, gamma, beta, running_mean,
+                               running_var, nbt, momentum, eps, mean, invstd, scale, shift, relu, 1, 0, st);
+}
+
+int bn_fwd_fused_groups(const void* y, const void* res, void* out, float* partials, int dtype, long long P, int C, int Cp,
+                        int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, long long* nbt, float momentum, float eps, float* mean, float* invstd,
+                        float* scale, float* shift, int relu, int groups, int stat_stride, cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V) || Cp / V > BN_THREADS || P < 1 || groups < 1 ||
+        groups > 64)
+        return VAE2_ERR_ARG;
     BnFwdArgs A{g_bn_prof, y, res, out, partials, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
-                nbt, momentum, eps, mean, invstd, scale, shift};
+                nbt, momentum, eps, mean, invstd, scale, shift, groups, P * ld_y, P * ld_res, P * ld_out, stat_stride};
     return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
 }
 
@@ -866,8 +914,23 @@ int bn_bwd_fused(const void* g, const void* a, const void* y, void* dy, void* dr
     if (Cp % V || ld_g % V || ld_y % V || ld_dy % V || (relu == 1 && (a == nullptr || ld_a % V)) ||
         (relu == 2 && shift == nullptr) || relu < 0 || relu > 2 || (dres && ld_dres % V) || Cp / V > BN_THREADS || P < 1)
         return VAE2_ERR_ARG;
+    return bn_bwd_fused_groups(g, a, y, dy, dres, partials, dtype, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd,
+                               scale, shift, dgamma, dbeta, accumulate_param, c1, c2, relu, acc_dy, acc_dres, 1, 0, st);
+}
+
+int bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                        long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                        const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                        int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
+                        int stat_stride, cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_g % V || ld_y % V || ld_dy % V || (relu == 1 && (a == nullptr || ld_a % V)) ||
+        (relu == 2 && shift == nullptr) || relu < 0 || relu > 2 || (dres && ld_dres % V) || Cp / V > BN_THREADS || P < 1 ||
+        groups < 1 || groups > 64)
+        return VAE2_ERR_ARG;
     BnBwdArgs A{g_bn_prof, g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
-                accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, 1.0f / (float)P};
+                accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, 1.0f / (float)P, groups, P * ld_g,
+                P * ld_a, P * ld_y, P * ld_dy, P * ld_dres, stat_stride};
     return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
 }
 

@@ -69,6 +69,15 @@ int bn_bwd_fused(const void* g, const void* a, const void* y, void* dy, void* dr
                  long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
                  const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
                  int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, cudaStream_t st);
+int bn_fwd_fused_groups(const void* y, const void* res, void* out, float* partials, int dtype, long long P, int C, int Cp,
+                        int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, long long* nbt, float momentum, float eps, float* mean, float* invstd,
+                        float* scale, float* shift, int relu, int groups, int stat_stride, cudaStream_t st);
+int bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                        long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                        const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                        int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
+                        int stat_stride, cudaStream_t st);
 int bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, cudaStream_t st);
 int bn_bwd_coeffs(const float* sums, int C, int Cp, float inv_count, float* dgamma, float* dbeta, int accumulate_param,
                   const float* sums_for_param, float* c1, float* c2, cudaStream_t st);

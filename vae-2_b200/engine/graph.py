@@ -1014,6 +1014,13 @@ class BnOp:
         npix, ldy, ldo, C_, Cp = self.npix_g, y.ld, out.ld, y.C, y.Cp
         gp, bp, rm, rv, nbt, mom, eps = self._bn_ptrs()
         relu = 1 if self.relu else 0
+        p0, G = self.parts[0], len(self.parts)
+        if G > 1 and os.environ.get("VAE2_BN_GROUP_LAUNCH", "1") != "0":
+            # all statistics groups in ONE cooperative launch (csrc/bn.cu: the grid is split evenly between the groups)
+            plan.fwd.append(lambda st: N.call.vae2_bn_fwd_fused_groups(
+                p0.yp, p0.resp, p0.outp, ws, pr.code, npix, C_, Cp, ldy, ldr, ldo, gp, bp, rm, rv, nbt, mom, eps,
+                p0.mean, p0.invstd, p0.scale, p0.shift, relu, G, 6 * Cp, st))
+            return
         for pt in self.parts:
             plan.fwd.append(lambda st, pt=pt: N.call.vae2_bn_fwd_fused(
                 pt.yp, pt.resp, pt.outp, ws, pr.code, npix, C_, Cp, ldy, ldr, ldo, gp, bp, rm, rv, nbt, mom, eps,
@@ -1037,6 +1044,14 @@ class BnOp:
         relu = 0 if not self.relu else (1 if res is not None else 2)
         gld, old, yld, dld = g.ld, out.ld, y.ld, dy.ld
         es = pr.esize
+        p0, G = self.parts[0], len(self.parts)
+        if G > 1 and os.environ.get("VAE2_BN_GROUP_LAUNCH", "1") != "0":
+            dres0 = res.grad().ptr if has_dres else None
+            gp0, dyp0 = g.ptr, dy.ptr
+            plan.bwd.append(lambda st: N.call.vae2_bn_bwd_fused_groups(
+                gp0, p0.outp, p0.yp, dyp0, dres0, ws, pr.code, npix, C_, lanes, gld, old, yld, dld, ld_dres, p0.mean,
+                p0.invstd, p0.scale, p0.shift, dgam, dbet, 0, p0.c1, p0.c2, relu, acc_dy, acc_res, G, 6 * y.Cp, st))
+            return
         for pt in reversed(self.parts):
             gp_, dyp = g.ptr + pt.off * gld * es, dy.ptr + pt.off * dld * es
             dres_p = (res.grad().ptr + pt.off * ld_dres * es) if has_dres else None
