@@ -104,6 +104,13 @@ long long vae2_conv2d_wgrad_tc_workspace(const vae2_conv_geom* g);
 int vae2_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, float* workspace, const vae2_conv_geom* g,
                          vae2_stream_t stream);
 
+/* fp32 tensor-core weight gradient (engine-2 companion): x and dy (fp32 act) are split into two bf16 planes each and the
+ * three leading plane products run on the tcgen05 weight-gradient kernel with separate accumulators; dw_packed fp32
+ * [tap][Cin_p][Cout_p] is OVERWRITTEN.  `workspace`: vae2_conv2d_wgrad_f32x2_workspace(g) BYTES (negative = unsupported) */
+long long vae2_conv2d_wgrad_f32x2_workspace(const vae2_conv_geom* g);
+int vae2_conv2d_wgrad_f32x2(const float* x, const float* dy, float* dw_packed, void* workspace, const vae2_conv_geom* g,
+                            vae2_stream_t stream);
+
 /* ---- batch norm: BatchNorm2d(momentum=0.01) / SyncBatchNorm, enc_hrnet.py:22-23, train.py:217 - */
 int vae2_bn_max_partials(void);
 /* per-CTA Welford partials [n_partials][3][Cp] = (count, mean, M2); *n_partials is a HOST out */

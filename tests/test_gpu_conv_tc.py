@@ -170,3 +170,38 @@ def test_conv_f32x3_fwd_dgrad(case):
     N.call.vae2_conv2d_dgrad(gya.data_ptr(), wb.data_ptr(), dxa.data_ptr(), 0, C.byref(g), 1, 2, st())
     torch.cuda.synchronize()
     assert rel_err(from_act(dxa, "fp32", B, Cin, H, W, Cin_p), 2 * xr.grad) < 3e-5, "f32x3 dgrad accumulate"
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_wgrad_f32x2(case):
+    """The fp32 path's tensor-core weight gradient (bf16 hi/lo planes, three products on the tcgen05 wgrad kernel with
+    separate accumulators) against a float64 weight gradient; the CUDA-core split-K kernel it replaces is measured
+    beside it."""
+    from helpers import log_err
+    B, Cin, Cout, H, W, k, use_bias, stride = case
+    tag = "wx2%s" % (case,)
+    x = O.det_normal(tag + "x", (B, Cin, H, W))
+    w = O.det_normal(tag + "w", (Cout, Cin, k, k), 0.05).double().requires_grad_(True)
+    yr = F.conv2d(x.double(), w, None, stride=stride, padding=k // 2)
+    gy = O.det_normal(tag + "gy", tuple(yr.shape))
+    yr.backward(gy.double())
+    Ho, Wo = yr.shape[-2:]
+    xa, Cin_p = to_act(x, "fp32")
+    gya, Cout_p = to_act(gy, "fp32")
+    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin_p, ldx=Cin_p, Ho=Ho, Wo=Wo, Cout_p=Cout_p, ldy=Cout_p, k=k, stride=stride, pad=k // 2)
+    need = N.lib().vae2_conv2d_wgrad_f32x2_workspace(C.byref(g))
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device=dev())
+    dwp = torch.full((k * k * Cin_p * Cout_p,), 7.0, dtype=torch.float32, device=dev())      # must be overwritten
+    N.call.vae2_conv2d_wgrad_f32x2(xa.data_ptr(), gya.data_ptr(), dwp.data_ptr(), ws.data_ptr(), C.byref(g), st())
+    dws = torch.zeros_like(dwp)
+    N.call.vae2_conv2d_wgrad(xa.data_ptr(), gya.data_ptr(), dws.data_ptr(), 0, C.byref(g), 0, st())
+    torch.cuda.synchronize()
+
+    def unpack(t):       # [tap][Cin_p][Cout_p] -> OIHW
+        return t.view(k, k, Cin_p, Cout_p)[:, :, :Cin, :Cout].permute(3, 2, 0, 1).cpu()
+    e_tc, e_simt = rel_err(unpack(dwp), w.grad), rel_err(unpack(dws), w.grad)
+    log_err("wgrad_f32x2_%s" % (case,), f32x2_vs_fp64=e_tc, cuda_core_vs_fp64=e_simt)
+    assert e_tc < 3e-5, (e_tc, e_simt)
+    pads = dwp.view(k * k, Cin_p, Cout_p)
+    assert float(pads[:, Cin:, :].abs().sum()) == 0.0 and float(pads[:, :, Cout:].abs().sum()) == 0.0

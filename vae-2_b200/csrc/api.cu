@@ -103,6 +103,12 @@ int vae2_conv2d_wgrad_tc(const void* x, const void* dy, float* dw_packed, float*
     return conv_wgrad_tc(x, dy, dw_packed, workspace, G(g), S(stream));
 }
 
+long long vae2_conv2d_wgrad_f32x2_workspace(const vae2_conv_geom* g) { return conv_wgrad_f32x2_workspace(G(g)); }
+int vae2_conv2d_wgrad_f32x2(const float* x, const float* dy, float* dw_packed, void* workspace, const vae2_conv_geom* g,
+                            vae2_stream_t stream) {
+    return conv_wgrad_f32x2(x, dy, dw_packed, workspace, G(g), S(stream));
+}
+
 int vae2_bn_max_partials(void) { return bn_stats_max_partials(); }
 int vae2_bn_stats(const void* y, float* partials, int* n_partials, int dtype, int64_t npix, int Cp, int ld,
                   vae2_stream_t stream) {

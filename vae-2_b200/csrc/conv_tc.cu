@@ -456,7 +456,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t row_by
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t rowA = p.atomA * 2, rowB = p.atomB * 2;
@@ -607,20 +607,33 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long 
 static int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
 // Fills p (everything except ws) and returns the workspace size in floats; <0 if unsupported.
-static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages);
+static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages, int ctas);
 
 // 64 pixels per stage when that still leaves a 3-deep pipeline, else 32
 static long long plan_wgrad(const ConvGeom& g, WParams& p) {
     int first = 64;
     if (const char* e = getenv("VAE2_WGRAD_KP")) { const int v = atoi(e); if (v == 32) first = 32; }
-    if (first == 64) {
-        const long long r = plan_wgrad_kp(g, p, 64, 3);
+    // Two co-resident CTAs per SM (each half the shared memory, <= 256 TMEM columns) when the operands are narrow: the
+    // kernel is bound by the single issuing thread's barrier round trips (ncu r2a: tensor pipe 7.6 % active, 9 % occupancy
+    // on the 18->18 layers), and a second independent issuer per SM overlaps them.  VAE2_WGRAD_CTAS=1 restores one.
+    int ctas = 2;
+    if (const char* e = getenv("VAE2_WGRAD_CTAS")) { const int v = atoi(e); if (v == 1) ctas = 1; }
+    if (ctas == 2) {
+        if (first == 64) {
+            const long long r = plan_wgrad_kp(g, p, 64, 3, 2);
+            if (r >= 0) return r;
+        }
+        const long long r = plan_wgrad_kp(g, p, 32, 3, 2);
         if (r >= 0) return r;
     }
-    return plan_wgrad_kp(g, p, 32, 2);
+    if (first == 64) {
+        const long long r = plan_wgrad_kp(g, p, 64, 3, 1);
+        if (r >= 0) return r;
+    }
+    return plan_wgrad_kp(g, p, 32, 2, 1);
 }
 
-static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages) {
+static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages, int ctas) {
     // K runs over OUTPUT pixels (Ho x Wo); x is sampled at stride g.stride
     p.B = g.B; p.H = g.Ho; p.W = g.Wo; p.sA = g.stride;
     p.n_tiles = (g.Cout_p + 255) / 256;
@@ -640,8 +653,10 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
     const int groups_total = (p.M_total + 127) / 128;
     // groups per CTA ("set"): as many as TMEM holds (512 columns), shrunk until the stage ring is deep enough
     const int nchunkA = g.Cin_p / p.atomA;
-    int sg_max = 512 / p.NT;
+    int sg_max = (512 / ctas) / p.NT;
     if (sg_max > groups_total) sg_max = groups_total;
+    if (sg_max < 1) return -1;
+    if (ctas > 1 && sg_max < groups_total) return -1;      // co-residency only when one set holds every accumulator
     int sg = 0, stages = 0, worst = 0;
     for (int cand = sg_max; cand >= 1; --cand) {
         const int nsets = (groups_total + cand - 1) / cand;
@@ -658,7 +673,7 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
         }
         const long long a_b = (long long)w * p.KP * p.atomA * 2, b_b = (long long)p.NT * p.KP * 2;
         const long long sb = ((a_b + b_b + 1023) / 1024) * 1024;
-        int st_ = (int)(kSmemBudget / sb);
+        int st_ = (int)((kSmemBudget / ctas - (ctas > 1 ? 2048 : 0)) / sb);
         if (st_ > kMaxStages) st_ = kMaxStages;
         if (st_ >= min_stages) { sg = cand; stages = st_; worst = w; break; }
     }
@@ -668,7 +683,7 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
     p.tmem_cols = next_pow2_cols(sg * p.NT);
     p.a_atoms_stage = worst;
     p.stages = stages;
-    int nranges = kNumSMs / (p.nsets * p.n_tiles);
+    int nranges = ctas * kNumSMs / (p.nsets * p.n_tiles);
     if (nranges < 1) nranges = 1;
     if (nranges > p.total_ptiles) nranges = p.total_ptiles;
     const long long slot = (long long)p.M_total * g.Cout_p;
@@ -955,6 +970,136 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
     if (int e = check_launch()) return e;
     const long long n = (long long)p.M_total * g.Cout_p;
     wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(ws, dwp, n, p.nranges);
+    return check_launch();
+}
+
+
+// =================================================================================================
+// fp32 weight gradient on tcgen05 ("f32x2"): fp32 activations are split into two bf16 planes
+// (hi = bf16(x), lo = bf16(x - hi); what is dropped is <= 2^-17 |x|) and the gradient is the sum of three plane
+// products  hi*hi + hi*lo + lo*hi, each one launch of wgrad_tc_kernel above with its OWN accumulators and split-K
+// slots (so the small products never share a truncating accumulator with the leading one); the slots of all three
+// are folded by wgrad_reduce_kernel in fixed order and cropped into the fp32 path's [tap][Cin_p][Cout_p] layout.
+// Replaces conv_igemm's split-K FMA weight gradient for the >= 40-lane layers of the fp32 path
+// (ncu r2b: 270->270 1x1 @B=4 3577 us, 64->64 3x3 1279 us -- 27 % of the fp32 step).
+// =================================================================================================
+namespace tc {
+
+// src fp32 [npix][ld] (lanes used: C) -> hi, lo bf16 [npix][Cq] (Cq = C padded to 16, pad lanes zero)
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                    long long npix, int C, int ld, int Cq) {
+    const int vec = Cq / 8;                                   // 8 output lanes (16 bytes of bf16) per thread
+    const long long total = npix * vec;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / vec;
+        const int c0 = (int)(i - p * vec) * 8;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k += 4) {
+            if (c0 + k < C) {                                 // C and ld are multiples of 4
+                const float4 f = *reinterpret_cast<const float4*>(src + p * ld + c0 + k);
+                v[k] = f.x; v[k + 1] = f.y; v[k + 2] = f.z; v[k + 3] = f.w;
+            } else {
+                v[k] = v[k + 1] = v[k + 2] = v[k + 3] = 0.f;
+            }
+        }
+        uint4 oh, ol;
+        __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(&oh);
+        __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(&ol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            h[k] = __float2bfloat16_rn(v[k]);
+            l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k]));
+        }
+        *reinterpret_cast<uint4*>(hi + p * Cq + c0) = oh;
+        *reinterpret_cast<uint4*>(lo + p * Cq + c0) = ol;
+    }
+}
+
+// dwp[t][ci][co] (Cin_p x Cout_p lanes) = src[t][ci][co] (Ciq x Coq lanes)
+__global__ void crop_dw_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int Cin_p, int Cout_p,
+                               int Ciq, int Coq) {
+    const int total = taps * Cin_p * Cout_p;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % Cout_p;
+        const int ci = (i / Cout_p) % Cin_p;
+        const int t = i / (Cout_p * Cin_p);
+        dst[i] = src[((long long)t * Ciq + ci) * Coq + co];
+    }
+}
+
+static ConvGeom geom16(const ConvGeom& g) {
+    ConvGeom q = g;
+    q.Cin_p = (g.Cin_p + 15) / 16 * 16; q.ldx = q.Cin_p;
+    q.Cout_p = (g.Cout_p + 15) / 16 * 16; q.ldy = q.Cout_p;
+    return q;
+}
+
+}  // namespace tc
+
+// bytes of workspace conv_wgrad_f32x2 needs (negative: unsupported geometry)
+long long conv_wgrad_f32x2_workspace(const ConvGeom& g) {
+    const ConvGeom q = tc::geom16(g);
+    if (!conv_tc_supported(q)) return -1;
+    tc::WParams p;
+    const long long part = tc::plan_wgrad(q, p);            // floats of ONE product's split-K slots
+    if (part < 0) return -1;
+    const long long nx = (long long)g.B * g.H * g.W * q.Cin_p, ny = (long long)g.B * g.Ho * g.Wo * q.Cout_p;
+    const long long dw16 = (long long)p.M_total * q.Cout_p;
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    return al(2 * nx * 2) + al(2 * ny * 2) + al(3 * part * 4) + al(dw16 * 4);
+}
+
+int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspace, const ConvGeom& g, cudaStream_t st) {
+    using namespace tc;
+    const ConvGeom q = geom16(g);
+    if (!conv_tc_supported(q) || g.Cin_p % 4 || g.Cout_p % 4 || g.ldx % 4 || g.ldy % 4) return VAE2_ERR_UNSUPPORTED;
+    WParams p;
+    const long long part = plan_wgrad(q, p);
+    if (part < 0) return VAE2_ERR_UNSUPPORTED;
+    const long long npx = (long long)g.B * g.H * g.W, npy = (long long)g.B * g.Ho * g.Wo;
+    const long long nx = npx * q.Cin_p, ny = npy * q.Cout_p;
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(w);
+    __nv_bfloat16* xl = xh + nx;
+    w += al(2 * nx * 2);
+    __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(w);
+    __nv_bfloat16* yl = yh + ny;
+    w += al(2 * ny * 2);
+    float* slots = reinterpret_cast<float*>(w);
+    w += al(3 * part * 4);
+    float* dw16 = reinterpret_cast<float*>(w);
+    note_kernel("tc::wgrad_tc_kernel (f32x2 planes)");
+    split_planes_kernel<<<stream_grid(npx * (q.Cin_p / 8), 256), 256, 0, st>>>(x, xh, xl, npx, g.Cin_p, g.ldx, q.Cin_p);
+    split_planes_kernel<<<stream_grid(npy * (q.Cout_p / 8), 256), 256, 0, st>>>(dy, yh, yl, npy, g.Cout_p, g.ldy, q.Cout_p);
+    if (int e = check_launch()) return e;
+    EncodeTiledFn enc = encode_fn();
+    const long long a_bytes = (long long)p.a_atoms_stage * p.KP * p.atomA * 2;
+    const long long b_bytes = (long long)p.NT * p.KP * 2;
+    const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return VAE2_ERR_CUDA;
+        attr_set = true;
+    }
+    const __nv_bfloat16* xa[3] = {xl, xh, xh};      // smallest products first in the fold: lo*hi, hi*lo, hi*hi
+    const __nv_bfloat16* ya[3] = {yh, yl, yh};
+    for (int t = 0; t < 3; ++t) {
+        CUtensorMap map_x, map_dy;
+        if (make_map5(enc, &map_x, xa[t], p.atomA, q.Cin_p, q.Cin_p, q.ldx, q.B, q.H, q.W, p.TW, p.TH, q.stride)) return VAE2_ERR_ARG;
+        if (make_map5(enc, &map_dy, ya[t], p.atomB, q.Cout_p, p.NT, q.ldy, q.B, q.Ho, q.Wo, p.TW, p.TH, 1)) return VAE2_ERR_ARG;
+        p.ws = slots + (long long)t * part;
+        wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
+        if (int e = check_launch()) return e;
+    }
+    const long long n = (long long)p.M_total * q.Cout_p;
+    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, 3 * p.nranges);
+    const int total = g.k * g.k * g.Cin_p * g.Cout_p;
+    crop_dw_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw16, dwp, g.k * g.k, g.Cin_p, g.Cout_p, q.Cin_p, q.Cout_p);
     return check_launch();
 }
 

@@ -146,6 +146,8 @@ int conv_tc_supported(const ConvGeom& g);
 long long conv_wgrad_tc_workspace(const ConvGeom& g);
 int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const ConvGeom& g, cudaStream_t st);
 int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, int accumulate, cudaStream_t st);
+long long conv_wgrad_f32x2_workspace(const ConvGeom& g);      // bytes
+int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspace, const ConvGeom& g, cudaStream_t st);
 
 // conv_f32x3.cu (fp32-accurate tcgen05 convolution by an exact 3-way bf16 split: forward and data gradient of the fp32 path)
 struct Tf32PackDesc {

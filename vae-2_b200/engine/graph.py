@@ -493,6 +493,16 @@ class Plan:
                         o.wgrad_tc = True
                         ws_floats = max(ws_floats, need)
         self.wgrad_ws = torch.zeros(ws_floats, dtype=torch.float32, device=dev) if ws_floats else None
+        # fp32 path: weight gradient of the tensor-core (engine 2) layers through bf16 hi/lo planes on the tcgen05 wgrad
+        # kernel (csrc/conv_tc.cu: conv_wgrad_f32x2); one shared workspace, the convs run one after another
+        x2_bytes = 0
+        if self.training and os.environ.get("VAE2_FP32_TC_WGRAD", "1") != "0":
+            for o in x3:
+                need = N.lib().vae2_conv2d_wgrad_f32x2_workspace(C.byref(o._geom()))
+                o.wgrad_x2 = need > 0 and o.conv.weight.requires_grad
+                if o.wgrad_x2:
+                    x2_bytes = max(x2_bytes, need)
+        self.wgrad_x2_ws = torch.empty(x2_bytes, dtype=torch.uint8, device=dev) if x2_bytes else None
         self.wp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev)
         self.wpT_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
         self.dwp_flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=dev) if self.training else None
@@ -906,6 +916,9 @@ class ConvOp:
         elif getattr(self, "wgrad_tc", False):
             wsp = plan.wgrad_ws.data_ptr()
             plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad_tc(xp, dyp, dwp, wsp, gp, st))
+        elif getattr(self, "wgrad_x2", False):
+            wsp = plan.wgrad_x2_ws.data_ptr()
+            plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad_f32x2(xp, dyp, dwp, wsp, gp, st))
         else:
             plan.bwd.append(lambda st: N.call.vae2_conv2d_wgrad(xp, dyp, dwp, pr.code, gp, 0, st))
         if self.conv.bias is not None and self.conv.bias.requires_grad:

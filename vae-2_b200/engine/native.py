@@ -66,6 +66,7 @@ _PROTOS = {
     "vae2_bias_grad": [vp, vp, i32, i64, i32, i32, i32, vp],
     "vae2_conv2d_wgrad_tc": [vp, vp, vp, vp, C.POINTER(ConvGeom), vp],
     "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)],
+    "vae2_conv2d_wgrad_f32x2": [vp, vp, vp, vp, C.POINTER(ConvGeom), vp],
     "vae2_bn_stats": [vp, vp, ip, i32, i64, i32, i32, vp],
     "vae2_bn_merge": [vp, i32, i32, vp, vp],
     "vae2_bn_finalize": [vp, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp],
@@ -102,7 +103,8 @@ _PLAIN_INT = {"vae2_abi_version": [], "vae2_bn_max_partials": [], "vae2_elbo_acc
               "vae2_conv2d_tc_supported": [C.POINTER(ConvGeom)], "vae2_conv2d_tf32_supported": [C.POINTER(ConvGeom)]}
 
 EXPORTS = sorted(set(_PROTOS) | set(_PLAIN_INT) | {"vae2_status_string", "vae2_last_cuda_error", "vae2_last_kernel",
-                                                     "vae2_conv2d_wgrad_tc_workspace", "vae2_conv2d_tf32_dims"})
+                                                     "vae2_conv2d_wgrad_tc_workspace", "vae2_conv2d_wgrad_f32x2_workspace",
+                                                     "vae2_conv2d_tf32_dims"})
 
 _lib = None
 
@@ -126,6 +128,8 @@ def lib():
             fn.restype = C.c_int
         h.vae2_conv2d_wgrad_tc_workspace.argtypes = [C.POINTER(ConvGeom)]
         h.vae2_conv2d_wgrad_tc_workspace.restype = C.c_longlong
+        h.vae2_conv2d_wgrad_f32x2_workspace.argtypes = [C.POINTER(ConvGeom)]
+        h.vae2_conv2d_wgrad_f32x2_workspace.restype = C.c_longlong
         h.vae2_conv2d_tf32_dims.argtypes = [C.POINTER(ConvGeom), ip, ip, ip, ip]
         h.vae2_conv2d_tf32_dims.restype = None
         h.vae2_status_string.argtypes = [C.c_int]

@@ -40,28 +40,34 @@ def describe(name, args):
     g = _geom_of(args)
     if g is not None and name.startswith("vae2_conv2d"):
         code = {"vae2_conv2d_fwd": lambda a: a[4], "vae2_conv2d_dgrad": lambda a: a[3], "vae2_conv2d_wgrad": lambda a: a[3],
-                "vae2_conv2d_wgrad_tc": lambda a: 1}[name](args)
+                "vae2_conv2d_wgrad_tc": lambda a: 1, "vae2_conv2d_wgrad_f32x2": lambda a: 0}[name](args)
         s = _ESZ[code]
         flop, nx, ny, nw = _conv_work(g, name)
         by = s * (nx + ny) + (4 if "wgrad" in name else s) * nw
         what = {"vae2_conv2d_fwd": "fwd", "vae2_conv2d_dgrad": "dgrad", "vae2_conv2d_wgrad": "wgrad",
-                "vae2_conv2d_wgrad_tc": "wgrad"}[name]
+                "vae2_conv2d_wgrad_tc": "wgrad", "vae2_conv2d_wgrad_f32x2": "wgrad"}[name]
         shape = "%s %d->%d k%d s%d @%dx%d B=%d" % (what, getattr(g, "Cin", g.Cin_p), getattr(g, "Cout", g.Cout_p), g.k,
                                                    g.stride, g.H, g.W, g.B)
         kern = N.lib().vae2_last_kernel().decode() or name
         if name == "vae2_conv2d_wgrad_tc":
             kern = "tc::wgrad_tc_kernel+wgrad_reduce_kernel"
+        if name == "vae2_conv2d_wgrad_f32x2":
+            kern = "split_planes+3x tc::wgrad_tc_kernel+reduce (fp32 wgrad)"
         return kern, shape, flop, float(by)
-    if name == "vae2_bn_fwd_fused":
+    if name in ("vae2_bn_fwd_fused", "vae2_bn_fwd_fused_groups"):
         code, npix, C_ = args[4], args[5], args[6]
+        G = args[23] if name.endswith("groups") else 1
         res = args[1] is not None
-        return "bn_fwd_fused_kernel", "C=%d npix=%d%s" % (C_, npix, " +res" if res else ""), 0.0, float(_ESZ[code] * npix * C_ * (3 + res))
-    if name == "vae2_bn_bwd_fused":
+        return ("bn_fwd_fused_kernel", "C=%d npix=%d%s%s" % (C_, npix, " +res" if res else "", " x%d groups" % G if G > 1 else ""),
+                0.0, float(_ESZ[code] * npix * G * C_ * (3 + res)))
+    if name in ("vae2_bn_bwd_fused", "vae2_bn_bwd_fused_groups"):
         code, npix, C_ = args[6], args[7], args[8]
+        G = args[27] if name.endswith("groups") else 1
         dres = args[4] is not None
         relu = args[24]
-        return ("bn_bwd_fused_kernel", "C=%d npix=%d relu=%d%s" % (C_, npix, relu, " +dres" if dres else ""), 0.0,
-                float(_ESZ[code] * npix * C_ * (5 + dres + (1 if relu == 1 else 0))))
+        return ("bn_bwd_fused_kernel", "C=%d npix=%d relu=%d%s%s" % (C_, npix, relu, " +dres" if dres else "",
+                                                                     " x%d groups" % G if G > 1 else ""), 0.0,
+                float(_ESZ[code] * npix * G * C_ * (5 + dres + (1 if relu == 1 else 0))))
     if name in ("vae2_bn_stats", "vae2_bn_apply", "vae2_bn_bwd_reduce", "vae2_bn_bwd_elemt"):
         idx = {"vae2_bn_stats": (3, 4, 5, 1), "vae2_bn_apply": (3, 4, 5, 2), "vae2_bn_bwd_reduce": (5, 6, 7, 2),
                "vae2_bn_bwd_elemt": (5, 6, 7, 3)}[name]
