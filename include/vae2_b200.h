@@ -54,6 +54,15 @@ int vae2_slice_copy(const void* src, void* dst, int dtype, int64_t npix, int Cp,
 int vae2_code_broadcast(const float* code, void* dst, int dtype, int B, int Z, int Zp, int H, int W, int ld,
                         vae2_stream_t stream);
 
+/* nn.AdaptiveAvgPool2d((1,1)) of the non-HD_Z posterior head (enc_hrnet.py:1023-1041) and the gradient of the spatial
+ * repeat of a per-sample z (enc_hrnet.py:454-462):  out[b][c] (=|+=) scale * sum_p x[b][p][c]; out is fp32 (out_fp32=1)
+ * or an act of x's dtype, row pitch out_ld elements */
+int vae2_spatial_sum(const void* x, void* out, int dtype, int out_fp32, int B, int HW, int C, int ld, int out_ld, float scale,
+                     int accumulate, vae2_stream_t stream);
+/* its transpose: dx[b][p][c] (=|+=) scale * g[b][c] for c < C, 0 for the pad lanes C..Cp */
+int vae2_spatial_bcast(const void* g, void* dx, int dtype, int g_fp32, int B, int HW, int C, int Cp, int ld, int g_ld,
+                       float scale, int accumulate, vae2_stream_t stream);
+
 /* ---- weights: OIHW nn.Conv2d parameters <-> GEMM operand layouts ---------------------------- */
 typedef struct {
     const float* w;      /* OIHW fp32 (pack: source, unpack: destination gradient) */

@@ -96,8 +96,9 @@ def hrnet_case(fname, cfg_name, B, H, W, wmode, enc_hrnet, rutils, rcrit, keep_g
     sd0 = {k: v.clone() for k, v in sd.items()}   # state_dict() aliases the live buffers: keep a snapshot
     Z = cfg.MODEL.EXTRA.Z_DIM
     xt, x2t, x3t = O.make_clips(fname, B, H, W)
-    eps_z, code = O.make_eps(fname, B, Z, H, W)
-    out = {"meta": np.array([B, H, W, Z]), "cfg": np.array(cfg_name), "wmode": np.array(wmode)}
+    eps_z, code = O.make_eps(fname, B, Z, H, W, hd_z=bool(cfg.MODEL.EXTRA.HD_Z))
+    out = {"meta": np.array([B, H, W, Z]), "cfg": np.array(cfg_name), "wmode": np.array(wmode),
+           "hd_z": np.array(int(bool(cfg.MODEL.EXTRA.HD_Z)))}
 
     # --- G step, training mode ---
     g.train()
@@ -242,6 +243,9 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
     enc_hrnet, toy_fc, rutils, rcrit = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "nohdz":     # non-HD_Z posterior head
+        hrnet_case("tiny_b2_32x64_nohdz", "vae2_hrnet_tiny_32x64_nohdz.yaml", 2, 32, 64, "trained", enc_hrnet, rutils, rcrit)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "w18_full":   # BASELINE configs[1] size (about 2 min, 30 GB of host memory)
         hrnet_case_fullsize("w18_b1_256x512", "vae2_hrnet_w18_small_v2_256x512.yaml", 1, 256, 512, "trained",
                             enc_hrnet, rutils, rcrit, backward=True)

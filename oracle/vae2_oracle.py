@@ -95,9 +95,11 @@ def branch_sizes(H, W, n=4):
     return out
 
 
-def make_eps(tag, B, Z, H, W):
-    """eps for the 4 posterior maps (utils.py:92-93 call order) and the encoder's
-    random code [B,Z,1,1] (enc_hrnet.py:456, drawn after them)."""
+def make_eps(tag, B, Z, H, W, hd_z=True):
+    """eps for the 4 posterior maps (utils.py:92-93 call order) -- or the single [B,Z,1,1] draw without HD_Z
+    (utils.py:98-100) -- and the encoder's random code [B,Z,1,1] (enc_hrnet.py:456, drawn after them)."""
+    if not hd_z:
+        return [det_normal("%s:eps0" % tag, (B, Z, 1, 1))], det_normal(tag + ":code", (B, Z, 1, 1))
     eps_z = [det_normal("%s:eps%d" % (tag, i), (B, Z, h, w)) for i, (h, w) in enumerate(branch_sizes(H, W))]
     code = det_normal(tag + ":code", (B, Z, 1, 1))
     return eps_z, code
@@ -291,6 +293,11 @@ def encz_forward(sd, cfg, x, training=True, taps=None):
     """HighResolutionNetEDz.forward (HD_Z), enc_hrnet.py:1070-1122 -> 4 maps [B,2Z,H_i,W_i]."""
     c = _Ctx(sd, training, taps)
     ys = _trunk(c, "", x, cfg.MODEL.EXTRA)
+    if not cfg.MODEL.EXTRA.HD_Z:
+        # non-HD_Z head, enc_hrnet.py:1023-1041 / :1107-1116: avgpool -> 1x1+bias -> BN -> ReLU -> 1x1+bias -> [B,2Z,1,1]
+        h = F.adaptive_avg_pool2d(_upcat(ys), (1, 1))
+        h = F.relu(_bn(c, "last_layer.2", _conv(c, "last_layer.1", h)))
+        return _conv(c, "last_layer.4", h)
     return [_conv(c, "last_layer.%d.0" % i, ys[i]) for i in range(len(ys))]
 
 
@@ -306,6 +313,8 @@ def _one_net(c, pre, x, extra, z, code, is_encoder):
     nb = extra["STAGE4"]["NUM_BRANCHES"]
     H, W = x.shape[-2:]
     sizes = branch_sizes(H, W, nb)
+    if torch.is_tensor(z):      # no HD_Z: one per-sample z [B,Z,1,1] repeated over every map (_gen_code_map(x_list, z), :819)
+        z = [z.repeat(1, 1, h, w) for (h, w) in sizes]
     if is_encoder:
         cmaps = [[code.repeat(1, 1, h, w), z[b]] for b, (h, w) in enumerate(sizes)]
     else:
@@ -373,12 +382,17 @@ def full_encdec_forward(sd, cfg, xt, x2t, x3t, eps_z, code, multiplier=1.0,
     L = cfg.TRAIN.CLIP_LENGTH
     klw = l3w * multiplier if baseline_mode == "VAE_ANNEAL" else l3w  # utils.py:74
     muvars = encz_forward(split_sd(sd, "encz_model."), cfg, torch.cat([xt, x3t], 1), training, taps)
+    hd = cfg.MODEL.EXTRA.HD_Z
+    if not hd:                   # utils.py:82-83, 96-100: one [B,2Z,1,1] tensor, eps_z one [B,Z,1,1] tensor
+        muvars, eps_z = [muvars], ([eps_z] if torch.is_tensor(eps_z) else list(eps_z))
     mus = [mv[:, :Z] for mv in muvars]
     logvars = [mv[:, Z:] for mv in muvars]
     if sampling_mode == "prior_sampling":
         z = list(eps_z)  # utils.py:88-90
     else:
         z = reparam(mus, logvars, eps_z)
+    if not hd:
+        z = z[0]
     x1p, x2p, x3p = encdec_forward(split_sd(sd, "encdec_model."), cfg, xt, z, code, training, taps)
     lx1, lx2, lx3 = l1_loss(x1p, xt), l1_loss(x2p, x2t), l1_loss(x3p, x3t)
     kl = kl_loss(mus, logvars)

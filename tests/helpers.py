@@ -40,7 +40,8 @@ def golden(name):
 def case_inputs(name, gold):
     B, H, W, Z = [int(v) for v in gold["meta"]]
     xt, x2t, x3t = O.make_clips(name, B, H, W)
-    eps_z, code = O.make_eps(name, B, Z, H, W)
+    hd = bool(int(gold["hd_z"])) if "hd_z" in gold.files else True
+    eps_z, code = O.make_eps(name, B, Z, H, W, hd_z=hd)
     return B, H, W, Z, xt, x2t, x3t, eps_z, code
 
 

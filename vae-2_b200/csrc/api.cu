@@ -51,6 +51,14 @@ int vae2_code_broadcast(const float* code, void* dst, int dtype, int B, int Z, i
                         vae2_stream_t stream) {
     return code_broadcast(code, dst, dtype, B, Z, Zp, H, W, ld, S(stream));
 }
+int vae2_spatial_sum(const void* x, void* out, int dtype, int out_fp32, int B, int HW, int C, int ld, int out_ld, float scale,
+                     int accumulate, vae2_stream_t stream) {
+    return spatial_sum(x, out, dtype, out_fp32, B, HW, C, ld, out_ld, scale, accumulate, S(stream));
+}
+int vae2_spatial_bcast(const void* g, void* dx, int dtype, int g_fp32, int B, int HW, int C, int Cp, int ld, int g_ld,
+                       float scale, int accumulate, vae2_stream_t stream) {
+    return spatial_bcast(g, dx, dtype, g_fp32, B, HW, C, Cp, ld, g_ld, scale, accumulate, S(stream));
+}
 int vae2_pack_weights(const vae2_pack_desc* d, int n, vae2_stream_t stream) {
     return pack_weights(reinterpret_cast<const PackDesc*>(d), n, S(stream));
 }

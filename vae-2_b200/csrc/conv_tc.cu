@@ -656,7 +656,9 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
     int sg_max = (512 / ctas) / p.NT;
     if (sg_max > groups_total) sg_max = groups_total;
     if (sg_max < 1) return -1;
-    if (ctas > 1 && sg_max < groups_total) return -1;      // co-residency only when one set holds every accumulator
+    if (ctas > 1 && (sg_max < groups_total || p.NT > 64)) return -1;   // co-residency: one set holds every accumulator, narrow N
+                                                                      // (measured: 18->18 31.7 vs 35.9 us, 36->36 23.6 vs 27.5 us;
+                                                                      //  64->256 1x1 was 12 % slower with halved stages)
     int sg = 0, stages = 0, worst = 0;
     for (int cand = sg_max; cand >= 1; --cand) {
         const int nsets = (groups_total + cand - 1) / cand;

@@ -32,6 +32,10 @@ int nhwc_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, in
 int slice_copy(const void* src, void* dst, int dtype, long long P, int Cp, int ld_src, int ld_dst, int accumulate,
                cudaStream_t st);
 int code_broadcast(const float* code, void* dst, int dtype, int B, int Z, int Zp, int H, int W, int ld, cudaStream_t st);
+int spatial_sum(const void* x, void* out, int dtype, int out_fp32, int B, int HW, int C, int ld, int out_ld, float scale,
+                int accumulate, cudaStream_t st);
+int spatial_bcast(const void* g, void* dx, int dtype, int g_fp32, int B, int HW, int C, int Cp, int ld, int g_ld, float scale,
+                  int accumulate, cudaStream_t st);
 int pack_weights(const PackDesc* descs_dev, int n, cudaStream_t st);
 int unpack_wgrad(const PackDesc* descs_dev, int n, int accumulate, cudaStream_t st);
 

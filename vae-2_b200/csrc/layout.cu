@@ -179,4 +179,74 @@ int unpack_wgrad(const PackDesc* descs_dev, int n, int accumulate, cudaStream_t 
     return check_launch();
 }
 
+
+// ---------------------------------------------------------------------------
+// Per-sample spatial reductions / broadcasts (reference: nn.AdaptiveAvgPool2d((1,1)) of the non-HD_Z posterior head,
+// enc_hrnet.py:1023-1041, and the gradient of `_gen_code_map`'s spatial repeat of a per-sample z, :454-462).
+//   spatial_sum  : out[b][c] (=|+=) scale * sum_p x[b][p][c]     x act (T), out fp32 [B][out_ld] or act (T) [B][out_ld]
+//   spatial_bcast: dx[b][p][c] (=|+=) scale * g[b][c]            g fp32 or act (T), dx act (T)
+// ---------------------------------------------------------------------------
+template <typename T, typename U>
+__global__ void __launch_bounds__(256)
+spatial_sum_kernel(const T* __restrict__ x, U* __restrict__ out, int HW, int C, int ld, int out_ld, float scale, int accumulate) {
+    __shared__ float red[8][33];
+    const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), row = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < C)
+        for (int p = row; p < HW; p += 8) s += to_f<T>(x[((long long)b * HW + p) * ld + c]);
+    red[row][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (row == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x & 31];
+        t *= scale;
+        U* o = out + (long long)b * out_ld + c;
+        if (accumulate) t += to_f<U>(*o);
+        *o = from_f<U>(t);
+    }
+}
+
+template <typename T, typename U>
+__global__ void __launch_bounds__(256)
+spatial_bcast_kernel(const U* __restrict__ g, T* __restrict__ dx, int HW, int C, int Cp, int ld, int g_ld, float scale,
+                     int accumulate, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp);
+        const long long p = i / Cp;
+        const int b = (int)(p / HW);
+        float v = c < C ? scale * to_f<U>(g[(long long)b * g_ld + c]) : 0.f;
+        T* d = dx + p * ld + c;
+        if (accumulate) v += to_f<T>(*d);
+        *d = from_f<T>(v);
+    }
+}
+
+int spatial_sum(const void* x, void* out, int dtype, int out_fp32, int B, int HW, int C, int ld, int out_ld, float scale,
+                int accumulate, cudaStream_t st) {
+    if (B < 1 || HW < 1 || C < 1) return VAE2_ERR_ARG;
+    dim3 grid((C + 31) / 32, B);
+    if (dtype == VAE2_DT_F32)
+        spatial_sum_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, HW, C, ld, out_ld, scale, accumulate);
+    else if (out_fp32)
+        spatial_sum_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)out, HW, C, ld, out_ld, scale, accumulate);
+    else
+        spatial_sum_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, HW, C, ld, out_ld, scale, accumulate);
+    return check_launch();
+}
+
+int spatial_bcast(const void* g, void* dx, int dtype, int g_fp32, int B, int HW, int C, int Cp, int ld, int g_ld, float scale,
+                  int accumulate, cudaStream_t st) {
+    const long long total = (long long)B * HW * Cp;
+    if (total < 1) return VAE2_ERR_ARG;
+    const int grid = stream_grid(total, 256);
+    if (dtype == VAE2_DT_F32)
+        spatial_bcast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)g, (float*)dx, HW, C, Cp, ld, g_ld, scale, accumulate, total);
+    else if (g_fp32)
+        spatial_bcast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const float*)g, (__nv_bfloat16*)dx, HW, C, Cp, ld, g_ld, scale, accumulate, total);
+    else
+        spatial_bcast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)dx, HW, C, Cp, ld, g_ld, scale, accumulate, total);
+    return check_launch();
+}
+
 }  // namespace vae2

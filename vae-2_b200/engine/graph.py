@@ -395,7 +395,7 @@ class Plan:
         for o in self.ops:
             for a in o.writes():
                 a.root._nw += 1
-            if isinstance(o, (InputOp, GroupInputOp)) and o.needs_grad:
+            if isinstance(o, (InputOp, GroupInputOp, CodeOp)) and o.needs_grad:
                 for a in o.writes():
                     a.root._pin = True      # read by the eager epilogue AFTER the whole program: never recycled
             if isinstance(o, OutputOp):
@@ -448,11 +448,11 @@ class Plan:
         if self.prec.code == 1 and dev.type == "cuda" and self.use_tc:
             for o in convs:
                 g = o._geom()
-                o.engine = 1 if N.lib().vae2_conv2d_tc_supported(C.byref(g)) else 0
+                o.engine = 1 if (o.x.H * o.x.W > 1 and N.lib().vae2_conv2d_tc_supported(C.byref(g))) else 0
         # fp32 storage with the fwd/dgrad GEMMs on tensor cores through the exact 3-way bf16 split (opt-in:
         # its truncating fp32 accumulation is ~1e-6..1e-5 per conv)
         x3 = [o for o in convs if self.prec.code == 0 and self.fp32_tc not in ("0", "") and dev.type == "cuda"
-              and (self.fp32_tc == "all" or max(o.x.root_cp(), o.y.Cp) >= self.fp32_tc_min_lanes)
+              and (self.fp32_tc == "all" or max(o.x.root_cp(), o.y.Cp) >= self.fp32_tc_min_lanes) and o.x.H * o.x.W > 1
               and N.lib().vae2_conv2d_tf32_supported(C.byref(o._geom()))]
         tot3f = tot3b = 0
         for o in x3:
@@ -796,9 +796,10 @@ class CodeOp:
     def writes(self):
         return [self.dst]
 
-    def __init__(self, plan, slot, Z, dst):
+    def __init__(self, plan, slot, Z, dst, needs_grad=False):
         self.slot, self.Z, self.dst = slot, Z, dst
-        dst.needs_grad = False
+        self.needs_grad = needs_grad and plan.training       # a per-sample z that is a function of the posterior net
+        dst.needs_grad = self.needs_grad
 
     def emit_fwd(self, plan):
         pr = plan.prec
@@ -810,7 +811,14 @@ class CodeOp:
         plan.pre_fwd.append(run)
 
     def emit_bwd(self, plan):
-        pass
+        if not self.needs_grad:
+            return
+        pr, d = plan.prec, self.dst
+
+        def run(st, self=self):      # d z[b][c] += sum over the pixels of the map the code was repeated into
+            dst = plan.cur_input_grads[self.slot]
+            N.call.vae2_spatial_sum(d.grad().ptr, dst.data_ptr(), pr.code, 1, d.B, d.H * d.W, self.Z, d.ld, self.Z, 1.0, 1, st)
+        plan.post_bwd.append(run)
 
 
 class OutputOp:
@@ -1342,6 +1350,35 @@ class CopyOp:
         plan.bwd.append(lambda st: N.call.vae2_slice_copy(gd, gs, pr.code, s.npix, lanes, d.ld, s.ld, acc, st))
 
 
+class PoolOp:
+    """nn.AdaptiveAvgPool2d((1, 1)): out[b][0][0][c] = mean over the pixels of x[b]  (non-HD_Z posterior head,
+    enc_hrnet.py:1023-1041)."""
+
+    def __init__(self, plan, x, out=None):
+        self.x = x
+        self.out = out if out is not None else plan.new_act(x.C, 1, 1, name="pool", B=x.B)
+
+    def reads(self):
+        return [self.x]
+
+    def writes(self):
+        return [self.out]
+
+    def emit_fwd(self, plan):
+        pr, x, o = plan.prec, self.x, self.out
+        lanes, hw = min(x.Cp, o.Cp), x.H * x.W
+        plan.fwd.append(lambda st: N.call.vae2_spatial_sum(x.ptr, o.ptr, pr.code, 0, x.B, hw, lanes, x.ld, o.ld, 1.0 / hw, 0, st))
+
+    def emit_bwd(self, plan):
+        pr, x, o = plan.prec, self.x, self.out
+        if not x.needs_grad:
+            return
+        lanes, hw = min(x.Cp, o.Cp), x.H * x.W
+        acc = x.take_acc_flag()
+        gp, dxp = o.grad().ptr, x.grad().ptr
+        plan.bwd.append(lambda st: N.call.vae2_spatial_bcast(gp, dxp, pr.code, 0, x.B, hw, lanes, x.Cp, x.ld, o.ld, 1.0 / hw, acc, st))
+
+
 class TileOp:
     """dst[k*Bs + b] = src[b] for k < K: a feature computed once per context clip feeds all K latent draws stacked along
     the batch axis (K-sample inference, SURVEY.md §8 f1: the encoder trunk does not depend on z).  Forward only."""
@@ -1399,8 +1436,11 @@ class Recorder:
         self.n_in += 1
         return s
 
-    def code(self, slot, Z, dst):
-        self.plan.add(CodeOp(self.plan, slot, Z, dst))
+    def code(self, slot, Z, dst, needs_grad=False):
+        self.plan.add(CodeOp(self.plan, slot, Z, dst, needs_grad))
+
+    def pool(self, x):
+        return self.plan.add(PoolOp(self.plan, x)).out
 
     def output(self, act, dst_ctot=None, dst_coff=0, slot=None):
         if slot is None:

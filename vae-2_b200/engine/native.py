@@ -57,6 +57,8 @@ _PROTOS = {
     "vae2_act_to_nchw": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "vae2_slice_copy": [vp, vp, i32, i64, i32, i32, i32, i32, vp],
     "vae2_code_broadcast": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "vae2_spatial_sum": [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32, vp],
+    "vae2_spatial_bcast": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, vp],
     "vae2_pack_weights": [vp, i32, vp],
     "vae2_unpack_wgrad": [vp, i32, i32, vp],
     "vae2_pack_weights_tf32": [vp, i32, vp],

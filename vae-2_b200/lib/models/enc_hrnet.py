@@ -473,9 +473,10 @@ class HighResolutionNetED(HighResolutionNet):
         K = tag[1] if isinstance(tag, tuple) and tag[0] == "ksample" else 1
         KB = K * B                                  # plan.B; the context clips (and the encoder trunk) have B samples
         x = rec.input(Cx, H, W, needs[0], B=B)
-        z_slots = [rec.new_input_slot() for _ in range(4)] if coded else []
+        nz = 4 if self.hd_z else 1            # HD_Z: one latent map per branch; otherwise ONE per-sample z [B, Z, 1, 1]
+        z_slots = [rec.new_input_slot() for _ in range(nz)] if coded else []
         code_slot = rec.new_input_slot() if (coded and not self.is_baseline) else None
-        z_needs = needs[1:5] if coded else []
+        z_needs = needs[1:1 + nz] if coded else []
 
         def maps_for(first):
             pending = {}
@@ -505,8 +506,12 @@ class HighResolutionNetED(HighResolutionNet):
             preds.append((root, sl))
         # z inputs fan out into the three nets' concat buffers (enc_hrnet.py:825-826, 885, 943)
         for b in range(4 if coded else 0):
-            _, zc, zh, zw = shapes[1 + b]
-            rec.input(zc, zh, zw, z_needs[b], slot=z_slots[b], into=z_dsts[b])
+            if self.hd_z:
+                _, zc, zh, zw = shapes[1 + b]
+                rec.input(zc, zh, zw, z_needs[b], slot=z_slots[b], into=z_dsts[b])
+            else:                              # _gen_code_map(x_list, z): the per-sample z repeated over every map (:819)
+                for dst in z_dsts[b]:
+                    rec.code(z_slots[0], Z, dst, needs_grad=z_needs[0])
         # outputs in the reference's return order: (x1t, x2t, x3t) = (decp, enc, decf)   (:981)
         for root, sl in (preds[2], preds[0], preds[1]):
             slot = rec.new_output_slot()
@@ -519,10 +524,16 @@ class HighResolutionNetED(HighResolutionNet):
             raise NotImplementedError("vae2_b200: the IS_BASELINE ablation path is not built (SURVEY.md §8 scope)")
         inputs = [x]
         if self.enable_random_code:
-            if not (self.hd_z and isinstance(z, (list, tuple)) and len(z) == 4):
-                raise NotImplementedError("vae2_b200: HD_Z posterior maps (a list of 4 tensors) are required")
+            if self.hd_z:
+                if not (isinstance(z, (list, tuple)) and len(z) == 4):
+                    raise ValueError("vae2_b200: HD_Z expects z as a list of 4 latent maps")
+                zs = list(z)
+            else:
+                if not (torch.is_tensor(z) and z.dim() == 4 and z.shape[2:] == (1, 1)):
+                    raise ValueError("vae2_b200: without HD_Z, z is one tensor [B, Z, 1, 1]")
+                zs = [z]
             code = torch.randn(x.shape[0], self.z_dim, 1, 1, device=x.device).detach()   # reference :456
-            inputs += list(z) + [code]
+            inputs += zs + [code]
         x1, x2, x3 = self._run(inputs)
         return x1, x2, x3
 
@@ -554,8 +565,9 @@ class HighResolutionNetEDz(HighResolutionNet):
         return {"": L * 3 if self.extra.IS_BASELINE else L * 2}
 
     def _make_z_layer(self):
-        if not self.hd_z:
-            raise NotImplementedError("vae2_b200: only HD_Z posterior heads are built (SURVEY.md §8 a10)")
+        if not self.hd_z:      # reference :1023-1041: global average pool -> 1x1(+bias) -> BN -> ReLU -> 1x1(+bias)
+            return nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), _c(self.last_inp_channels, 512, 1, bias=True), _b(512),
+                                 nn.ReLU(inplace=True), _c(512, 2 * self.z_dim, 1, bias=True))
         layers = []
         for c in self.last_stage_channels:       # reference :1000-1022
             layers.append(nn.Sequential(_c(c, self.z_dim * 2, 1)) if c != self.z_dim * 2 else None)
@@ -563,6 +575,12 @@ class HighResolutionNetEDz(HighResolutionNet):
 
     def _record(self, rec, shapes, needs, tag):
         _, Cx, H, W = shapes[0]
+        if not self.hd_z:      # reference :1107-1116: up-sample + concat the four branches, then the pooled head
+            _, cat = self._emit_trunk(rec, "", rec.input(Cx, H, W, needs[0]), head_cat=True)
+            h = rec.conv_bn(rec.pool(cat), self.last_layer[1], self.last_layer[2], relu=True)
+            o = rec.conv(h, self.last_layer[4])
+            rec.output(o)
+            return [(o.C, 1, 1)]
         ys, _ = self._emit_trunk(rec, "", rec.input(Cx, H, W, needs[0]), head_cat=False)
         outs = [rec.conv(y, self.last_layer[i][0]) for i, y in enumerate(ys)]
         for o in outs:
@@ -570,7 +588,8 @@ class HighResolutionNetEDz(HighResolutionNet):
         return [(o.C, o.H, o.W) for o in outs]
 
     def forward(self, x, *args, **kwargs):
-        return list(self._run([x]))
+        outs = self._run([x])
+        return list(outs) if self.hd_z else outs[0]
 
 
 class HighResolutionNetDsc(HighResolutionNet):

@@ -214,8 +214,8 @@ class FullModel_encdec(nn.Module):
         if sampling_mode == "momentum_sampling":
             assert xt_last is not None
             assert x3t_last is not None
-        if is_baseline or baseline_mode == "DETERMINISTIC" or not self.encz_model.hd_z:
-            raise NotImplementedError("vae2_b200: baseline / non-HD_Z ablations are outside the built hot path")
+        if is_baseline or baseline_mode == "DETERMINISTIC":
+            raise NotImplementedError("vae2_b200: the baseline ablations are outside the built hot path")
         baseline_mode = baseline_mode or "VAE_NATIVE"
         self._anomoly_detection()
         B, Z = xt.shape[0], self.encz_model.z_dim
@@ -223,6 +223,11 @@ class FullModel_encdec(nn.Module):
         prior = sampling_mode == "prior_sampling"
 
         muvars = self.encz_model(x=torch.cat([xt, x3t], 1))                       # reference :77
+        hd = self.encz_model.hd_z
+        if not hd:                                 # one [B, 2Z, 1, 1] tensor (reference :82-83, :96-100)
+            muvars = [muvars]
+            if eps is not None and torch.is_tensor(eps):
+                eps = [eps]
         # eps in the reference's draw order: one randn per posterior map (:89-93)
         if eps is None:
             eps = [torch.randn(mv.shape[0], Z, mv.shape[2], mv.shape[3], device=mv.device) for mv in muvars]
@@ -232,6 +237,8 @@ class FullModel_encdec(nn.Module):
                 for i in range(n)]
         out = _E.elbo_terms(spec, 1, tensors)
         z_KL_loss, z = out[0][0], list(out[1:])
+        if not hd:
+            z = z[0]
 
         xt_predict, x2t_predict, x3t_predict = self.encdec_model(x=xt, z=z, is_baseline=False)   # :105
 
