@@ -25,7 +25,10 @@ g, d = build_product(cfg)
 O.fill_state_dict(g.state_dict(), seed_tag=name, mode="trained")
 B, H, W, Z, xt, x2t, x3t, eps_z, code = case_inputs(name, gold)
 assert B == world
+g.skip_dead_D_grads = "skip" in sys.argv[2:]         # eager GAN terms with the discriminators frozen in the G step
 g = torch.nn.SyncBatchNorm.convert_sync_batchnorm(g).to(dev).train()
+d = torch.nn.SyncBatchNorm.convert_sync_batchnorm(d).to(dev).train()
+dd = torch.nn.parallel.DistributedDataParallel(d, device_ids=[rank], find_unused_parameters=True)
 gd = torch.nn.parallel.DistributedDataParallel(g, device_ids=[rank], find_unused_parameters=True)
 sl = slice(rank, rank + 1)
 with RandnQueue([code[sl]]):
@@ -52,13 +55,30 @@ ok &= e2 < (1e-4 if prec == "fp32" else 8e-2)
 if prec == "fp32":
     norms = dict(zip(gold["g_grad_names"].tolist(), gold["g_grad_norms"]))
     en = np.array([abs(float(p.grad.double().norm()) - norms[k]) / norms[k] for k, p in g.named_parameters()
-                   if norms[k] > 1e-9 and ".0.bias" not in k])
+                   if norms[k] > 1e-9 and ".0.bias" not in k and p.grad is not None])
     msgs.append("DDP-averaged grad norms vs reference: median rel err %.2e, max %.2e" % (np.median(en), en.max()))
     ok &= bool(np.median(en) < 2e-2)
 sd = g.state_dict()
 e3 = rel_err(sd["encz_model.bn1.running_mean"], gold["after:encz_model.bn1.running_mean"])
 msgs.append("synced running_mean rel err %.2e" % e3)
 ok &= e3 < (1e-4 if prec == "fp32" else 5e-2)
+# D step (stacked passes, eager backward) under DDP + SyncBN against the reference's single-process B=2 D losses / grad norms
+x2_full = torch.from_numpy(gold["x2p"]).to(dev)
+dl = dd(x2t=x2t[sl].to(dev), x2t_predict=x2_full[sl])
+d.zero_grad()
+dl[0].backward()
+dv = torch.stack([l.detach().reshape(()) for l in dl])
+dist.all_reduce(dv)
+dv = (dv / world).cpu().numpy()
+drel = np.abs(dv - gold["d_losses"]) / np.abs(gold["d_losses"])
+msgs.append("D step: mean-of-rank losses vs reference B=2: max rel err %.2e" % drel.max())
+ok &= bool(drel.max() < (2e-4 if prec == "fp32" else 3e-2))
+if prec == "fp32":
+    dn = dict(zip(gold["d_grad_names"].tolist(), gold["d_grad_norms"]))
+    en = np.array([abs(float(p.grad.double().norm()) - dn[k]) / dn[k] for k, p in d.named_parameters()
+                   if dn[k] > 1e-9 and not k.endswith("last_layer.0.bias")])
+    msgs.append("D step: DDP-averaged grad norms vs reference: median rel err %.2e, max %.2e" % (np.median(en), en.max()))
+    ok &= bool(np.median(en) < 3e-2)
 plans = [p for m in g.modules() if hasattr(m, "_plans") for pool in m._plans().values() for p in pool]
 msgs.append("SyncBN collectives fwd %d for %d BNs" % (sum(p.n_collectives_fwd for p in plans),
                                                      sum(1 for m in g.modules() if isinstance(m, torch.nn.SyncBatchNorm))))
