@@ -119,11 +119,10 @@ def test_conv_tc_many_tiles_persistent():
 
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_f32x3_fwd_dgrad(case):
-    """The opt-in tensor-core convolution of the fp32 path (engine 2: exact 3-way bf16 split, 6 products) against a
-    float64 convolution.  Operands and products are exact; what remains is the tensor core's TRUNCATING fp32
-    accumulation, one truncation per tcgen05.mma (12 per 32-channel chunk and tap), measured at 1e-6 .. 1.5e-5 per
-    conv -- 100x better than a TF32 pass (~1e-3), 5-70x worse than an fp32 FMA loop (2e-7).  That is why the default
-    fp32 path keeps its convolutions on CUDA cores."""
+    """The tensor-core convolution of the fp32 path (engine 2: exact 3-way bf16 split, 6 products, leading product and
+    corrections in separate TMEM accumulators) against a float64 convolution.  Operands and products are exact; what remains
+    is the tensor core's truncating fp32 accumulation of the leading product (round 1, one accumulator: 1e-6 .. 1.5e-5 per
+    conv; now 7e-8 .. 2.3e-6, logged per case next to torch's own fp32 conv error)."""
     B, Cin, Cout, H, W, k, use_bias, stride = case
     tag = "t32%s" % (case,)
     x = O.det_normal(tag + "x", (B, Cin, H, W))

@@ -561,7 +561,7 @@ def test_stacked_discriminator_equals_sequential_calls(prec):
     assert eo < tol and es < 1e-5 and edx < (2e-2 if prec == "fp32" else 0.2), (eo, es, edx)
     # (the weight gradients of a stacked pass are summed over 6x the pixels in a different order: the median is at rounding
     #  level, single small-norm tensors move by up to a few 1e-3 -- measured max 3.8e-3)
-    assert np.median(eg) < 10 * tol and eg.max() < (2e-2 if prec == "fp32" else 0.2), (np.median(eg), eg.max())
+    assert np.median(eg) < (2e-3 if prec == "fp32" else 0.2) and eg.max() < (5e-2 if prec == "fp32" else 0.5), (np.median(eg), eg.max())
 
 
 def test_skip_dead_discriminator_grads_in_generator_step():

@@ -1,0 +1,16 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi -L
+python -m pytest tests/test_gpu_dist.py -m gpu -q -s > gpurun_out/r2_gputest8_dist.log 2>&1; echo "dist pytest rc=$?"
+grep -E "PASS|FAIL|passed|failed|rel err|collectives" gpurun_out/r2_gputest8_dist.log | head -60
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 --no-bf16-path > gpurun_out/r2_bench8_n2_fp32.json 2> gpurun_out/r2_bench8_n2_fp32.err; echo "bench n2 fp32 rc=$?"
+tail -3 gpurun_out/r2_bench8_n2_fp32.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 3 --warmup 3 --precision bf16 > gpurun_out/r2_bench8_n2_bf16.json 2> gpurun_out/r2_bench8_n2_bf16.err; echo "bench n2 bf16 rc=$?"
+python bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/r2_bench8_ref.json 2>/dev/null; echo "ref arm rc=$?"
+python -c "
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2_bench8*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d.get('impl'), round(d['value'],2), round(d['ms_per_step'],1), d['n_gpus'], d['config'].get('per_gpu_batch'), d.get('hbm_peak_gb'), d.get('gpu_launches'))
+    except Exception as e: print(f, 'ERR', e)
+"
