@@ -487,11 +487,24 @@ def main():
             line["cpu_baseline"], _ = cpu_baseline(cfg, H, W, steps=1, warmup=0)
         print(json.dumps(line), flush=True)
     if world > 1:
-        # leave without tearing NCCL down: destroying a process group whose collectives live inside captured
-        # CUDA graphs was seen to hang at exit; every rank has passed the final barrier by now
+        # Tear down in order: drop the plans (their captured CUDA graphs hold the NCCL collectives), then the process
+        # group.  Destroying a group whose collectives still sit inside live graphs was seen to hang at exit, so a
+        # watchdog ends the process if the orderly path does not finish; every rank has passed the final barrier by now.
         dist.barrier()
         sys.stdout.flush()
-        os._exit(0)
+        import gc
+        import threading
+        wd = threading.Timer(45.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        for m in list(g.modules()) + list(d.modules()):
+            if hasattr(m, "reset_plans"):
+                m.reset_plans()
+        del g, d, opt_g, opt_d
+        gc.collect()
+        torch.cuda.synchronize(dev)
+        dist.destroy_process_group()
+        wd.cancel()
 
 
 if __name__ == "__main__":

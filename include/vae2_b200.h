@@ -188,6 +188,25 @@ int vae2_bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* 
                              float* dbeta, int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres,
                              int groups, int stat_stride, vae2_stream_t stream);
 
+/* SyncBatchNorm (tools/train.py:217; torch nn/modules/_functions.py:39-122) as TWO cooperative launches per direction around
+ * the NCCL collective the host issues between them, every statistics group of a stacked pass in the same launch:
+ *   forward : vae2_bn_sync_fwd_stats  -> msg[g][3][Cp] = rank-local (count, mean, M2)      | all-gather of the messages |
+ *             vae2_bn_sync_fwd_apply  <- gathered: set r of group g at gathered + r*part_stride + g*3*Cp (n_parts = world)
+ *   backward: vae2_bn_sync_bwd(1,..)  -> msg[g][2][Cp] = rank-local (sum dyb, sum dyb*xhat), d(gamma)/d(beta) from them
+ *             | all-reduce | vae2_bn_sync_bwd(2,..) <- gsum[g][2][Cp], inv_count = 1 / (npix * world) */
+int vae2_bn_sync_fwd_stats(const void* y, float* partials, int dtype, int64_t npix, int C, int Cp, int ld_y, int groups,
+                           float* msg, vae2_stream_t stream);
+int vae2_bn_sync_fwd_apply(const void* y, const void* res, void* out, int dtype, int64_t npix, int C, int Cp, int ld_y,
+                           int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* mean,
+                           float* invstd, float* scale, float* shift, int relu, int groups, int stat_stride,
+                           const float* gathered, int n_parts, int64_t part_stride, vae2_stream_t stream);
+int vae2_bn_sync_bwd(int phase, const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                     int64_t npix, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                     const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                     int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
+                     int stat_stride, float* msg, const float* gsum, float inv_count, vae2_stream_t stream);
+
 /* ---- branch fusion / upsampling: HighResolutionModule.forward enc_hrnet.py:233-248, :833-839 -- */
 typedef struct { const void* ptr; int32_t H, W, ld; } vae2_fuse_src;        /* HOST array */
 typedef struct { void* ptr; int32_t ld, accumulate; } vae2_fuse_dst;         /* HOST array */

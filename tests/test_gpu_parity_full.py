@@ -658,3 +658,102 @@ def test_grouped_fused_bn_equals_per_group_calls(shape, G, relu, with_res, prec)
             dbeta=e_db, dres=e_dr)
     assert int(nbt) == G and e_out < tol and e_run < 1e-5, (int(nbt), e_out, e_run)
     assert e_dx < 5 * tol and e_dg < 5 * tol and e_db < 5 * tol and e_dr < 5 * tol, (e_dx, e_dg, e_db, e_dr)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,G,relu,with_res", [((8, 18, 17, 23), 2, True, True), ((4, 270, 9, 12), 1, False, False),
+                                                   ((12, 64, 16, 32), 3, True, False)])
+def test_syncbn_cooperative_halves_two_ranks_on_one_gpu(shape, G, relu, with_res, prec):
+    """The SyncBN path as the plans run it (vae2_bn_sync_fwd_stats | all-gather | vae2_bn_sync_fwd_apply and
+    vae2_bn_sync_bwd(1) | all-reduce | vae2_bn_sync_bwd(2)), two "ranks" emulated on one GPU: rank r holds half of the
+    samples of every statistics group, the collectives are a concatenation / a sum.  Must equal F.batch_norm over each
+    group's WHOLE batch (what torch's SyncBatchNorm computes), including the running statistics after G updates."""
+    code, tdt, al, tol = (0, torch.float32, 4, 2e-5) if prec == "fp32" else (1, torch.bfloat16, 8, 2e-2)
+    B, C_, H, W = shape
+    Bg, world = B // G, 2
+    Bl = Bg // world                           # samples per rank and group
+    Cp = (C_ + al - 1) // al * al
+    tag = "sbh%s" % (shape,)
+    y = O.det_normal(tag + "y", shape, 2.0, 0.5)
+    y[::2] += 0.6
+    res = O.det_normal(tag + "r", shape) if with_res else None
+    go = O.det_normal(tag + "go", shape)
+    if prec == "bf16":
+        y, go = y.bfloat16().float(), go.bfloat16().float()
+        res = res.bfloat16().float() if res is not None else None
+    gam, bet = O.det_uniform(tag + "g", (C_,), 0.5, 1.5), O.det_normal(tag + "b", (C_,), 0.1)
+    rm, rv = O.det_normal(tag + "rm", (C_,), 0.1), O.det_uniform(tag + "rv", (C_,), 0.5, 1.5)
+    yr = y.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if res is not None else None
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    rm_r, rv_r = rm.clone(), rv.clone()
+    outs = []
+    for gi in range(G):
+        sl = slice(gi * Bg, (gi + 1) * Bg)
+        o = F.batch_norm(yr[sl], rm_r, rv_r, gr, br, True, 0.01, 1e-5)
+        o = o + rr[sl] if rr is not None else o
+        outs.append(F.relu(o) if relu else o)
+    ref = torch.cat(outs, 0)
+    ref.backward(go)
+    # rank r's stacked tensor: for every group its Bl samples
+    idx = [torch.cat([torch.arange(gi * Bg + r * Bl, gi * Bg + (r + 1) * Bl) for gi in range(G)]) for r in range(world)]
+    f32 = dict(dtype=torch.float32, device=DEV)
+    P = Bl * H * W
+    total = G * 3 * Cp + 16                    # this BN's message inside a wider group message
+    gathered = torch.zeros(world * total, **f32)
+    ws = torch.zeros(N.lib().vae2_bn_max_partials() * 3 * Cp, **f32)
+    ya = [_to_act(y[i], code, tdt, Cp) for i in idx]
+    ga = [_to_act(go[i], code, tdt, Cp) for i in idx]
+    ra = [_to_act(res[i], code, tdt, Cp) for i in idx] if res is not None else [None, None]
+    for r in range(world):
+        N.call.vae2_bn_sync_fwd_stats(ya[r].data_ptr(), ws.data_ptr(), code, P, C_, Cp, Cp, G, gathered.data_ptr() + 4 * r * total, _st())
+    stat = [torch.zeros(G, 6, Cp, **f32) for _ in range(world)]
+    run = [(rm.to(DEV), rv.to(DEV), torch.zeros(1, dtype=torch.int64, device=DEV)) for _ in range(world)]
+    gd, bd = gam.to(DEV), bet.to(DEV)
+    oa = [torch.zeros_like(t) for t in ya]
+    for r in range(world):
+        sp = lambda j: stat[r][0, j].data_ptr()
+        N.call.vae2_bn_sync_fwd_apply(ya[r].data_ptr(), ra[r].data_ptr() if ra[r] is not None else None, oa[r].data_ptr(), code, P,
+                                      C_, Cp, Cp, Cp, Cp, gd.data_ptr(), bd.data_ptr(), run[r][0].data_ptr(), run[r][1].data_ptr(),
+                                      run[r][2].data_ptr(), 0.01, 1e-5, sp(0), sp(1), sp(2), sp(3), 1 if relu else 0, G, 6 * Cp,
+                                      gathered.data_ptr(), world, total, _st())
+    out = torch.zeros(shape)
+    for r in range(world):
+        out[idx[r]] = _from_act(oa[r], code, len(idx[r]), C_, H, W, Cp)
+    e_out = rel_err(out, ref.detach())
+    e_run = max(rel_err(run[r][0].cpu(), rm_r) for r in range(world)) + max(rel_err(run[r][1].cpu(), rv_r) for r in range(world))
+    assert all(int(run[r][2]) == G for r in range(world))
+    # backward
+    gmsg = [torch.zeros(G * 2 * Cp, **f32) for _ in range(world)]
+    dg = [torch.zeros(C_, **f32) for _ in range(world)]
+    db = [torch.zeros(C_, **f32) for _ in range(world)]
+    dya = [torch.zeros_like(t) for t in ya]
+    dra = [torch.zeros_like(t) if res is not None else None for t in ya]
+    mode = 0 if not relu else (1 if with_res else 2)
+
+    def bwd(phase, r, msg, gs):
+        sp = lambda j: stat[r][0, j].data_ptr()
+        N.call.vae2_bn_sync_bwd(phase, ga[r].data_ptr(), oa[r].data_ptr(), ya[r].data_ptr(), dya[r].data_ptr(),
+                                dra[r].data_ptr() if dra[r] is not None else None, ws.data_ptr(), code, P, C_, Cp, Cp, Cp, Cp, Cp, Cp,
+                                sp(0), sp(1), sp(2), sp(3), dg[r].data_ptr() if phase == 1 else None,
+                                db[r].data_ptr() if phase == 1 else None, 0, sp(4), sp(5), mode, 0, 0, G, 6 * Cp,
+                                msg, gs, 1.0 / (P * world), _st())
+    for r in range(world):
+        bwd(1, r, gmsg[r].data_ptr(), None)
+    gsum = gmsg[0] + gmsg[1]                   # the all-reduce
+    for r in range(world):
+        bwd(2, r, None, gsum.data_ptr())
+    dx = torch.zeros(shape)
+    dr = torch.zeros(shape)
+    for r in range(world):
+        dx[idx[r]] = _from_act(dya[r], code, len(idx[r]), C_, H, W, Cp)
+        if res is not None:
+            dr[idx[r]] = _from_act(dra[r], code, len(idx[r]), C_, H, W, Cp)
+    e_dx = rel_err(dx, yr.grad)
+    e_dg = rel_err(dg[0].cpu() + dg[1].cpu(), gr.grad)     # DDP sums / averages the per-rank parameter gradients
+    e_db = rel_err(db[0].cpu() + db[1].cpu(), br.grad)
+    e_dr = rel_err(dr, rr.grad) if res is not None else 0.0
+    log_err("syncbn_halves_%s_%s_G%d" % (prec, "x".join(map(str, shape)), G), out=e_out, running=e_run, dx=e_dx, dgamma=e_dg,
+            dbeta=e_db, dres=e_dr)
+    assert e_out < tol and e_run < 2e-5, (e_out, e_run)
+    assert e_dx < 5 * tol and e_dg < 5 * tol and e_db < 5 * tol and e_dr < 5 * tol, (e_dx, e_dg, e_db, e_dr)

@@ -185,6 +185,28 @@ int vae2_bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* 
                                scale, shift, dgamma, dbeta, accumulate_param, c1, c2, relu, acc_dy, acc_dres, groups,
                                stat_stride, S(stream));
 }
+int vae2_bn_sync_fwd_stats(const void* y, float* partials, int dtype, int64_t npix, int C, int Cp, int ld_y, int groups,
+                           float* msg, vae2_stream_t stream) {
+    return bn_sync_fwd_stats(y, partials, dtype, npix, C, Cp, ld_y, groups, msg, S(stream));
+}
+int vae2_bn_sync_fwd_apply(const void* y, const void* res, void* out, int dtype, int64_t npix, int C, int Cp, int ld_y,
+                           int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* mean,
+                           float* invstd, float* scale, float* shift, int relu, int groups, int stat_stride,
+                           const float* gathered, int n_parts, int64_t part_stride, vae2_stream_t stream) {
+    return bn_sync_fwd_apply(y, res, out, dtype, npix, C, Cp, ld_y, ld_res, ld_out, gamma, beta, running_mean, running_var,
+                             (long long*)num_batches_tracked, momentum, eps, mean, invstd, scale, shift, relu, groups,
+                             stat_stride, gathered, n_parts, part_stride, S(stream));
+}
+int vae2_bn_sync_bwd(int phase, const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                     int64_t npix, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                     const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                     int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
+                     int stat_stride, float* msg, const float* gsum, float inv_count, vae2_stream_t stream) {
+    return bn_sync_bwd(phase, g, a, y, dy, dres, partials, dtype, npix, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd,
+                       scale, shift, dgamma, dbeta, accumulate_param, c1, c2, relu, acc_dy, acc_dres, groups, stat_stride, msg,
+                       gsum, inv_count, S(stream));
+}
 int vae2_bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, vae2_stream_t stream) {
     return bn_bwd_finalize(partials, n_partials, C, Cp, sums, S(stream));
 }

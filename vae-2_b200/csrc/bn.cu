@@ -618,6 +618,14 @@ struct BnFwdArgs {
     int G;
     long long gs_y, gs_res, gs_out;
     int stat_stride;
+    // SyncBN halves (a collective sits between them): phase 0 = the whole BN; 1 = statistics + rank-local merge only,
+    // group g's (count, mean, M2) goes to msg + g*3*Cp; 2 = finalize from `ext_parts` gathered partial sets (set r of
+    // group g at ext + r*ext_stride + g*3*Cp) + apply.
+    int phase;
+    float* msg;
+    const float* ext;
+    int ext_parts;
+    long long ext_stride;
 };
 
 template <typename T>
@@ -630,26 +638,29 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
     const int grp = blockIdx.x / nbpg, lb = blockIdx.x - grp * nbpg;
     // parameters of the channel this CTA will finalize: cold in HBM, so fetched under the statistics pass
     float gm0 = 0.f, bt0 = 0.f, rm00 = 0.f, rv00 = 0.f;
-    if (threadIdx.x == 0 && (int)blockIdx.x < A.C) {
+    if (A.phase != 1 && threadIdx.x == 0 && (int)blockIdx.x < A.C) {
         gm0 = A.gamma[blockIdx.x]; bt0 = A.beta[blockIdx.x];
         if (A.running_mean != nullptr) { rm00 = A.running_mean[blockIdx.x]; rv00 = A.running_var[blockIdx.x]; }
     }
-    stats_to_partials<T>((const T*)A.y + grp * A.gs_y, A.partials, A.P, A.Cp, A.ld_y, sm, lb, nbpg);
-    prof_mark(A.prof, 1);
-    grid.sync();
+    if (A.phase != 2) {
+        stats_to_partials<T>((const T*)A.y + grp * A.gs_y, A.partials, A.P, A.Cp, A.ld_y, sm, lb, nbpg);
+        prof_mark(A.prof, 1);
+        grid.sync();
+    }
     prof_mark(A.prof, 2);
     // One CTA per channel: every thread fetches <= 3 partials at once (one L2 round trip for the whole merge),
     // warp butterflies, then the 8 warp results meet in shared memory.  Groups are finalized one after the other by
     // the same CTA so that the running statistics see their momentum updates in the reference's call order.
     for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {
-        const int n_parts = nbpg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int n_parts = A.phase == 2 ? A.ext_parts : nbpg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const long long part_stride = A.phase == 2 ? A.ext_stride : 3LL * A.Cp;
         float gm = gm0, bt = bt0, rm0 = rm00, rv0 = rv00;      // first channel: fetched before the statistics pass
-        if (threadIdx.x == 0 && c < A.C && c != blockIdx.x) {
+        if (A.phase != 1 && threadIdx.x == 0 && c < A.C && c != blockIdx.x) {
             gm = A.gamma[c]; bt = A.beta[c];
             if (A.running_mean != nullptr) { rm0 = A.running_mean[c]; rv0 = A.running_var[c]; }
         }
         for (int gq = 0; gq < A.G; ++gq) {
-            const float* parts = A.partials + (long long)gq * nbpg * 3 * A.Cp;
+            const float* parts = A.phase == 2 ? A.ext + (long long)gq * 3 * A.Cp : A.partials + (long long)gq * nbpg * 3 * A.Cp;
             float n = 0.f, mean = 0.f, m2 = 0.f;
             if (c < A.C) {
                 float a[3][3];
@@ -657,7 +668,7 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
                 for (int j = 0; j < 3; ++j) {
                     const int k = threadIdx.x + j * BN_THREADS;
                     const bool valid = k < n_parts;
-                    const float* p = parts + (long long)(valid ? k : 0) * 3 * A.Cp;
+                    const float* p = parts + (long long)(valid ? k : 0) * part_stride;
                     a[j][0] = valid ? __ldcg(p + c) : 0.f;
                     a[j][1] = __ldcg(p + A.Cp + c);
                     a[j][2] = __ldcg(p + 2 * A.Cp + c);
@@ -686,7 +697,10 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
                     }
                     n = nn;
                 }
-                if (lane == 0) {
+                if (lane == 0 && A.phase == 1) {               // rank-local (count, mean, M2) of this group -> the message
+                    float* o = A.msg + (long long)gq * 3 * A.Cp;
+                    o[c] = c < A.C ? n : 0.f; o[A.Cp + c] = c < A.C ? mean : 0.f; o[2 * A.Cp + c] = c < A.C ? m2 : 0.f;
+                } else if (lane == 0) {
                     const int so = gq * A.stat_stride + c;
                     if (c >= A.C) {
                         A.mean[so] = 0.f; A.invstd[so] = 0.f; A.scale[so] = 0.f; A.shift[so] = 0.f;
@@ -706,6 +720,7 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
             }
         }
     }
+    if (A.phase == 1) return;
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.nbt != nullptr) *A.nbt += A.G;
     prof_mark(A.prof, 3);
     grid.sync();
@@ -730,6 +745,12 @@ struct BnBwdArgs {
     int G;                                         // statistics groups, as in BnFwdArgs; d(gamma), d(beta) sum over them
     long long gs_g, gs_a, gs_y, gs_dy, gs_dres;
     int stat_stride;
+    // SyncBN halves: phase 1 = reduce + per-channel rank-local sums (group g's (sum dyb, sum dyb*xhat) to msg + g*2*Cp,
+    // d(gamma)/d(beta) from those LOCAL sums, as torch's SyncBatchNorm does); phase 2 = coefficients from the all-reduced
+    // sums at ext + g*2*Cp (inv_count covers every rank's pixels) + the elementwise pass.
+    int phase;
+    float* msg;
+    const float* ext;
 };
 
 template <typename T, int RELU, bool DRES>
@@ -744,16 +765,26 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
     const T* gp = (const T*)A.g + grp * A.gs_g;
     const T* ap = A.a != nullptr ? (const T*)A.a + grp * A.gs_a : nullptr;
     const T* yp = (const T*)A.y + grp * A.gs_y;
-    bwd_reduce_to_partials_t<T, RELU>(gp, ap, yp, A.partials, A.P, A.Cp, A.ld_g, A.ld_a, A.ld_y, A.mean + so_g,
-                                      A.invstd + so_g, sm, A.scale + so_g, A.shift != nullptr ? A.shift + so_g : nullptr, lb,
-                                      nbpg);
-    prof_mark(A.prof, 1);
-    grid.sync();
+    if (A.phase != 2) {
+        bwd_reduce_to_partials_t<T, RELU>(gp, ap, yp, A.partials, A.P, A.Cp, A.ld_g, A.ld_a, A.ld_y, A.mean + so_g,
+                                          A.invstd + so_g, sm, A.scale + so_g, A.shift != nullptr ? A.shift + so_g : nullptr,
+                                          lb, nbpg);
+        prof_mark(A.prof, 1);
+        grid.sync();
+    }
     prof_mark(A.prof, 2);
     for (int c = blockIdx.x; c < A.Cp; c += gridDim.x) {      // one CTA per channel, one L2 round trip per group
         const int n_parts = nbpg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         float t1 = 0.f, t2 = 0.f;                              // sums over the groups: parameter gradients
         for (int gq = 0; gq < A.G; ++gq) {
+            if (A.phase == 2) {                                // global sums arrive all-reduced: one value per channel
+                if (threadIdx.x == 0) {
+                    const float* e = A.ext + (long long)gq * 2 * A.Cp;
+                    A.c1[gq * A.stat_stride + c] = (c < A.C ? e[c] : 0.f) * A.inv_count;
+                    A.c2[gq * A.stat_stride + c] = (c < A.C ? e[A.Cp + c] : 0.f) * A.inv_count;
+                }
+                continue;
+            }
             const float* parts = A.partials + (long long)gq * nbpg * 2 * A.Cp;
             float s1 = 0.f, s2 = 0.f;
             if (c < A.C) {
@@ -774,16 +805,23 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
                 s1 = 0.f; s2 = 0.f;
 #pragma unroll
                 for (int w = 0; w < BN_THREADS / 32; ++w) { s1 += sm[w * 2]; s2 += sm[w * 2 + 1]; }
-                A.c1[gq * A.stat_stride + c] = s1 * A.inv_count;
-                A.c2[gq * A.stat_stride + c] = s2 * A.inv_count;
+                if (A.phase == 1) {
+                    float* o = A.msg + (long long)gq * 2 * A.Cp;
+                    o[c] = s1; o[A.Cp + c] = s2;
+                } else {
+                    A.c1[gq * A.stat_stride + c] = s1 * A.inv_count;
+                    A.c2[gq * A.stat_stride + c] = s2 * A.inv_count;
+                }
                 t1 += s1; t2 += s2;
             }
         }
+        if (A.phase == 2) continue;
         if (threadIdx.x == 0 && c < A.C) {
             if (A.dbeta != nullptr) A.dbeta[c] = A.acc_param ? A.dbeta[c] + t1 : t1;
             if (A.dgamma != nullptr) A.dgamma[c] = A.acc_param ? A.dgamma[c] + t2 : t2;
         }
     }
+    if (A.phase == 1) return;
     prof_mark(A.prof, 3);
     grid.sync();
     prof_mark(A.prof, 4);
@@ -902,7 +940,34 @@ int bn_fwd_fused_groups(const void* y, const void* res, void* out, float* partia
         groups > 64)
         return VAE2_ERR_ARG;
     BnFwdArgs A{g_bn_prof, y, res, out, partials, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
-                nbt, momentum, eps, mean, invstd, scale, shift, groups, P * ld_y, P * ld_res, P * ld_out, stat_stride};
+                nbt, momentum, eps, mean, invstd, scale, shift, groups, P * ld_y, P * ld_res, P * ld_out, stat_stride,
+                0, nullptr, nullptr, 0, 0};
+    return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
+}
+
+// SyncBN forward, first half: statistics of every group + rank-local merge -> msg[g][3][Cp] (one cooperative launch)
+int bn_sync_fwd_stats(const void* y, float* partials, int dtype, long long P, int C, int Cp, int ld_y, int groups, float* msg,
+                      cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_y % V || Cp / V > BN_THREADS || P < 1 || groups < 1 || groups > 64) return VAE2_ERR_ARG;
+    BnFwdArgs A{g_bn_prof, y, nullptr, nullptr, partials, P, C, Cp, ld_y, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                0.f, 0.f, nullptr, nullptr, nullptr, nullptr, groups, P * ld_y, 0, 0, 0, 1, msg, nullptr, 0, 0};
+    return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
+}
+
+// SyncBN forward, second half: finalize every group from `n_parts` gathered sets + running statistics + apply
+int bn_sync_fwd_apply(const void* y, const void* res, void* out, int dtype, long long P, int C, int Cp, int ld_y, int ld_res,
+                      int ld_out, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                      int relu, int groups, int stat_stride, const float* gathered, int n_parts, long long part_stride,
+                      cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V) || Cp / V > BN_THREADS || P < 1 || groups < 1 ||
+        groups > 64 || n_parts < 1 || n_parts > 3 * BN_THREADS)
+        return VAE2_ERR_ARG;
+    BnFwdArgs A{g_bn_prof, y, res, out, nullptr, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
+                nbt, momentum, eps, mean, invstd, scale, shift, groups, P * ld_y, P * ld_res, P * ld_out, stat_stride,
+                2, nullptr, gathered, n_parts, part_stride};
     return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
 }
 
@@ -930,7 +995,26 @@ int bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* dy, v
         return VAE2_ERR_ARG;
     BnBwdArgs A{g_bn_prof, g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
                 accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, 1.0f / (float)P, groups, P * ld_g,
-                P * ld_a, P * ld_y, P * ld_dy, P * ld_dres, stat_stride};
+                P * ld_a, P * ld_y, P * ld_dy, P * ld_dres, stat_stride, 0, nullptr, nullptr};
+    return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
+}
+
+// SyncBN backward halves (phase 1: reduce + local sums -> msg[g][2][Cp], d(gamma)/d(beta); phase 2: coefficients from the
+// all-reduced sums `gsum` with inv_count over ALL ranks' pixels + elementwise pass).  `dres` only matters in phase 2, but
+// both halves must name the same kernel variant, so it is passed to both.
+int bn_sync_bwd(int phase, const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups, int stat_stride,
+                float* msg, const float* gsum, float inv_count, cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_g % V || ld_y % V || (phase == 2 && ld_dy % V) || (relu == 1 && (a == nullptr || ld_a % V)) ||
+        (relu == 2 && shift == nullptr) || relu < 0 || relu > 2 || (dres && ld_dres % V) || Cp / V > BN_THREADS || P < 1 ||
+        groups < 1 || groups > 64 || (phase != 1 && phase != 2))
+        return VAE2_ERR_ARG;
+    BnBwdArgs A{g_bn_prof, g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
+                accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, inv_count, groups, P * ld_g,
+                P * ld_a, P * ld_y, P * ld_dy, P * ld_dres, stat_stride, phase, msg, gsum};
     return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
 }
 

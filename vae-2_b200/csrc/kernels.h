@@ -82,6 +82,18 @@ int bn_bwd_fused_groups(const void* g, const void* a, const void* y, void* dy, v
                         const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
                         int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
                         int stat_stride, cudaStream_t st);
+int bn_sync_fwd_stats(const void* y, float* partials, int dtype, long long P, int C, int Cp, int ld_y, int groups, float* msg,
+                      cudaStream_t st);
+int bn_sync_fwd_apply(const void* y, const void* res, void* out, int dtype, long long P, int C, int Cp, int ld_y, int ld_res,
+                      int ld_out, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      long long* nbt, float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                      int relu, int groups, int stat_stride, const float* gathered, int n_parts, long long part_stride,
+                      cudaStream_t st);
+int bn_sync_bwd(int phase, const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups, int stat_stride,
+                float* msg, const float* gsum, float inv_count, cudaStream_t st);
 int bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, cudaStream_t st);
 int bn_bwd_coeffs(const float* sums, int C, int Cp, float inv_count, float* dgamma, float* dbeta, int accumulate_param,
                   const float* sums_for_param, float* c1, float* c2, cudaStream_t st);

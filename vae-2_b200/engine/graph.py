@@ -1122,6 +1122,56 @@ class BnOp:
             plan.fwd.append(lambda st, pt=pt: N.call.vae2_bn_apply(pt.yp, pt.resp, pt.outp, pr.code, npix, lanes, ldy, ldr,
                                                                   ldo, pt.scale, pt.shift, relu, st))
 
+    def _emit_sync_fwd1(self, plan, msg_ptr):
+        """SyncBN forward, first half: statistics + rank-local merge of every group in ONE cooperative launch."""
+        pr, y = plan.prec, self.y
+        ws = self._scratch(plan).data_ptr()
+        p0, G, npix = self.parts[0], len(self.parts), self.npix_g
+        plan.fwd.append(lambda st: N.call.vae2_bn_sync_fwd_stats(p0.yp, ws, pr.code, npix, y.C, y.Cp, y.ld, G, msg_ptr, st))
+
+    def _emit_sync_fwd2(self, plan, gathered_ptr, world, stride):
+        """second half: finalize every group from the `world` gathered sets (+ running statistics) and apply."""
+        pr, y, out, res = plan.prec, self.y, self.out, self.res
+        ldr = res.ld if res is not None else 0
+        gp, bp, rm, rv, nbt, mom, eps = self._bn_ptrs()
+        relu = 1 if self.relu else 0
+        p0, G, npix = self.parts[0], len(self.parts), self.npix_g
+        plan.fwd.append(lambda st: N.call.vae2_bn_sync_fwd_apply(
+            p0.yp, p0.resp, p0.outp, pr.code, npix, y.C, y.Cp, y.ld, ldr, out.ld, gp, bp, rm, rv, nbt, mom, eps, p0.mean,
+            p0.invstd, p0.scale, p0.shift, relu, G, 6 * y.Cp, gathered_ptr, world, stride, st))
+
+    def _emit_sync_bwd(self, plan, phase, msg_ptr):
+        """SyncBN backward halves (phase 1 before, phase 2 after the all-reduce), every group in one cooperative launch."""
+        pr = plan.prec
+        y, out, res, g = self.y, self.out, self.res, self.g
+        npix, lanes, C_ = self.npix_g, self.lanes, y.C
+        ws = self._scratch(plan).data_ptr()
+        want_p = self.param_grads
+        dgam = plan.grad_ptr(self.bn.weight) if want_p else None
+        dbet = plan.grad_ptr(self.bn.bias) if want_p else None
+        relu = 0 if not self.relu else (1 if res is not None else 2)
+        p0, G = self.parts[0], len(self.parts)
+        has_dres = res is not None and res.needs_grad
+        if phase == 1:
+            # (the elementwise outputs are not touched in this half; the residual-gradient pointer only selects the variant)
+            self._sync_state = (y.grad(), res.grad() if has_dres else None)
+            dyb, dres = self._sync_state
+            gp0, dyp0, dres0 = g.ptr, dyb.ptr, (dres.ptr if dres is not None else None)
+            plan.bwd.append(lambda st: N.call.vae2_bn_sync_bwd(
+                1, gp0, p0.outp, p0.yp, dyp0, dres0, ws, pr.code, npix, C_, lanes, g.ld, out.ld, y.ld, dyb.ld,
+                res.ld if has_dres else 0, p0.mean, p0.invstd, p0.scale, p0.shift, dgam, dbet, 0, p0.c1, p0.c2, relu, 0, 0, G,
+                6 * y.Cp, msg_ptr, None, 0.0, st))
+            return
+        dyb, dres = self._sync_state
+        acc_dy = y.take_acc_flag()
+        acc_res = res.take_acc_flag() if has_dres else 0
+        gp0, dyp0, dres0 = g.ptr, dyb.ptr, (dres.ptr if dres is not None else None)
+        inv_count = 1.0 / (npix * plan.world_size)
+        plan.bwd.append(lambda st: N.call.vae2_bn_sync_bwd(
+            2, gp0, p0.outp, p0.yp, dyp0, dres0, ws, pr.code, npix, C_, lanes, g.ld, out.ld, y.ld, dyb.ld,
+            res.ld if has_dres else 0, p0.mean, p0.invstd, p0.scale, p0.shift, None, None, 0, p0.c1, p0.c2, relu, acc_dy,
+            acc_res, G, 6 * y.Cp, None, msg_ptr, inv_count, st))
+
     def emit_fwd(self, plan):
         """Stand-alone BN (its own collective under SyncBN)."""
         BnGroupOp(plan, [self]).emit_fwd(plan)
@@ -1228,14 +1278,23 @@ class BnGroupOp:
             offs.append(o)
         msg, gathered = torch.zeros(total, **f32), torch.zeros(plan.world_size * total, **f32)
         plan.keep += [msg, gathered]
+        # two cooperative launches per BN (all statistics groups in each) around the collective instead of
+        # stats | merge | finalize | apply per group (VAE2_SYNCBN_HALVES=0 restores the split kernels)
+        halves = os.environ.get("VAE2_SYNCBN_HALVES", "1") != "0" and all(m.out.Cp >= m.y.Cp for m in ms)
         for m, o in zip(ms, offs):
-            m._emit_stats(plan, merged_ptrs=[msg.data_ptr() + 4 * x for x in o])
+            if halves:
+                m._emit_sync_fwd1(plan, msg.data_ptr() + 4 * o[0])
+            else:
+                m._emit_stats(plan, merged_ptrs=[msg.data_ptr() + 4 * x for x in o])
         grp = plan.group
         plan.fwd.append(lambda st: dist.all_gather_into_tensor(gathered, msg, group=grp))
         plan.n_collectives_fwd += 1
         for m, o in zip(ms, offs):
-            m._emit_finalize(plan, parts_ptrs=[gathered.data_ptr() + 4 * x for x in o], n_parts=plan.world_size, stride=total)
-            m._emit_apply(plan)
+            if halves:
+                m._emit_sync_fwd2(plan, gathered.data_ptr() + 4 * o[0], plan.world_size, total)
+            else:
+                m._emit_finalize(plan, parts_ptrs=[gathered.data_ptr() + 4 * x for x in o], n_parts=plan.world_size, stride=total)
+                m._emit_apply(plan)
 
     def emit_bwd(self, plan):
         ms = list(reversed(self.members))
@@ -1259,7 +1318,11 @@ class BnGroupOp:
             offs.append(o)
         gsum = torch.zeros(total, **f32)
         plan.keep.append(gsum)
+        halves = os.environ.get("VAE2_SYNCBN_HALVES", "1") != "0" and all(m.lanes == m.y.Cp for m in ms)
         for m, o in zip(ms, offs):
+            if halves:
+                m._emit_sync_bwd(plan, 1, gsum.data_ptr() + 4 * o[0])
+                continue
             m._emit_bwd_reduce(plan)
             for pt, off in zip(m.parts, o):
                 dst, src, n = gsum[off:off + 2 * m.lanes], pt.sums, 2 * m.lanes
@@ -1268,7 +1331,10 @@ class BnGroupOp:
         plan.bwd.append(lambda st: dist.all_reduce(gsum, group=grp))
         plan.n_collectives_bwd += 1
         for m, o in zip(ms, offs):
-            m._emit_bwd_apply(plan, gsum_ptrs=[gsum.data_ptr() + 4 * x for x in o])
+            if halves:
+                m._emit_sync_bwd(plan, 2, gsum.data_ptr() + 4 * o[0])
+            else:
+                m._emit_bwd_apply(plan, gsum_ptrs=[gsum.data_ptr() + 4 * x for x in o])
 
 
 class FuseOp:

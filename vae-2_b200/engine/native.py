@@ -89,6 +89,11 @@ _PROTOS = {
                                  vp, i32, i32, i32, vp],
     "vae2_bn_bwd_fused_groups": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                                  i32, vp, vp, i32, i32, i32, i32, i32, vp],
+    "vae2_bn_sync_fwd_stats": [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp],
+    "vae2_bn_sync_fwd_apply": [vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp,
+                               i32, i32, i32, vp, i32, i64, vp],
+    "vae2_bn_sync_bwd": [i32, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                         i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, f32, vp],
     "vae2_fuse_sum": [C.POINTER(FuseSrc), i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "vae2_fuse_bwd_same": [vp, vp, C.POINTER(FuseDst), i32, i32, i64, i32, i32, i32, i32, vp],
     "vae2_fuse_bwd_up": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -97,8 +97,9 @@ def describe(name, args):
 
 
 class _TimedCaller:
-    SPIN_EVERY = 192          # launches per device-side spin
-    SPIN_CYCLES = 12_000_000  # ~6 ms at 1.9 GHz: longer than the host needs to enqueue SPIN_EVERY launches
+    SPIN_EVERY = 128          # launches per device-side spin
+    SPIN_CYCLES = 40_000_000  # ~20 ms at 1.9 GHz: well beyond what the host needs to enqueue SPIN_EVERY launches (~30 us each
+                              # with the two event records; cooperative launches more) -- a starved GPU would time host latency
 
     def __init__(self, records):
         self.records, self.n = records, 0
