@@ -26,6 +26,9 @@ TC_CASES = [  # (B, Cin, Cout, H, W, k, bias, stride)
     (1, 36, 72, 33, 47, 3, False, 2),     # stride 2, odd size (Ho = ceil(H/2))
     (1, 256, 36, 24, 40, 3, False, 2),    # transition1 new branch
     (2, 72, 144, 9, 12, 3, False, 2),
+    (4, 18, 18, 64, 128, 3, False, 1),    # halo weight gradient: several patches per split-K range (stage ring wraps)
+    (2, 30, 150, 19, 9, 3, False, 1),     # halo weight gradient: Cin_p=32, N=160 (3 x 160 TMEM columns), ragged patches
+    (1, 64, 72, 40, 24, 3, False, 1),     # halo weight gradient: Cin_p=64, two M=128 instructions per kernel row, N=80
 ]
 
 

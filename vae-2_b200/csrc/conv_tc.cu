@@ -604,6 +604,173 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long 
     }
 }
 
+// ---- weight gradient of 3x3 stride-1 layers with ONE halo tile per pixel patch --------------------------------------------
+// wgrad_tc_kernel fetches the nine tap-shifted x tiles of a patch separately: 9x the activation bytes through L2 -> shared
+// memory (ncu r2a, 18->18: 335 MB for a 67 MB problem; the kernel sits at 11 % of its HBM floor).  Here the patch is 16 rows
+// x 8 pixels and ONE TMA box [Cin_p][10][18] brings it with its halo.  The operands stay MN-major (rows = pixels = K), and
+// a tap is a descriptor, not a copy:
+//   * kernel row ky   -> start address shifted by ky box rows;
+//   * the two 8-pixel K groups of a 16-pixel K step are consecutive patch rows, one BOX row apart (SBO = 10 pixels);
+//   * the taps kx = 0,1,2 of one kernel row are stacked on the M axis as consecutive "atoms" ONE PIXEL apart (LBO = one
+//     row): M = 128 covers 4 atoms of 32 channels (the fourth, kx = 3, is junk and dropped in the epilogue) or 2 atoms of 64.
+// tools/probes/umma_mn_shift_probe.cu established on the device that MN-major descriptors take unaligned starts, an SBO of a
+// box row and overlapping atoms exactly (profiles/r2_probe_mn.txt).  Accumulators: one TMEM region per kernel row (and per
+// atom pair for 64 channels); split-K over patches with per-range partials, folded by wgrad_reduce_kernel as before.
+struct WHParams {
+    int B, H, W;
+    int Cin_p, Cout_p;          // Cin_p = 32 or 64 (one swizzle atom per pixel row), Cout_p <= 256
+    int atomB, NT;
+    int tiles_w, tiles_h, total_ptiles, nranges;
+    int mmas_per_row;           // 1 (Cin_p = 32: kx 0..3 in one M=128) or 2 (Cin_p = 64: kx {0,1} and {2,3})
+    int stages, tmem_cols;
+    float* ws;                  // [nranges][9][Cin_p][Cout_p]
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_ex(uint32_t saddr, uint32_t row_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WHParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t rowA = p.Cin_p * 2, rowB = p.atomB * 2;
+    const uint32_t a_bytes = kHaloBW * kHaloBH * rowA;                         // TMA transaction size of the halo tile
+    const uint32_t a_stage = (a_bytes + 4 * rowA + 1023) / 1024 * 1024;       // + the junk tap's overhang
+    const uint32_t atomB_bytes = 128 * rowB;
+    const uint32_t b_bytes = (uint32_t)(p.NT / p.atomB) * atomB_bytes;
+    const uint32_t stage_bytes = a_stage + ((b_bytes + 1023) / 1024) * 1024;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kMaxStages;
+    uint64_t* acc_full = bars + 2 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int range = blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int n_my = (p.total_ptiles - range + p.nranges - 1) / p.nranges;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_my; ++i) {
+                const int pt = range + i * p.nranges;
+                const int b = pt / per_img;
+                const int r = pt - b * per_img;
+                const int h0 = (r / p.tiles_w) * kHaloTH, w0 = (r % p.tiles_w) * kHaloTW;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full[stage], a_bytes + b_bytes);
+                tma_load_4d(sa, &map_x, &full[stage], 0, w0 - 1, h0 - 1, b);
+                tma_load_5d(sa + a_stage, &map_dy, &full[stage], 0, w0, h0, b, 0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = NT, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t atoms_per_mma = 128u / (uint32_t)p.Cin_p;            // 4 or 2 taps (kx) per instruction
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_my; ++i) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + a_stage;
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int j = 0; j < p.mmas_per_row; ++j) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((ky * p.mmas_per_row + j) * p.NT);
+                        for (int ks = 0; ks < kHaloTH / 2; ++ks) {             // 16 pixels = two patch rows per K step
+                            const uint32_t a0 = sa + (uint32_t)(((2 * ks + ky) * kHaloBW) + j * (int)atoms_per_mma) * rowA;
+                            umma_bf16(d_tmem, make_desc_mn_ex(a0, rowA, rowA, kHaloBW * rowA),
+                                      make_desc_mn(sb + (uint32_t)ks * 16 * rowB, rowB, atomB_bytes), idesc, (i | ks) ? 1u : 0u);
+                        }
+                    }
+                umma_commit(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        float* ws = p.ws + (size_t)range * 9 * p.Cin_p * p.Cout_p;
+        const int atoms_per_mma = 128 / p.Cin_p;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int j = 0; j < p.mmas_per_row; ++j) {
+                const int m = q * 32 + lane;                                    // accumulator row = (kx_local, ci)
+                const int kx = j * atoms_per_mma + m / p.Cin_p, ci = m % p.Cin_p;
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ky * p.mmas_per_row + j) * p.NT);
+                for (int c0 = 0; c0 < p.NT; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t0 + c0, v);
+                    tmem_ld_wait();
+                    if (kx < 3 && c0 < p.Cout_p) {
+                        float4* dst = reinterpret_cast<float4*>(ws + ((size_t)(ky * 3 + kx) * p.Cin_p + ci) * p.Cout_p + c0);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            dst[e] = n_my > 0 ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                                            __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// fills p (except ws); returns the workspace floats, < 0 when the shape is not a halo candidate
+static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p) {
+    if (const char* e = getenv("VAE2_WGRAD_HALO")) { if (atoi(e) == 0) return -1; }
+    if (g.k != 3 || g.stride != 1 || g.H != g.Ho || g.W != g.Wo) return -1;
+    if (!(g.Cin_p == 32 || g.Cin_p == 64) || g.ldx % 8 || g.Cout_p > 256 || g.Cout_p % 16) return -1;
+    p.B = g.B; p.H = g.H; p.W = g.W; p.Cin_p = g.Cin_p; p.Cout_p = g.Cout_p;
+    p.atomB = g.Cout_p % 64 == 0 ? 64 : (g.Cout_p % 32 == 0 ? 32 : 16);
+    p.NT = g.Cout_p;
+    p.mmas_per_row = g.Cin_p == 32 ? 1 : 2;
+    const int cols = 3 * p.mmas_per_row * p.NT;
+    if (cols > 512) return -1;
+    p.tmem_cols = next_pow2_cols(cols);
+    p.tiles_w = (g.W + kHaloTW - 1) / kHaloTW;
+    p.tiles_h = (g.H + kHaloTH - 1) / kHaloTH;
+    p.total_ptiles = g.B * p.tiles_w * p.tiles_h;
+    const int rowA = g.Cin_p * 2;
+    const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
+    const long long b_stage = ((long long)p.NT * 128 * 2 + 1023) / 1024 * 1024;
+    const int ctas = p.tmem_cols <= 256 ? 2 : 1;
+    int stages = (int)((kSmemBudget / ctas - 2048) / (a_stage + b_stage));
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return -1;
+    p.stages = stages;
+    int nranges = ctas * kNumSMs;
+    if (nranges > p.total_ptiles) nranges = p.total_ptiles;
+    p.nranges = nranges;
+    return (long long)nranges * 9 * g.Cin_p * g.Cout_p;
+}
+
 static int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
 // Fills p (everything except ws) and returns the workspace size in floats; <0 if unsupported.
@@ -928,11 +1095,6 @@ int conv_dgrad_tc(const void* dy, const void* wqT, void* dx, const ConvGeom& g, 
 
 namespace vae2 {
 
-long long conv_wgrad_tc_workspace(const ConvGeom& g) {
-    if (!conv_tc_supported(g)) return -1;
-    tc::WParams p;
-    return tc::plan_wgrad(g, p);
-}
 
 static int make_map5(tc::EncodeTiledFn enc, CUtensorMap* m, const void* base, int atom, int C, int boxC, int ld, int B, int H,
                      int W, int TW, int TH, int estride) {
@@ -946,15 +1108,64 @@ static int make_map5(tc::EncodeTiledFn enc, CUtensorMap* m, const void* base, in
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
 }
 
-// dwp [tap][Cin_p][Cout_p] fp32 (overwritten); ws: at least conv_wgrad_tc_workspace(g) floats
-int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const ConvGeom& g, cudaStream_t st) {
-    using namespace tc;
-    if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
-    WParams p;
-    if (plan_wgrad(g, p) < 0) return VAE2_ERR_UNSUPPORTED;
-    p.ws = ws;
+namespace tc {
+// one product's split-K partials: which kernel, how many slots, floats per slot
+struct WgradPlan {
+    bool halo;
+    WParams w;
+    WHParams h;
+    long long part;     // floats of all slots
+    int nslots;
+    long long n;        // floats of one slot = taps * Cin_p * Cout_p
+};
+
+static int plan_wgrad_any(const ConvGeom& g, WgradPlan& P) {
+    P.part = plan_wgrad_halo(g, P.h);
+    if (P.part > 0) {
+        P.halo = true; P.nslots = P.h.nranges; P.n = 9LL * g.Cin_p * g.Cout_p;
+        return 0;
+    }
+    P.halo = false;
+    P.part = plan_wgrad(g, P.w);
+    if (P.part < 0) return -1;
+    P.nslots = P.w.nranges; P.n = (long long)P.w.M_total * g.Cout_p;
+    return 0;
+}
+
+// ws[slot][tap][Cin_p][Cout_p] = partial weight gradients of bf16 x [B][H][W][ldx] and dy [B][Ho][Wo][ldy]
+static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGeom& g, const WgradPlan& P, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return VAE2_ERR_UNSUPPORTED;
     CUtensorMap map_x, map_dy;
+    if (P.halo) {
+        WHParams p = P.h;
+        p.ws = ws;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)g.Cin_p, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+            cuuint64_t strides[3] = {(cuuint64_t)g.ldx * 2, (cuuint64_t)g.W * g.ldx * 2, (cuuint64_t)g.H * g.W * g.ldx * 2};
+            cuuint32_t box[4] = {(cuuint32_t)g.Cin_p, (cuuint32_t)kHaloBW, (cuuint32_t)kHaloBH, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz(g.Cin_p), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return VAE2_ERR_ARG;
+        }
+        if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, kHaloTW, kHaloTH, 1)) return VAE2_ERR_ARG;
+        const int rowA = g.Cin_p * 2;
+        const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
+        const long long b_stage = ((long long)p.NT * 128 * 2 + 1023) / 1024 * 1024;
+        const size_t smem = (size_t)p.stages * (a_stage + b_stage) + 1024 + (2 * kMaxStages + 4) * 8 + 16;
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                return VAE2_ERR_CUDA;
+            attr_set = true;
+        }
+        wgrad_halo_kernel<<<p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
+        return check_launch();
+    }
+    WParams p = P.w;
+    p.ws = ws;
     if (make_map5(enc, &map_x, x, p.atomA, g.Cin_p, g.Cin_p, g.ldx, g.B, g.H, g.W, p.TW, p.TH, g.stride)) return VAE2_ERR_ARG;
     if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, p.TW, p.TH, 1)) return VAE2_ERR_ARG;
     const long long a_bytes = (long long)p.a_atoms_stage * p.KP * p.atomA * 2;
@@ -967,14 +1178,28 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
             return VAE2_ERR_CUDA;
         attr_set = true;
     }
-    note_kernel("tc::wgrad_tc_kernel");
     wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
-    if (int e = check_launch()) return e;
-    const long long n = (long long)p.M_total * g.Cout_p;
-    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(ws, dwp, n, p.nranges);
     return check_launch();
 }
+}  // namespace tc
 
+long long conv_wgrad_tc_workspace(const ConvGeom& g) {
+    if (!conv_tc_supported(g)) return -1;
+    tc::WgradPlan P;
+    return tc::plan_wgrad_any(g, P) ? -1 : P.part;
+}
+
+// dwp [tap][Cin_p][Cout_p] fp32 (overwritten); ws: at least conv_wgrad_tc_workspace(g) floats
+int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const ConvGeom& g, cudaStream_t st) {
+    using namespace tc;
+    if (!conv_tc_supported(g)) return VAE2_ERR_UNSUPPORTED;
+    WgradPlan P;
+    if (plan_wgrad_any(g, P)) return VAE2_ERR_UNSUPPORTED;
+    note_kernel(P.halo ? "tc::wgrad_halo_kernel" : "tc::wgrad_tc_kernel");
+    if (int e = wgrad_partials(x, dy, ws, g, P, st)) return e;
+    wgrad_reduce_kernel<<<(unsigned)((P.n / 4 + 31) / 32), 256, 0, st>>>(ws, dwp, P.n, P.nslots);
+    return check_launch();
+}
 
 // =================================================================================================
 // fp32 weight gradient on tcgen05 ("f32x2"): fp32 activations are split into two bf16 planes
@@ -1044,11 +1269,11 @@ static ConvGeom geom16(const ConvGeom& g) {
 long long conv_wgrad_f32x2_workspace(const ConvGeom& g) {
     const ConvGeom q = tc::geom16(g);
     if (!conv_tc_supported(q)) return -1;
-    tc::WParams p;
-    const long long part = tc::plan_wgrad(q, p);            // floats of ONE product's split-K slots
-    if (part < 0) return -1;
+    tc::WgradPlan P;
+    if (tc::plan_wgrad_any(q, P)) return -1;
+    const long long part = P.part;                          // floats of ONE product's split-K slots
     const long long nx = (long long)g.B * g.H * g.W * q.Cin_p, ny = (long long)g.B * g.Ho * g.Wo * q.Cout_p;
-    const long long dw16 = (long long)p.M_total * q.Cout_p;
+    const long long dw16 = P.n;
     auto al = [](long long b) { return (b + 255) / 256 * 256; };
     return al(2 * nx * 2) + al(2 * ny * 2) + al(3 * part * 4) + al(dw16 * 4);
 }
@@ -1057,9 +1282,9 @@ int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspac
     using namespace tc;
     const ConvGeom q = geom16(g);
     if (!conv_tc_supported(q) || g.Cin_p % 4 || g.Cout_p % 4 || g.ldx % 4 || g.ldy % 4) return VAE2_ERR_UNSUPPORTED;
-    WParams p;
-    const long long part = plan_wgrad(q, p);
-    if (part < 0) return VAE2_ERR_UNSUPPORTED;
+    WgradPlan P;
+    if (plan_wgrad_any(q, P)) return VAE2_ERR_UNSUPPORTED;
+    const long long part = P.part;
     const long long npx = (long long)g.B * g.H * g.W, npy = (long long)g.B * g.Ho * g.Wo;
     const long long nx = npx * q.Cin_p, ny = npy * q.Cout_p;
     auto al = [](long long b) { return (b + 255) / 256 * 256; };
@@ -1073,33 +1298,16 @@ int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspac
     float* slots = reinterpret_cast<float*>(w);
     w += al(3 * part * 4);
     float* dw16 = reinterpret_cast<float*>(w);
-    note_kernel("tc::wgrad_tc_kernel (f32x2 planes)");
+    note_kernel(P.halo ? "tc::wgrad_halo_kernel (f32x2 planes)" : "tc::wgrad_tc_kernel (f32x2 planes)");
     split_planes_kernel<<<stream_grid(npx * (q.Cin_p / 8), 256), 256, 0, st>>>(x, xh, xl, npx, g.Cin_p, g.ldx, q.Cin_p);
     split_planes_kernel<<<stream_grid(npy * (q.Cout_p / 8), 256), 256, 0, st>>>(dy, yh, yl, npy, g.Cout_p, g.ldy, q.Cout_p);
     if (int e = check_launch()) return e;
-    EncodeTiledFn enc = encode_fn();
-    const long long a_bytes = (long long)p.a_atoms_stage * p.KP * p.atomA * 2;
-    const long long b_bytes = (long long)p.NT * p.KP * 2;
-    const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return VAE2_ERR_CUDA;
-        attr_set = true;
-    }
     const __nv_bfloat16* xa[3] = {xl, xh, xh};      // smallest products first in the fold: lo*hi, hi*lo, hi*hi
     const __nv_bfloat16* ya[3] = {yh, yl, yh};
-    for (int t = 0; t < 3; ++t) {
-        CUtensorMap map_x, map_dy;
-        if (make_map5(enc, &map_x, xa[t], p.atomA, q.Cin_p, q.Cin_p, q.ldx, q.B, q.H, q.W, p.TW, p.TH, q.stride)) return VAE2_ERR_ARG;
-        if (make_map5(enc, &map_dy, ya[t], p.atomB, q.Cout_p, p.NT, q.ldy, q.B, q.Ho, q.Wo, p.TW, p.TH, 1)) return VAE2_ERR_ARG;
-        p.ws = slots + (long long)t * part;
-        wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
-        if (int e = check_launch()) return e;
-    }
-    const long long n = (long long)p.M_total * q.Cout_p;
-    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, 3 * p.nranges);
+    for (int t = 0; t < 3; ++t)
+        if (int e = wgrad_partials(xa[t], ya[t], slots + (long long)t * part, q, P, st)) return e;
+    const long long n = P.n;
+    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, 3 * P.nslots);
     const int total = g.k * g.k * g.Cin_p * g.Cout_p;
     crop_dw_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw16, dwp, g.k * g.k, g.Cin_p, g.Cout_p, q.Cin_p, q.Cout_p);
     return check_launch();
