@@ -158,6 +158,11 @@ def step_roofline(E, dev, step_fn, hbm_peak, tf_peak, src):
     fams = kp.by_kernel()
     total = sum(f["ms"] for f in fams) or 1.0
     top = fams[0]
+    if os.environ.get("VAE2_BENCH_SHAPES"):         # per (kernel, shape) table of the profiled iteration, for tuning
+        with open(os.environ["VAE2_BENCH_SHAPES"], "w") as fh:
+            for r in kp.rows()[:120]:
+                fh.write("%9.3f ms  n=%4d  %8.3f ms/launch  %7.1f GB/s %7.1f TF/s  %-58s %s\n" % (
+                    r["ms"], r["n"], r["ms"] / r["n"], r["bytes"] / r["ms"] / 1e6, r["flop"] / r["ms"] / 1e9, r["kernel"], r["shape"]))
 
     def fr(r):
         t = r["ms"] * 1e-3

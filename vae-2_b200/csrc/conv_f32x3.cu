@@ -72,6 +72,63 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, ui
         ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// epilogue warps 6..9 (TMEM -> registers -> fp32 global): D_main + D_corr (+bias) (+previous value)
+__device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                          int warp, int lane) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int total = p.total_tiles, gstride = gridDim.x, n_tiles = p.n_tiles;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ri = row / p.TW, rj = row % p.TW;
+    const int two_acc = p.acc_stages == 2, NT = p.NT, Cn = p.Cn, accumulate = p.accumulate;
+    const float* bias = p.bias;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
+        const int as = two_acc ? (it & 1) : 0;
+        const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
+        const int nt = tile % n_tiles;
+        const int pt = tile / n_tiles;
+        const int b = pt / per_img;
+        const int r = pt - b * per_img;
+        const int gi = (r / p.tiles_w) * p.TH + ri, gj = (r % p.tiles_w) * p.TW + rj;
+        const bool in_img = gi < p.MH && gj < p.MW;
+        const int h = gi * p.sO + p.oh_off, w = gj * p.sO + p.ow_off;
+        mbar_wait(&acc_full[as], use & 1);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * NT);
+        float* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t v[16], u[16];
+            tmem_ld16(t0 + c0, v);               // D_main
+            tmem_ld16(t0 + NT + c0, u);          // D_corr
+            tmem_ld_wait();
+            const int n = nt * NT + c0;
+            if (in_img) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int nn = n + 4 * i;
+                    if (nn < Cn) {                      // Cn is a multiple of 4
+                        float4 f = make_float4(__uint_as_float(v[4 * i]) + __uint_as_float(u[4 * i]),
+                                               __uint_as_float(v[4 * i + 1]) + __uint_as_float(u[4 * i + 1]),
+                                               __uint_as_float(v[4 * i + 2]) + __uint_as_float(u[4 * i + 2]),
+                                               __uint_as_float(v[4 * i + 3]) + __uint_as_float(u[4 * i + 3]));
+                        if (bias != nullptr) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + nn));
+                            f.x += bb.x; f.y += bb.y; f.z += bb.z; f.w += bb.w;
+                        }
+                        float4* dst = reinterpret_cast<float4*>(orow + nn);
+                        if (accumulate) { const float4 o = *dst; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
+                        *dst = f;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -224,57 +281,176 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             }
         }
     } else {
-        // ================= epilogue warps 6..9 (TMEM -> registers -> fp32 global) =================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int ri = row / p.TW, rj = row % p.TW;
-        const int two_acc = p.acc_stages == 2, NT = p.NT, Cn = p.Cn, accumulate = p.accumulate;
-        const float* bias = p.bias;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
-            const int as = two_acc ? (it & 1) : 0;
-            const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
-            const int nt = tile % n_tiles;
-            const int pt = tile / n_tiles;
-            const int b = pt / per_img;
-            const int r = pt - b * per_img;
-            const int gi = (r / p.tiles_w) * p.TH + ri, gj = (r % p.tiles_w) * p.TW + rj;
-            const bool in_img = gi < p.MH && gj < p.MW;
-            const int h = gi * p.sO + p.oh_off, w = gj * p.sO + p.ow_off;
-            mbar_wait(&acc_full[as], use & 1);
-            tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * NT);
-            float* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
-            for (int c0 = 0; c0 < NT; c0 += 16) {
-                uint32_t v[16], u[16];
-                tmem_ld16(t0 + c0, v);               // D_main
-                tmem_ld16(t0 + NT + c0, u);          // D_corr
-                tmem_ld_wait();
-                const int n = nt * NT + c0;
-                if (in_img) {
+        epilogue_loop(p, tmem_base, acc_full, acc_empty, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- 3x3 stride-1 layers: ONE halo tile per patch and K chunk -------------------------------------------------------------
+// conv_f32x3_kernel gathers and splits the shifted tile of every tap: nine times the loads and nine times the split
+// arithmetic for a 3x3 layer, and its four producer warps are what the kernel waits for (in-step profile r2, 64->64 3x3:
+// 209 cycles per tcgen05.mma issued, against ~32 for the instruction itself).  Here the patch is 16 rows x 8 pixels and the
+// producers split its 18 x 10 halo box ONCE per 32-channel chunk into three bf16 planes; a tap is then only a different
+// start row of the K-major A descriptor (8-pixel row groups one box row apart, SBO = 10 rows; the swizzle is a function
+// of the absolute shared-memory address -- same trick as conv_tc_halo_kernel, tools/probes/umma_shift_probe.cu).
+// Weights stream through their own ring, one (chunk, tap) box of three planes per slot.
+constexpr int kHTW = 8, kHTH = 16, kHBW = kHTW + 2, kHBH = kHTH + 2;
+constexpr int kHaloRows = kHBW * kHBH;                       // 180 pixels
+constexpr int kHaloPlane = (kHaloRows * 64 + 1023) / 1024 * 1024;
+constexpr int kHaloItems = kHaloRows * 4;                    // (pixel, 8-channel group) work items of one stage
+constexpr int kHaloIters = (kHaloItems + 127) / 128;
+constexpr int kMaxWStages = 8, kMaxAStages = 3;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_f32x3_halo_kernel(const __grid_constant__ CUtensorMap map_w, const Params p, const int a_stages, const int w_stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t w_tx = 3u * (uint32_t)(p.NT * 64);
+    const uint32_t w_stage = (w_tx + 1023u) & ~1023u;
+    const uint32_t a_stage = 3 * kHaloPlane;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem + (size_t)a_stages * a_stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)w_stages * w_stage);
+    uint64_t* a_full = bars;                            // [kMaxAStages]  4 producer warps
+    uint64_t* a_empty = a_full + kMaxAStages;           // [kMaxAStages]  tcgen05.commit
+    uint64_t* w_full = a_empty + kMaxAStages;           // [kMaxWStages]  expect_tx
+    uint64_t* w_empty = w_full + kMaxWStages;           // [kMaxWStages]  tcgen05.commit
+    uint64_t* acc_full = w_empty + kMaxWStages;         // [2]
+    uint64_t* acc_empty = acc_full + 2;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a_stages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int total = p.total_tiles, gstride = gridDim.x, kchunks = p.kchunks;
+
+    if (warp < 4) {
+        // ================= A producers: halo gather + split + swizzled store =================
+        const int tid = threadIdx.x;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gstride) {
+            const int b = tile / per_img;
+            const int r = tile - b * per_img;
+            const int h0 = (r / p.tiles_w) * kHTH - 1, w0 = (r % p.tiles_w) * kHTW - 1;
+            const float* img = p.a + (long long)b * p.AH * p.AW * p.lda;
+            for (int kc = 0; kc < kchunks; ++kc) {
+                float4 v[kHaloIters][2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int nn = n + 4 * i;
-                        if (nn < Cn) {                      // Cn is a multiple of 4
-                            float4 f = make_float4(__uint_as_float(v[4 * i]) + __uint_as_float(u[4 * i]),
-                                                   __uint_as_float(v[4 * i + 1]) + __uint_as_float(u[4 * i + 1]),
-                                                   __uint_as_float(v[4 * i + 2]) + __uint_as_float(u[4 * i + 2]),
-                                                   __uint_as_float(v[4 * i + 3]) + __uint_as_float(u[4 * i + 3]));
-                            if (bias != nullptr) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + nn));
-                                f.x += bb.x; f.y += bb.y; f.z += bb.z; f.w += bb.w;
-                            }
-                            float4* dst = reinterpret_cast<float4*>(orow + nn);
-                            if (accumulate) { const float4 o = *dst; f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w; }
-                            *dst = f;
-                        }
+                for (int i = 0; i < kHaloIters; ++i) {             // loads first: in flight while the slot drains
+                    const int item = i * 128 + tid;
+                    const int row = item >> 2, c = kc * KC + (item & 3) * 8;
+                    const int ih = h0 + row / kHBW, iw = w0 + row % kHBW;
+                    const bool ok = item < kHaloItems && ih >= 0 && ih < p.AH && iw >= 0 && iw < p.AW;
+                    const float* src = img + ((long long)(ok ? ih : 0) * p.AW + (ok ? iw : 0)) * p.lda + c;
+                    v[i][0] = (ok && c < p.Ck) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i][1] = (ok && c + 4 < p.Ck) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&a_empty[stage], phase ^ 1);
+                uint8_t* a1 = smem + (size_t)stage * a_stage;
+#pragma unroll
+                for (int i = 0; i < kHaloIters; ++i) {
+                    const int item = i * 128 + tid;
+                    if (item < kHaloItems) {
+                        const int row = item >> 2, j = item & 3;
+                        const float xs[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+                        uint4 o1, o2, o3;
+                        __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(&o1);
+                        __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(&o2);
+                        __nv_bfloat16* h3 = reinterpret_cast<__nv_bfloat16*>(&o3);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) split3(xs[e], h1[e], h2[e], h3[e]);
+                        const uint32_t off = (uint32_t)row * 64 + (((uint32_t)j ^ (uint32_t)((row >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4*>(a1 + off) = o1;
+                        *reinterpret_cast<uint4*>(a1 + kHaloPlane + off) = o2;
+                        *reinterpret_cast<uint4*>(a1 + 2 * kHaloPlane + off) = o3;
                     }
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[stage]);
+                if (++stage == a_stages) { stage = 0; phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+    } else if (warp == 5) {
+        // ================= weight TMA producer: one (chunk, tap) box of three planes per slot =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gstride)
+                for (int kc = 0; kc < kchunks; ++kc)
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&w_empty[stage], phase ^ 1);
+                        mbar_expect_tx(&w_full[stage], w_tx);
+                        tma_load_4d(wsm + (size_t)stage * w_stage, &map_w, &w_full[stage], kc * KC, 0, p.tap_w[tap], 0);
+                        if (++stage == w_stages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t hi_w = desc_hi_word(64);
+            const uint32_t hi_a = ((uint32_t)(kHBW * 64) >> 4) | (1u << 14) | (4u << 29);     // SBO = one box row
+            const uint32_t lo_flags = 1u << 16;
+            const uint32_t a_base = smem_u32(smem), w_base = smem_u32(wsm);
+            const uint32_t w_step = (uint32_t)(p.NT * 64) >> 4, a_step = (uint32_t)kHaloPlane >> 4;
+            const int two_acc = p.acc_stages == 2, NT = p.NT;
+            int sa = 0, sw = 0, it = 0;
+            uint32_t pa = 0, pw = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
+                const int as = two_acc ? (it & 1) : 0;
+                const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
+                mbar_wait(&acc_empty[as], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * NT), d_corr = d_main + (uint32_t)NT;
+                uint32_t accum = 0;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_stage_addr = a_base + (uint32_t)sa * a_stage;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&w_full[sw], pw);
+                        tc_fence_after();
+                        const uint32_t ta = a_stage_addr + (uint32_t)((p.tap_dh[tap] + 1) * kHBW + (p.tap_dw[tap] + 1)) * 64u;
+                        const uint32_t a1 = ((ta >> 4) & 0x3FFFu) | lo_flags, a2 = a1 + a_step, a3 = a2 + a_step;
+                        const uint32_t w1 = (((w_base + (uint32_t)sw * w_stage) >> 4) & 0x3FFFu) | lo_flags, w2 = w1 + w_step, w3 = w2 + w_step;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w3 + 2 * k, hi_w, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
+                        accum = 1;
+                        umma_commit(&w_empty[sw]);
+                        if (++sw == w_stages) { sw = 0; pw ^= 1; }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        epilogue_loop(p, tmem_base, acc_full, acc_empty, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -380,23 +556,12 @@ static int launch_t32(const t32::Launch& L, cudaStream_t st) {
     p.kchunks = L.Kf / KC;
     t32_ntile(L.Cn, &p.n_tiles, &p.NT);
     if (p.n_tiles * p.NT != L.Nf) return VAE2_ERR_ARG;
-    int tw = 128;
-    while (tw > 8 && tw / 2 >= L.MW) tw >>= 1;
-    p.TW = tw; p.TH = 128 / tw;
-    p.tiles_w = (L.MW + p.TW - 1) / p.TW;
-    p.tiles_h = (L.MH + p.TH - 1) / p.TH;
-    p.total_tiles = L.B * p.tiles_w * p.tiles_h * p.n_tiles;
-    const int stage_bytes = 3 * kABytes + (3 * p.NT * 64 + 1023) / 1024 * 1024;
-    int stages = kSmemBudget / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return VAE2_ERR_UNSUPPORTED;
-    p.stages = stages;
+    p.accumulate = L.accumulate;
+    p.a = L.a; p.bias = L.bias; p.out = L.out;
     p.acc_stages = (4 * p.NT <= 512) ? 2 : 1;          // two accumulators (main + correction) per stage
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_stages * 2 * p.NT) p.tmem_cols <<= 1;
     if (p.tmem_cols > 512) return VAE2_ERR_UNSUPPORTED;
-    p.accumulate = L.accumulate;
-    p.a = L.a; p.bias = L.bias; p.out = L.out;
 
     CUtensorMap map_w;
     {
@@ -409,6 +574,49 @@ static int launch_t32(const t32::Launch& L, cudaStream_t st) {
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return VAE2_ERR_ARG;
     }
+    // ---- halo path: 3x3, unit strides, one N tile ----
+    {
+        bool halo = L.ntaps == 9 && L.sA == 1 && L.sO == 1 && L.oh_off == 0 && L.ow_off == 0 && p.n_tiles == 1 &&
+                    L.MH == L.AH && L.MW == L.AW && L.MH >= 4 && L.MW >= 4;
+        for (int i = 0; halo && i < 9; ++i) halo = L.dh[i] >= -1 && L.dh[i] <= 1 && L.dw[i] >= -1 && L.dw[i] <= 1;
+        if (const char* e = getenv("VAE2_F32X3_HALO")) { if (atoi(e) == 0) halo = false; }
+        const int w_stage = (3 * p.NT * 64 + 1023) / 1024 * 1024;
+        const int bar_bytes = 1024 + (2 * kMaxAStages + 2 * kMaxWStages + 4) * 8 + 16;
+        const int budget = 227 * 1024 - bar_bytes;
+        int a_stages = kMaxAStages;
+        while (a_stages > 2 && (budget - a_stages * 3 * kHaloPlane) / w_stage < 4) --a_stages;
+        int w_stages = (budget - a_stages * 3 * kHaloPlane) / w_stage;
+        if (w_stages > kMaxWStages) w_stages = kMaxWStages;
+        if (halo && w_stages >= 2) {
+            p.TW = kHTW; p.TH = kHTH;
+            p.tiles_w = (L.MW + kHTW - 1) / kHTW;
+            p.tiles_h = (L.MH + kHTH - 1) / kHTH;
+            p.total_tiles = L.B * p.tiles_w * p.tiles_h;
+            p.stages = a_stages;
+            const size_t smem = (size_t)a_stages * 3 * kHaloPlane + (size_t)w_stages * w_stage + bar_bytes;
+            static bool attr_set_h = false;
+            if (!attr_set_h) {
+                if (cudaFuncSetAttribute(conv_f32x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                    return VAE2_ERR_CUDA;
+                attr_set_h = true;
+            }
+            const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+            note_kernel("t32::conv_f32x3_halo_kernel");
+            conv_f32x3_halo_kernel<<<grid, kThreads, smem, st>>>(map_w, p, a_stages, w_stages);
+            return check_launch();
+        }
+    }
+    int tw = 128;
+    while (tw > 8 && tw / 2 >= L.MW) tw >>= 1;
+    p.TW = tw; p.TH = 128 / tw;
+    p.tiles_w = (L.MW + p.TW - 1) / p.TW;
+    p.tiles_h = (L.MH + p.TH - 1) / p.TH;
+    p.total_tiles = L.B * p.tiles_w * p.tiles_h * p.n_tiles;
+    const int stage_bytes = 3 * kABytes + (3 * p.NT * 64 + 1023) / 1024 * 1024;
+    int stages = kSmemBudget / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return VAE2_ERR_UNSUPPORTED;
+    p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {

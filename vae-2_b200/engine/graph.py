@@ -497,9 +497,10 @@ class Plan:
         # kernel (csrc/conv_tc.cu: conv_wgrad_f32x2); one shared workspace, the convs run one after another
         x2_bytes = 0
         if self.training and os.environ.get("VAE2_FP32_TC_WGRAD", "1") != "0":
+            wmin = int(os.environ.get("VAE2_FP32_TC_WGRAD_MIN_LANES", "40"))
             for o in x3:
                 need = N.lib().vae2_conv2d_wgrad_f32x2_workspace(C.byref(o._geom()))
-                o.wgrad_x2 = need > 0 and o.conv.weight.requires_grad
+                o.wgrad_x2 = need > 0 and o.conv.weight.requires_grad and max(o.x.root_cp(), o.y.Cp) >= wmin
                 if o.wgrad_x2:
                     x2_bytes = max(x2_bytes, need)
         self.wgrad_x2_ws = torch.empty(x2_bytes, dtype=torch.uint8, device=dev) if x2_bytes else None

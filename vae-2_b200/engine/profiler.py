@@ -50,9 +50,9 @@ def describe(name, args):
                                                    g.stride, g.H, g.W, g.B)
         kern = N.lib().vae2_last_kernel().decode() or name
         if name == "vae2_conv2d_wgrad_tc":
-            kern = "tc::wgrad_tc_kernel+wgrad_reduce_kernel"
+            kern = kern + "+wgrad_reduce_kernel"
         if name == "vae2_conv2d_wgrad_f32x2":
-            kern = "split_planes+3x tc::wgrad_tc_kernel+reduce (fp32 wgrad)"
+            kern = "split_planes+3x " + kern.replace(" (f32x2 planes)", "") + "+reduce (fp32 wgrad)"
         return kern, shape, flop, float(by)
     if name in ("vae2_bn_fwd_fused", "vae2_bn_fwd_fused_groups"):
         code, npix, C_ = args[4], args[5], args[6]
