@@ -161,60 +161,62 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 
     if (warp < 4) {
         // ================= A producers: gather + split + swizzled store =================
-        const int row = threadIdx.x;                       // tile row = pixel of the patch
-        const int ri = row / p.TW, rj = row % p.TW;
-        const uint32_t swz = (uint32_t)((row >> 1) & 3);
+        // Work item = (tile row, 8-channel group): consecutive threads take consecutive 32-byte pieces of a pixel's 128
+        // bytes, so a warp's 16-byte load covers four whole pixel rows (was: one pixel per thread, 32 lines per request).
+        // The loads of item i+1 are in flight while the slot of item i drains (an item = (tile, tap, 32-channel chunk)).
+        const int tid = threadIdx.x;
         int stage = 0;
         uint32_t phase = 0;
-        // Software-pipelined gather: the loads of item i+1 are in flight while item i is split and stored (ncu r2b: with the
-        // loads issued and consumed in the same iteration the four producer warps were latency-bound -- issue slots 22 %,
-        // tensor pipe 18 %).  An item = (tile, tap, 32-channel chunk) = one pipeline stage.
-        int c_tile = blockIdx.x, c_tap = 0, c_kc = 0;      // cursor of the next item to fetch
-        auto fetch = [&](float4 (&v)[8]) -> bool {
-            if (c_tile >= total) return false;
-            const int pt = c_tile / n_tiles;
+        for (int tile = blockIdx.x; tile < total; tile += gstride) {
+            const int pt = tile / n_tiles;
             const int b = pt / per_img;
             const int r = pt - b * per_img;
-            const int gi = (r / p.tiles_w) * p.TH + ri, gj = (r % p.tiles_w) * p.TW + rj;
-            const int ih = gi * p.sA + p.tap_dh[c_tap], iw = gj * p.sA + p.tap_dw[c_tap];
-            const bool ok = gi < p.MH && gj < p.MW && ih >= 0 && ih < p.AH && iw >= 0 && iw < p.AW;
-            const float* src = p.a + (((long long)b * p.AH + (ok ? ih : 0)) * p.AW + (ok ? iw : 0)) * p.lda;
+            const int gi0 = (r / p.tiles_w) * p.TH, gj0 = (r % p.tiles_w) * p.TW;
+            const float* img = p.a + (long long)b * p.AH * p.AW * p.lda;
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+                long long off[4];
+                bool okr[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = c_kc * KC + j * 4;
-                v[j] = (ok && c < p.Ck) ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (i * 128 + tid) >> 2;
+                    const int gi = gi0 + row / p.TW, gj = gj0 + row % p.TW;
+                    const int ih = gi * p.sA + dh, iw = gj * p.sA + dw;
+                    okr[i] = gi < p.MH && gj < p.MW && ih >= 0 && ih < p.AH && iw >= 0 && iw < p.AW;
+                    off[i] = ((long long)(okr[i] ? ih : 0) * p.AW + (okr[i] ? iw : 0)) * p.lda;
+                }
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    float4 v[4][2];
+                    const int c = kc * KC + (tid & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float* src = img + off[i] + c;
+                        v[i][0] = (okr[i] && c < p.Ck) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i][1] = (okr[i] && c + 4 < p.Ck) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* a1 = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = (i * 128 + tid) >> 2, j = tid & 3;
+                        const float xs[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+                        uint4 o1, o2, o3;
+                        __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(&o1);
+                        __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(&o2);
+                        __nv_bfloat16* h3 = reinterpret_cast<__nv_bfloat16*>(&o3);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) split3(xs[e], h1[e], h2[e], h3[e]);
+                        const uint32_t o = (uint32_t)row * 64 + (((uint32_t)j ^ (uint32_t)((row >> 1) & 3)) << 4);   // 64-byte swizzle
+                        *reinterpret_cast<uint4*>(a1 + o) = o1;
+                        *reinterpret_cast<uint4*>(a1 + kABytes + o) = o2;
+                        *reinterpret_cast<uint4*>(a1 + 2 * kABytes + o) = o3;
+                    }
+                    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[stage]);
+                    if (++stage == nstage) { stage = 0; phase ^= 1; }
+                }
             }
-            if (++c_kc == kchunks) { c_kc = 0; if (++c_tap == ntaps) { c_tap = 0; c_tile += gstride; } }
-            return true;
-        };
-        float4 v[8], nx[8];
-        bool have = fetch(v);
-        while (have) {
-            const bool have_next = fetch(nx);
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* a1 = smem + (size_t)stage * stage_bytes + (size_t)row * 64;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {          // 16-byte chunk j of the 64-byte row = channels 8j .. 8j+7
-                const float xs[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w,
-                                     v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
-                uint4 o1, o2, o3;
-                __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(&o1);
-                __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(&o2);
-                __nv_bfloat16* h3 = reinterpret_cast<__nv_bfloat16*>(&o3);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split3(xs[e], h1[e], h2[e], h3[e]);
-                const uint32_t off = ((uint32_t)j ^ swz) << 4;     // 64-byte swizzle: chunk ^ ((row >> 1) & 3)
-                *reinterpret_cast<uint4*>(a1 + off) = o1;
-                *reinterpret_cast<uint4*>(a1 + kABytes + off) = o2;
-                *reinterpret_cast<uint4*>(a1 + 2 * kABytes + off) = o3;
-            }
-            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[stage]);
-            if (++stage == nstage) { stage = 0; phase ^= 1; }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = nx[j];
-            have = have_next;
         }
     } else if (warp == 5) {
         // ================= weight TMA producer =================
@@ -256,23 +258,19 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * NT), d_corr = d_main + (uint32_t)NT;
                 uint32_t accum = 0;
                 for (int ks = 0; ks < nks; ++ks) {
+                    // K steps of 16 channels in this chunk: the last chunk of a 36/72/144/272-lane tensor holds <= 16
+                    const int nk = (p.Ck - (ks % kchunks) * KC > 16) ? 2 : 1;
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a1 = a_lo0 + (uint32_t)stage * stage_step, a2 = a1 + a_step, a3 = a2 + a_step;
                     const uint32_t w1 = a1 + w_off, w2 = w1 + w_step, w3 = w2 + w_step;
                     // correction products (smallest first) into D_corr, the leading product into D_main
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w3 + 2 * k, hi, idesc, 1u);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
+                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
+                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w3 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
+                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
                     accum = 1;
                     umma_commit(&empty[stage]);
                     if (++stage == nstage) { stage = 0; phase ^= 1; }
@@ -418,6 +416,7 @@ conv_f32x3_halo_kernel(const __grid_constant__ CUtensorMap map_w, const Params p
                 const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * NT), d_corr = d_main + (uint32_t)NT;
                 uint32_t accum = 0;
                 for (int kc = 0; kc < kchunks; ++kc) {
+                    const int nk = (p.Ck - kc * KC > 16) ? 2 : 1;      // K steps of 16 channels in this chunk
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
                     const uint32_t a_stage_addr = a_base + (uint32_t)sa * a_stage;
@@ -427,18 +426,12 @@ conv_f32x3_halo_kernel(const __grid_constant__ CUtensorMap map_w, const Params p
                         const uint32_t ta = a_stage_addr + (uint32_t)((p.tap_dh[tap] + 1) * kHBW + (p.tap_dw[tap] + 1)) * 64u;
                         const uint32_t a1 = ((ta >> 4) & 0x3FFFu) | lo_flags, a2 = a1 + a_step, a3 = a2 + a_step;
                         const uint32_t w1 = (((w_base + (uint32_t)sw * w_stage) >> 4) & 0x3FFFu) | lo_flags, w2 = w1 + w_step, w3 = w2 + w_step;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w3 + 2 * k, hi_w, idesc, 1u);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, 1u);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
+                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
+                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w3 + 2 * k, hi_w, idesc, 1u);
+                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
+                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, 1u);
+                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
+                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
                         accum = 1;
                         umma_commit(&w_empty[sw]);
                         if (++sw == w_stages) { sw = 0; pw ^= 1; }

@@ -451,9 +451,17 @@ class Plan:
                 o.engine = 1 if (o.x.H * o.x.W > 1 and N.lib().vae2_conv2d_tc_supported(C.byref(g))) else 0
         # fp32 storage with the fwd/dgrad GEMMs on tensor cores through the exact 3-way bf16 split (opt-in:
         # its truncating fp32 accumulation is ~1e-6..1e-5 per conv)
+        # which layers: >= 40 lanes on either side, and the 3x3 stride-1 layers from 36 lanes up (they take the halo-tile
+        # kernel: measured 36->36 0.40 vs 0.60 ms on conv_direct at B=24, but 18->18 0.78 vs 0.65 ms -- N=32 MMAs cost
+        # what N=64 ones do)
+        hmin = int(os.environ.get("VAE2_FP32_TC_HALO_MIN_LANES", "36"))
+
+        def on_tc(o):
+            if self.fp32_tc == "all" or max(o.x.root_cp(), o.y.Cp) >= self.fp32_tc_min_lanes:
+                return True
+            return o.conv.kernel_size[0] == 3 and o.conv.stride[0] == 1 and min(o.x.root_cp(), o.y.Cp) >= hmin
         x3 = [o for o in convs if self.prec.code == 0 and self.fp32_tc not in ("0", "") and dev.type == "cuda"
-              and (self.fp32_tc == "all" or max(o.x.root_cp(), o.y.Cp) >= self.fp32_tc_min_lanes) and o.x.H * o.x.W > 1
-              and N.lib().vae2_conv2d_tf32_supported(C.byref(o._geom()))]
+              and on_tc(o) and o.x.H * o.x.W > 1 and N.lib().vae2_conv2d_tf32_supported(C.byref(o._geom()))]
         tot3f = tot3b = 0
         for o in x3:
             o.engine = 2
