@@ -44,7 +44,7 @@ struct Params {
     int taps;
     signed char tap_dh[9], tap_dw[9], tap_w[9];
     int kchunks;
-    int NT, n_tiles, TW, TH, tiles_w, tiles_h, total_tiles, stages, tmem_cols, acc_stages, accumulate;
+    int NT, n_tiles, TW, TH, tiles_w, tiles_h, total_tiles, stages, tmem_cols, acc_stages, acc_blocks, accumulate;
     const float* a;
     const float* bias;
     float* out;
@@ -72,6 +72,38 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, ui
         ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// The six products of one 16-channel K step.  The issuing thread is the bottleneck of these kernels (in-step profile:
+// ~90 cycles per tcgen05.mma whatever its N), so products that share an A plane are issued as ONE instruction whose B
+// operand is the stack of weight planes (they lie back to back in shared memory, N = 2*NT or 3*NT rows):
+//   blocks == 3, 3*NT <= 256 :  a1 x [w1 w2 w3] -> C0 C1 C2 ;  a2 x [w1 w2] -> C1 C2 ;  a3 x w1 -> C2          (3 instructions)
+//   blocks == 3, 2*NT <= 256 :  a1 x [w1 w2] -> C0 C1 ;  a1 x w3 -> C2 ;  a2 x [w1 w2] -> C1 C2 ;  a3 x w1 -> C2  (4)
+//   blocks == 2              :  the six products one by one, corrections (smallest first) -> C1, a1 x w1 -> C0      (6)
+// C0 only ever receives the leading product a1*w1; the correction blocks are added to it in the epilogue.
+__device__ __forceinline__ void issue_kstep(int blocks, uint32_t NT, uint32_t d0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t hi_a,
+                                            uint32_t w1, uint32_t w_step, uint32_t hi_w, uint32_t idesc0, uint32_t first) {
+    const uint32_t acc = first ? 0u : 1u;
+    const uint32_t w2 = w1 + w_step, w3 = w2 + w_step;
+    const uint32_t idesc1 = idesc0 | ((NT >> 3) << 17), idesc2 = idesc0 | ((2 * NT >> 3) << 17), idesc3 = idesc0 | ((3 * NT >> 3) << 17);
+    if (blocks == 3 && 3 * NT <= 256) {
+        umma_bf16_lohi(d0, a1, hi_a, w1, hi_w, idesc3, acc);
+        umma_bf16_lohi(d0 + NT, a2, hi_a, w1, hi_w, idesc2, 1u);
+        umma_bf16_lohi(d0 + 2 * NT, a3, hi_a, w1, hi_w, idesc1, 1u);
+    } else if (blocks == 3) {
+        umma_bf16_lohi(d0, a1, hi_a, w1, hi_w, idesc2, acc);
+        umma_bf16_lohi(d0 + 2 * NT, a1, hi_a, w3, hi_w, idesc1, acc);
+        umma_bf16_lohi(d0 + NT, a2, hi_a, w1, hi_w, idesc2, 1u);
+        umma_bf16_lohi(d0 + 2 * NT, a3, hi_a, w1, hi_w, idesc1, 1u);
+    } else {
+        const uint32_t dc = d0 + NT;
+        umma_bf16_lohi(dc, a3, hi_a, w1, hi_w, idesc1, acc);
+        umma_bf16_lohi(dc, a1, hi_a, w3, hi_w, idesc1, 1u);
+        umma_bf16_lohi(dc, a2, hi_a, w2, hi_w, idesc1, 1u);
+        umma_bf16_lohi(dc, a2, hi_a, w1, hi_w, idesc1, 1u);
+        umma_bf16_lohi(dc, a1, hi_a, w2, hi_w, idesc1, 1u);
+        umma_bf16_lohi(d0, a1, hi_a, w1, hi_w, idesc1, acc);
+    }
+}
+
 // epilogue warps 6..9 (TMEM -> registers -> fp32 global): D_main + D_corr (+bias) (+previous value)
 __device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
                                           int warp, int lane) {
@@ -80,7 +112,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_bas
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ri = row / p.TW, rj = row % p.TW;
-    const int two_acc = p.acc_stages == 2, NT = p.NT, Cn = p.Cn, accumulate = p.accumulate;
+    const int two_acc = p.acc_stages == 2, NT = p.NT, Cn = p.Cn, accumulate = p.accumulate, blocks = p.acc_blocks;
     const float* bias = p.bias;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
@@ -95,13 +127,21 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_bas
         const int h = gi * p.sO + p.oh_off, w = gj * p.sO + p.ow_off;
         mbar_wait(&acc_full[as], use & 1);
         tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * NT);
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * blocks * NT);
         float* orow = p.out + (((long long)b * p.OH + h) * p.OW + w) * p.ldo;
         for (int c0 = 0; c0 < NT; c0 += 16) {
             uint32_t v[16], u[16];
-            tmem_ld16(t0 + c0, v);               // D_main
-            tmem_ld16(t0 + NT + c0, u);          // D_corr
-            tmem_ld_wait();
+            tmem_ld16(t0 + c0, v);               // leading product
+            tmem_ld16(t0 + NT + c0, u);          // corrections
+            if (blocks == 3) {
+                uint32_t u2[16];
+                tmem_ld16(t0 + 2 * NT + c0, u2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) + __uint_as_float(u2[i]));
+            } else {
+                tmem_ld_wait();
+            }
             const int n = nt * NT + c0;
             if (in_img) {
 #pragma unroll
@@ -241,13 +281,13 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         // ================= MMA issuer =================
         if (lane == 0) {
             // D = f32, A = B = bf16, K-major both, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);      // N is OR-ed in per instruction
             const uint32_t hi = desc_hi_word(64);
             const uint32_t lo_flags = 1u << 16;
             const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | lo_flags;
             const uint32_t stage_step = stage_bytes >> 4, a_step = kABytes >> 4, w_off = (3 * kABytes) >> 4;
             const uint32_t w_step = (uint32_t)(p.NT * 64) >> 4;          // planes are packed back to back by the TMA box
-            const int nks = ntaps * kchunks, two_acc = p.acc_stages == 2, NT = p.NT;
+            const int nks = ntaps * kchunks, two_acc = p.acc_stages == 2, NT = p.NT, blocks = p.acc_blocks;
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
@@ -255,23 +295,18 @@ conv_f32x3_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
                 mbar_wait(&acc_empty[as], (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * NT), d_corr = d_main + (uint32_t)NT;
-                uint32_t accum = 0;
+                const uint32_t d0 = tmem_base + (uint32_t)(as * blocks * NT);
+                uint32_t first = 1;
                 for (int ks = 0; ks < nks; ++ks) {
                     // K steps of 16 channels in this chunk: the last chunk of a 36/72/144/272-lane tensor holds <= 16
-                    const int nk = (p.Ck - (ks % kchunks) * KC > 16) ? 2 : 1;
+                    const bool two_k = p.Ck - (ks % kchunks) * KC > 16;
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a1 = a_lo0 + (uint32_t)stage * stage_step, a2 = a1 + a_step, a3 = a2 + a_step;
-                    const uint32_t w1 = a1 + w_off, w2 = w1 + w_step, w3 = w2 + w_step;
-                    // correction products (smallest first) into D_corr, the leading product into D_main
-                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
-                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w3 + 2 * k, hi, idesc, 1u);
-                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
-                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi, w1 + 2 * k, hi, idesc, 1u);
-                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi, w2 + 2 * k, hi, idesc, 1u);
-                    for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi, w1 + 2 * k, hi, idesc, (accum | (uint32_t)k));
-                    accum = 1;
+                    const uint32_t w1 = a1 + w_off;
+                    issue_kstep(blocks, (uint32_t)NT, d0, a1, a2, a3, hi, w1, w_step, hi, idesc0, first);
+                    if (two_k) issue_kstep(blocks, (uint32_t)NT, d0, a1 + 2, a2 + 2, a3 + 2, hi, w1 + 2, w_step, hi, idesc0, 0u);
+                    first = 0;
                     umma_commit(&empty[stage]);
                     if (++stage == nstage) { stage = 0; phase ^= 1; }
                 }
@@ -399,13 +434,13 @@ conv_f32x3_halo_kernel(const __grid_constant__ CUtensorMap map_w, const Params p
     } else if (warp == 4) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
             const uint32_t hi_w = desc_hi_word(64);
             const uint32_t hi_a = ((uint32_t)(kHBW * 64) >> 4) | (1u << 14) | (4u << 29);     // SBO = one box row
             const uint32_t lo_flags = 1u << 16;
             const uint32_t a_base = smem_u32(smem), w_base = smem_u32(wsm);
             const uint32_t w_step = (uint32_t)(p.NT * 64) >> 4, a_step = (uint32_t)kHaloPlane >> 4;
-            const int two_acc = p.acc_stages == 2, NT = p.NT;
+            const int two_acc = p.acc_stages == 2, NT = p.NT, blocks = p.acc_blocks;
             int sa = 0, sw = 0, it = 0;
             uint32_t pa = 0, pw = 0;
             for (int tile = blockIdx.x; tile < total; tile += gstride, ++it) {
@@ -413,10 +448,10 @@ conv_f32x3_halo_kernel(const __grid_constant__ CUtensorMap map_w, const Params p
                 const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
                 mbar_wait(&acc_empty[as], (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * NT), d_corr = d_main + (uint32_t)NT;
-                uint32_t accum = 0;
+                const uint32_t d0 = tmem_base + (uint32_t)(as * blocks * NT);
+                uint32_t first = 1;
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    const int nk = (p.Ck - kc * KC > 16) ? 2 : 1;      // K steps of 16 channels in this chunk
+                    const bool two_k = p.Ck - kc * KC > 16;            // K steps of 16 channels in this chunk
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
                     const uint32_t a_stage_addr = a_base + (uint32_t)sa * a_stage;
@@ -425,14 +460,10 @@ conv_f32x3_halo_kernel(const __grid_constant__ CUtensorMap map_w, const Params p
                         tc_fence_after();
                         const uint32_t ta = a_stage_addr + (uint32_t)((p.tap_dh[tap] + 1) * kHBW + (p.tap_dw[tap] + 1)) * 64u;
                         const uint32_t a1 = ((ta >> 4) & 0x3FFFu) | lo_flags, a2 = a1 + a_step, a3 = a2 + a_step;
-                        const uint32_t w1 = (((w_base + (uint32_t)sw * w_stage) >> 4) & 0x3FFFu) | lo_flags, w2 = w1 + w_step, w3 = w2 + w_step;
-                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a3 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
-                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w3 + 2 * k, hi_w, idesc, 1u);
-                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
-                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a2 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, 1u);
-                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_corr, a1 + 2 * k, hi_a, w2 + 2 * k, hi_w, idesc, 1u);
-                        for (int k = 0; k < nk; ++k) umma_bf16_lohi(d_main, a1 + 2 * k, hi_a, w1 + 2 * k, hi_w, idesc, (accum | (uint32_t)k));
-                        accum = 1;
+                        const uint32_t w1 = (((w_base + (uint32_t)sw * w_stage) >> 4) & 0x3FFFu) | lo_flags;
+                        issue_kstep(blocks, (uint32_t)NT, d0, a1, a2, a3, hi_a, w1, w_step, hi_w, idesc0, first);
+                        if (two_k) issue_kstep(blocks, (uint32_t)NT, d0, a1 + 2, a2 + 2, a3 + 2, hi_a, w1 + 2, w_step, hi_w, idesc0, 0u);
+                        first = 0;
                         umma_commit(&w_empty[sw]);
                         if (++sw == w_stages) { sw = 0; pw ^= 1; }
                     }
@@ -551,9 +582,12 @@ static int launch_t32(const t32::Launch& L, cudaStream_t st) {
     if (p.n_tiles * p.NT != L.Nf) return VAE2_ERR_ARG;
     p.accumulate = L.accumulate;
     p.a = L.a; p.bias = L.bias; p.out = L.out;
-    p.acc_stages = (4 * p.NT <= 512) ? 2 : 1;          // two accumulators (main + correction) per stage
+    // accumulator blocks per tile: leading product + one or two correction blocks (issue_kstep)
+    p.acc_blocks = (2 * p.NT <= 256 && 3 * p.NT <= 512) ? 3 : 2;
+    if (const char* e = getenv("VAE2_F32X3_MERGE")) { if (atoi(e) == 0) p.acc_blocks = 2; }
+    p.acc_stages = (2 * p.acc_blocks * p.NT <= 512) ? 2 : 1;
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.acc_stages * 2 * p.NT) p.tmem_cols <<= 1;
+    while (p.tmem_cols < p.acc_stages * p.acc_blocks * p.NT) p.tmem_cols <<= 1;
     if (p.tmem_cols > 512) return VAE2_ERR_UNSUPPORTED;
 
     CUtensorMap map_w;
