@@ -48,7 +48,8 @@ def twice(tag, fn):
 
 # ---- convolutions: (name, H, W, Cin, Cout, k, stride) -- the shapes with the largest time share (profiles/r1_step_callsites_*)
 CONVS = [("18->18 3x3", 256, 512, 18, 18, 3, 1), ("36->36 3x3", 128, 256, 36, 36, 3, 1), ("64->64 3x3", 256, 512, 64, 64, 3, 1),
-         ("270->270 1x1", 256, 512, 270, 270, 1, 1), ("64->256 1x1", 256, 512, 64, 256, 1, 1), ("18->36 3x3 s2", 256, 512, 18, 36, 3, 2)]
+         ("270->270 1x1", 256, 512, 270, 270, 1, 1), ("64->256 1x1", 256, 512, 64, 256, 1, 1), ("18->36 3x3 s2", 256, 512, 18, 36, 3, 2),
+         ("256->18 3x3", 256, 512, 256, 18, 3, 1), ("72->72 3x3", 64, 128, 72, 72, 3, 1)]
 for name, H, W, Cin, Cout, k, s_ in CONVS:
     Cip, Cop = pad(Cin), pad(Cout)
     Ho, Wo = (H + 2 * (k // 2) - k) // s_ + 1, (W + 2 * (k // 2) - k) // s_ + 1
@@ -68,8 +69,9 @@ for name, H, W, Cin, Cout, k, s_ in CONVS:
         twice("wgrad " + name, lambda: N.call.vae2_conv2d_wgrad_tc(p(x), p(dy), p(dwp), p(ws), C.byref(g), st))
     else:
         twice("wgrad " + name, lambda: N.call.vae2_conv2d_wgrad(p(x), p(dy), p(dwp), code, C.byref(g), 0, st))
-    if prec == "fp32" and max(Cip, Cop) >= 40 and N.lib().vae2_conv2d_tf32_supported(C.byref(g)):
-        # the fp32 path's tensor-core route for the >= 40-lane layers: exact 3-way bf16 split, split accumulators
+    if prec == "fp32" and N.lib().vae2_conv2d_tf32_supported(C.byref(g)):
+        # the fp32 path's tensor-core route (>= 40-lane layers and 3x3 stride-1 layers from 36 lanes; 18->18 is captured too,
+        # for the comparison with conv_direct): exact 3-way bf16 split, split accumulators
         Nf, Kf, NfT, KfT = N.tf32_dims(g)
         wsrc = torch.randn(Cout, Cin, k, k, device=dev) * 0.05
         wf = torch.zeros(3 * k * k * Nf * Kf, dtype=torch.bfloat16, device=dev)
@@ -80,6 +82,11 @@ for name, H, W, Cin, Cout, k, s_ in CONVS:
         N.call.vae2_pack_weights_tf32(tab.data_ptr(), 1, st)
         twice("f32x3 fwd " + name, lambda: N.call.vae2_conv2d_fwd(p(x), p(wf), None, p(y), 0, C.byref(g), 2, st))
         twice("f32x3 dgrad " + name, lambda: N.call.vae2_conv2d_dgrad(p(dy), p(wb), p(dx), 0, C.byref(g), 0, 2, st))
+        need = N.lib().vae2_conv2d_wgrad_f32x2_workspace(C.byref(g))
+        if need > 0:
+            wsb = torch.zeros(need, dtype=torch.uint8, device=dev)
+            twice("f32x2 wgrad " + name, lambda: N.call.vae2_conv2d_wgrad_f32x2(p(x), p(dy), p(dwp), p(wsb), C.byref(g), st))
+            del wsb
     del x, y, dy, dx, w, dwp
     torch.cuda.empty_cache()
 
