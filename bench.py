@@ -111,6 +111,10 @@ def build_models(cfg, dev, world, local_rank):
                                                       find_unused_parameters=True)
         g = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local_rank], output_device=local_rank,
                                                       find_unused_parameters=True)
+        from _engine_loader import engine
+        if engine().peer.active():      # SyncBN exchanges inside the BN launches: keep NCCL kernels out of their way
+            engine().peer.serialize_ddp(d)
+            engine().peer.serialize_ddp(g)
     # tools/train.py:251-261: Adam, encdec optimizer excludes D parameters, D optimizer takes only them
     pg = [p for n, p in gm.named_parameters() if p.requires_grad and "D_model" not in n]
     pd = [p for n, p in dm.named_parameters() if p.requires_grad and "D_model" in n]
@@ -397,6 +401,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", init_method="env://")
+        E.peer.enable()                 # SyncBN statistics over NVLink peer memory (VAE2_SYNCBN_P2P=0: NCCL collectives)
     torch.manual_seed(1234 + rank)
     g, d, opt_g, opt_d = build_models(cfg, dev, world, local_rank)
 
@@ -471,7 +476,9 @@ def main():
                        "l2": "activations per step >> 126 MB L2 (inputs larger than L2)",
                        "cuda_graphs": not args.no_graphs, "frame_size": [H, W], "skip_dead_D_grads": True,
                        "stacked_discriminator_passes": os.environ.get("VAE2_STACK_D", "1") != "0",
-                       "d_stack": int(os.environ.get("VAE2_D_STACK", "6"))},
+                       "d_stack": int(os.environ.get("VAE2_D_STACK", "6")),
+                       "syncbn": ("peer-memory exchange inside the BN launches" if E.peer.active() else
+                                  "NCCL all-gather / all-reduce per BN group") if world > 1 else "n/a"},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": 3 * B * 9 * H * W * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
@@ -492,6 +499,7 @@ def main():
             line["cpu_baseline"], _ = cpu_baseline(cfg, H, W, steps=1, warmup=0)
         print(json.dumps(line), flush=True)
     if world > 1:
+        E.peer.check()                  # raises if a BN launch gave up waiting for a peer rank
         # Tear down in order: drop the plans (their captured CUDA graphs hold the NCCL collectives), then the process
         # group.  Destroying a group whose collectives still sit inside live graphs was seen to hang at exit, so a
         # watchdog ends the process if the orderly path does not finish; every rank has passed the final barrier by now.
@@ -508,6 +516,7 @@ def main():
         del g, d, opt_g, opt_d
         gc.collect()
         torch.cuda.synchronize(dev)
+        E.peer.disable()
         dist.destroy_process_group()
         wd.cancel()
 

@@ -207,6 +207,35 @@ int vae2_bn_sync_bwd(int phase, const void* g, const void* a, const void* y, voi
                      int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
                      int stat_stride, float* msg, const float* gsum, float inv_count, vae2_stream_t stream);
 
+/* SyncBatchNorm with the cross-rank exchange INSIDE the launch, over NVLink peer memory (no NCCL call per layer): the same
+ * single cooperative launch per direction as on one GPU; the CTA that finalizes a channel stores its rank-local
+ * (count, mean, M2) / (sum dyb, sum dyb*xhat) into every rank's mailbox with P2P stores and merges what the other ranks
+ * stored into its own, in rank order (bit-identical statistics on every rank).  Replaces torch's SyncBatchNorm collectives
+ * (nn/modules/_functions.py:39-122: all_gather of the statistics, all_reduce of the backward sums) for tools/train.py:217.
+ *   vae2_ipc_alloc / vae2_ipc_open : one zeroed device allocation per process + its 64-byte CUDA IPC handle; peers map it.
+ *   vae2_bn_peer_setup             : bases[r] = rank r's mailbox as mapped in this process, seq = zeroed uint32 per op,
+ *                                    err = zeroed int (set when a peer did not answer within ~10 s; the host must raise).
+ *   vae2_bn_peer_slot_words        : 8-byte words an op needs in the mailbox; the host gives every op (and direction) its own
+ *                                    slot_word offset and seq_index, identical on every rank.
+ * Gradient all-reduce kernels must not be in flight while these launches wait for their peers. */
+int vae2_ipc_alloc(int64_t bytes, void** ptr, void* handle64);
+int vae2_ipc_open(const void* handle64, void** ptr);
+int vae2_ipc_close(void* ptr);
+int vae2_ipc_free(void* ptr);
+int vae2_bn_peer_setup(int world, int rank, void* const* bases, uint32_t* seq, int* err);
+int64_t vae2_bn_peer_slot_words(int world, int groups, int Cp, int backward);
+int vae2_bn_fwd_fused_peer(const void* y, const void* res, void* out, float* partials, int dtype, int64_t npix, int C,
+                           int Cp, int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                           float eps, float* mean, float* invstd, float* scale, float* shift, int relu, int groups,
+                           int stat_stride, int64_t slot_word, int seq_index, vae2_stream_t stream);
+int vae2_bn_bwd_fused_peer(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                           int64_t npix, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres,
+                           const float* mean, const float* invstd, const float* scale, const float* shift, float* dgamma,
+                           float* dbeta, int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres,
+                           int groups, int stat_stride, float inv_count, int64_t slot_word, int seq_index,
+                           vae2_stream_t stream);
+
 /* ---- branch fusion / upsampling: HighResolutionModule.forward enc_hrnet.py:233-248, :833-839 -- */
 typedef struct { const void* ptr; int32_t H, W, ld; } vae2_fuse_src;        /* HOST array */
 typedef struct { void* ptr; int32_t ld, accumulate; } vae2_fuse_dst;         /* HOST array */

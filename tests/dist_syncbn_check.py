@@ -15,6 +15,11 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dev = torch.device("cuda", rank)
 dist.init_process_group("nccl")
+P2P = "p2p" in sys.argv[2:]                           # SyncBN statistics over NVLink peer memory instead of NCCL (engine/peer.py)
+if P2P:
+    assert E.peer.enable(), "peer-memory SyncBN could not be enabled"
+else:
+    os.environ["VAE2_SYNCBN_P2P"] = "0"
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 E.set_precision(prec)
 E.use_cuda_graphs(len(sys.argv) > 2 and sys.argv[2] == "graphs")
@@ -30,6 +35,9 @@ g = torch.nn.SyncBatchNorm.convert_sync_batchnorm(g).to(dev).train()
 d = torch.nn.SyncBatchNorm.convert_sync_batchnorm(d).to(dev).train()
 dd = torch.nn.parallel.DistributedDataParallel(d, device_ids=[rank], find_unused_parameters=True)
 gd = torch.nn.parallel.DistributedDataParallel(g, device_ids=[rank], find_unused_parameters=True)
+if P2P:
+    E.peer.serialize_ddp(dd)
+    E.peer.serialize_ddp(gd)
 sl = slice(rank, rank + 1)
 with RandnQueue([code[sl]]):
     losses, x1p, x2p, x3p = gd(xt=xt[sl].to(dev), x2t=x2t[sl].to(dev), x3t=x3t[sl].to(dev), multiplier=1.0,
@@ -80,8 +88,12 @@ if prec == "fp32":
     msgs.append("D step: DDP-averaged grad norms vs reference: median rel err %.2e, max %.2e" % (np.median(en), en.max()))
     ok &= bool(np.median(en) < 3e-2)
 plans = [p for m in g.modules() if hasattr(m, "_plans") for pool in m._plans().values() for p in pool]
-msgs.append("SyncBN collectives fwd %d for %d BNs" % (sum(p.n_collectives_fwd for p in plans),
-                                                     sum(1 for m in g.modules() if isinstance(m, torch.nn.SyncBatchNorm))))
+msgs.append("SyncBN collectives fwd %d, peer-memory launches fwd %d bwd %d, for %d BNs" % (
+    sum(p.n_collectives_fwd for p in plans), sum(getattr(p, "n_peer_bn_fwd", 0) for p in plans),
+    sum(getattr(p, "n_peer_bn_bwd", 0) for p in plans), sum(1 for m in g.modules() if isinstance(m, torch.nn.SyncBatchNorm))))
+if P2P:
+    E.peer.check()
+    ok &= sum(p.n_collectives_fwd for p in plans) == 0 and sum(getattr(p, "n_peer_bn_fwd", 0) for p in plans) > 0
 if rank == 0:
     print("\n".join(msgs))
     print("DIST_SYNCBN_CHECK", "PASS" if ok else "FAIL", prec, flush=True)

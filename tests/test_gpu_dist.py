@@ -13,8 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", [["fp32"], ["fp32", "graphs"], ["fp32", "eager", "skip"], ["bf16", "graphs", "skip"]],
-                         ids=["fp32", "fp32-graphs", "fp32-skipdead", "bf16-graphs-skipdead"])
+@pytest.mark.parametrize("mode", [["fp32"], ["fp32", "graphs"], ["fp32", "eager", "skip"], ["bf16", "graphs", "skip"],
+                                  ["fp32", "eager", "p2p"], ["fp32", "graphs", "skip", "p2p"], ["bf16", "graphs", "skip", "p2p"]],
+                         ids=["fp32", "fp32-graphs", "fp32-skipdead", "bf16-graphs-skipdead", "fp32-p2p", "fp32-graphs-skipdead-p2p",
+                              "bf16-graphs-skipdead-p2p"])
 def test_ddp_syncbn_two_ranks_match_single_process_reference(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

@@ -207,6 +207,35 @@ int vae2_bn_sync_bwd(int phase, const void* g, const void* a, const void* y, voi
                        scale, shift, dgamma, dbeta, accumulate_param, c1, c2, relu, acc_dy, acc_dres, groups, stat_stride, msg,
                        gsum, inv_count, S(stream));
 }
+int vae2_ipc_alloc(int64_t bytes, void** ptr, void* handle64) { return ipc_alloc(bytes, ptr, handle64); }
+int vae2_ipc_open(const void* handle64, void** ptr) { return ipc_open(handle64, ptr); }
+int vae2_ipc_close(void* ptr) { return ipc_close(ptr); }
+int vae2_ipc_free(void* ptr) { return ipc_free(ptr); }
+int vae2_bn_peer_setup(int world, int rank, void* const* bases, uint32_t* seq, int* err) {
+    return bn_peer_setup(world, rank, bases, seq, err);
+}
+int64_t vae2_bn_peer_slot_words(int world, int groups, int Cp, int backward) {
+    return bn_peer_slot_words(world, groups, Cp, backward);
+}
+int vae2_bn_fwd_fused_peer(const void* y, const void* res, void* out, float* partials, int dtype, int64_t npix, int C,
+                           int Cp, int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                           float eps, float* mean, float* invstd, float* scale, float* shift, int relu, int groups,
+                           int stat_stride, int64_t slot_word, int seq_index, vae2_stream_t stream) {
+    return bn_fwd_fused_peer(y, res, out, partials, dtype, npix, C, Cp, ld_y, ld_res, ld_out, gamma, beta, running_mean,
+                             running_var, (long long*)num_batches_tracked, momentum, eps, mean, invstd, scale, shift, relu,
+                             groups, stat_stride, slot_word, seq_index, S(stream));
+}
+int vae2_bn_bwd_fused_peer(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                           int64_t npix, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres,
+                           const float* mean, const float* invstd, const float* scale, const float* shift, float* dgamma,
+                           float* dbeta, int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres,
+                           int groups, int stat_stride, float inv_count, int64_t slot_word, int seq_index,
+                           vae2_stream_t stream) {
+    return bn_bwd_fused_peer(g, a, y, dy, dres, partials, dtype, npix, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, mean, invstd,
+                             scale, shift, dgamma, dbeta, accumulate_param, c1, c2, relu, acc_dy, acc_dres, groups,
+                             stat_stride, inv_count, slot_word, seq_index, S(stream));
+}
 int vae2_bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, vae2_stream_t stream) {
     return bn_bwd_finalize(partials, n_partials, C, Cp, sums, S(stream));
 }

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -600,6 +601,50 @@ __device__ __forceinline__ void prof_mark(unsigned long long* prof, int i) {
     }
 }
 
+// ---- SyncBN over NVLink peer memory (phase 3) --------------------------------------------------------------------------
+// One cooperative launch per BN, as on a single GPU: after the rank-local merge the CTA that finalizes channel c stores its
+// (count, mean, M2) -- or (sum dy, sum dy*xhat) in the backward -- straight into every rank's mailbox (P2P stores through
+// NVSwitch), then reads the other ranks' values from its OWN mailbox and merges them in rank order, so every rank computes
+// bit-identical statistics.  Each value travels as one 8-byte word {float bits, sequence number}: an aligned 8-byte store
+// is single-copy atomic, so the flag can never be seen ahead of its data and no fence is needed (NCCL's LL protocol).  The
+// sequence number comes from a per-op device counter (the launch arguments are frozen inside CUDA graphs); words of
+// consecutive launches of an op alternate between two buffers.  A wait that exceeds kPeerSpinLimit sets a sticky error flag
+// and gives up (the host raises at the end of the step) instead of hanging the GPU.
+constexpr int kMaxPeers = 8;
+constexpr long long kPeerSpinLimit = 20000000000LL;     // ~10 s of SM clocks
+
+struct BnPeer {
+    int world, rank;
+    unsigned long long* box[kMaxPeers];   // this op's mailbox slot on rank r (peer-mapped); box[rank] is local
+    unsigned int* seq;                    // launches of this op so far (local)
+    int* err;                             // sticky (local)
+};
+
+__device__ __forceinline__ void peer_put(unsigned long long* p, float v, unsigned int seq) {
+    const unsigned long long w = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+
+__device__ __forceinline__ float peer_get(const unsigned long long* p, unsigned int seq, int* err) {
+    unsigned long long w;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (true) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+        if ((unsigned int)(w >> 32) == seq) break;
+        if ((++spins & 255) == 0) {
+            if (*(volatile int*)err != 0) break;
+            if (clock64() - t0 > kPeerSpinLimit) { *(volatile int*)err = 1; break; }
+        }
+    }
+    return __uint_as_float((unsigned int)w);
+}
+
+// word index of value k (of nv) of channel c, group gq, written by rank src, buffer par
+__device__ __forceinline__ long long peer_word(int par, int world, int src, int G, int gq, int nv, int k, int Cp, int c) {
+    return ((((long long)par * world + src) * G + gq) * nv + k) * Cp + c;
+}
+
 struct BnFwdArgs {
     unsigned long long* prof;
     const void *y, *res;
@@ -626,6 +671,7 @@ struct BnFwdArgs {
     const float* ext;
     int ext_parts;
     long long ext_stride;
+    BnPeer peer;                                   // phase 3: the whole BN with the cross-rank merge inside (see BnPeer)
 };
 
 template <typename T>
@@ -636,6 +682,7 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
     prof_mark(A.prof, 0);
     const int nbpg = gridDim.x / A.G;                 // CTAs per statistics group
     const int grp = blockIdx.x / nbpg, lb = blockIdx.x - grp * nbpg;
+    const unsigned int pseq = A.phase == 3 ? *(volatile unsigned int*)A.peer.seq + 1u : 0u;   // bumped after the last grid.sync
     // parameters of the channel this CTA will finalize: cold in HBM, so fetched under the statistics pass
     float gm0 = 0.f, bt0 = 0.f, rm00 = 0.f, rv00 = 0.f;
     if (A.phase != 1 && threadIdx.x == 0 && (int)blockIdx.x < A.C) {
@@ -697,6 +744,22 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
                     }
                     n = nn;
                 }
+                if (A.phase == 3 && c < A.C) {                 // cross-rank merge through peer memory (warp 0, lane r <-> rank r)
+                    const BnPeer& X = A.peer;
+                    const int par = (int)(pseq & 1u);
+                    n = __shfl_sync(0xffffffffu, n, 0); mean = __shfl_sync(0xffffffffu, mean, 0); m2 = __shfl_sync(0xffffffffu, m2, 0);
+                    float rn = 0.f, rmean = 0.f, rm2 = 0.f;
+                    if (lane < X.world) {
+                        unsigned long long* dst = X.box[lane] + peer_word(par, X.world, X.rank, A.G, gq, 3, 0, A.Cp, c);
+                        peer_put(dst, n, pseq); peer_put(dst + A.Cp, mean, pseq); peer_put(dst + 2 * A.Cp, m2, pseq);
+                        const unsigned long long* src = X.box[X.rank] + peer_word(par, X.world, lane, A.G, gq, 3, 0, A.Cp, c);
+                        rn = peer_get(src, pseq, X.err); rmean = peer_get(src + A.Cp, pseq, X.err); rm2 = peer_get(src + 2 * A.Cp, pseq, X.err);
+                    }
+                    n = 0.f; mean = 0.f; m2 = 0.f;
+                    for (int r = 0; r < X.world; ++r)          // fixed rank order: identical on every rank
+                        chan_merge(n, mean, m2, __shfl_sync(0xffffffffu, rn, r), __shfl_sync(0xffffffffu, rmean, r),
+                                   __shfl_sync(0xffffffffu, rm2, r));
+                }
                 if (lane == 0 && A.phase == 1) {               // rank-local (count, mean, M2) of this group -> the message
                     float* o = A.msg + (long long)gq * 3 * A.Cp;
                     o[c] = c < A.C ? n : 0.f; o[A.Cp + c] = c < A.C ? mean : 0.f; o[2 * A.Cp + c] = c < A.C ? m2 : 0.f;
@@ -725,6 +788,7 @@ bn_fwd_fused_kernel(const BnFwdArgs A) {
     prof_mark(A.prof, 3);
     grid.sync();
     prof_mark(A.prof, 4);
+    if (A.phase == 3 && blockIdx.x == 0 && threadIdx.x == 0) *A.peer.seq = pseq;
     const Lay<T> L(A.Cp, lb, nbpg);
     apply_pass<T>((const T*)A.y + grp * A.gs_y, A.res != nullptr ? (const T*)A.res + grp * A.gs_res : nullptr,
                   (T*)A.out + grp * A.gs_out, A.P, A.ld_y, A.ld_res, A.ld_out, A.scale + grp * A.stat_stride,
@@ -751,6 +815,7 @@ struct BnBwdArgs {
     int phase;
     float* msg;
     const float* ext;
+    BnPeer peer;                                   // phase 3: sums exchanged through peer memory inside the launch
 };
 
 template <typename T, int RELU, bool DRES>
@@ -765,6 +830,7 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
     const T* gp = (const T*)A.g + grp * A.gs_g;
     const T* ap = A.a != nullptr ? (const T*)A.a + grp * A.gs_a : nullptr;
     const T* yp = (const T*)A.y + grp * A.gs_y;
+    const unsigned int pseq = A.phase == 3 ? *(volatile unsigned int*)A.peer.seq + 1u : 0u;
     if (A.phase != 2) {
         bwd_reduce_to_partials_t<T, RELU>(gp, ap, yp, A.partials, A.P, A.Cp, A.ld_g, A.ld_a, A.ld_y, A.mean + so_g,
                                           A.invstd + so_g, sm, A.scale + so_g, A.shift != nullptr ? A.shift + so_g : nullptr,
@@ -801,18 +867,34 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
             __syncthreads();
             if (lane == 0) { sm[warp * 2] = s1; sm[warp * 2 + 1] = s2; }
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (warp == 0) {
                 s1 = 0.f; s2 = 0.f;
 #pragma unroll
-                for (int w = 0; w < BN_THREADS / 32; ++w) { s1 += sm[w * 2]; s2 += sm[w * 2 + 1]; }
-                if (A.phase == 1) {
-                    float* o = A.msg + (long long)gq * 2 * A.Cp;
-                    o[c] = s1; o[A.Cp + c] = s2;
-                } else {
-                    A.c1[gq * A.stat_stride + c] = s1 * A.inv_count;
-                    A.c2[gq * A.stat_stride + c] = s2 * A.inv_count;
+                for (int w = 0; w < BN_THREADS / 32; ++w) { s1 += sm[w * 2]; s2 += sm[w * 2 + 1]; }     // every lane: the local sums
+                float g1 = s1, g2 = s2;
+                if (A.phase == 3 && c < A.C) {                 // all-reduce through peer memory (lane r <-> rank r), rank order
+                    const BnPeer& X = A.peer;
+                    const int par = (int)(pseq & 1u);
+                    float r1 = 0.f, r2 = 0.f;
+                    if (lane < X.world) {
+                        unsigned long long* dst = X.box[lane] + peer_word(par, X.world, X.rank, A.G, gq, 2, 0, A.Cp, c);
+                        peer_put(dst, s1, pseq); peer_put(dst + A.Cp, s2, pseq);
+                        const unsigned long long* src = X.box[X.rank] + peer_word(par, X.world, lane, A.G, gq, 2, 0, A.Cp, c);
+                        r1 = peer_get(src, pseq, X.err); r2 = peer_get(src + A.Cp, pseq, X.err);
+                    }
+                    g1 = 0.f; g2 = 0.f;
+                    for (int r = 0; r < X.world; ++r) { g1 += __shfl_sync(0xffffffffu, r1, r); g2 += __shfl_sync(0xffffffffu, r2, r); }
                 }
-                t1 += s1; t2 += s2;
+                if (lane == 0) {
+                    if (A.phase == 1) {
+                        float* o = A.msg + (long long)gq * 2 * A.Cp;
+                        o[c] = s1; o[A.Cp + c] = s2;
+                    } else {
+                        A.c1[gq * A.stat_stride + c] = g1 * A.inv_count;
+                        A.c2[gq * A.stat_stride + c] = g2 * A.inv_count;
+                    }
+                    t1 += s1; t2 += s2;                        // parameter gradients from the LOCAL sums (DDP reduces them)
+                }
             }
         }
         if (A.phase == 2) continue;
@@ -825,6 +907,7 @@ bn_bwd_fused_kernel(const BnBwdArgs A) {
     prof_mark(A.prof, 3);
     grid.sync();
     prof_mark(A.prof, 4);
+    if (A.phase == 3 && blockIdx.x == 0 && threadIdx.x == 0) *A.peer.seq = pseq;
     const Lay<T> L(A.Cp, lb, nbpg);
     bwd_elemt_pass_t<T, RELU, DRES>(gp, ap, yp, (T*)A.dy + grp * A.gs_dy, A.dres != nullptr ? (T*)A.dres + grp * A.gs_dres : nullptr,
                                     A.P, A.ld_g, A.ld_a, A.ld_y, A.ld_dy, A.ld_dres, A.mean + so_g, A.invstd + so_g,
@@ -1017,6 +1100,97 @@ int bn_sync_bwd(int phase, const void* g, const void* a, const void* y, void* dy
                 P * ld_a, P * ld_y, P * ld_dy, P * ld_dres, stat_stride, phase, msg, gsum};
     return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
 }
+
+// ---- SyncBN over peer memory: process-wide context + the two launches ---------------------------------------------------
+static struct {
+    int world, rank;
+    unsigned long long* base[kMaxPeers];
+    unsigned int* seq;
+    int* err;
+} g_peer = {0, 0, {nullptr}, nullptr, nullptr};
+
+// bases[r]: rank r's mailbox as mapped into THIS process (bases[rank] is the local allocation); seq: local zeroed counters,
+// one per op; err: local zeroed int.  world = 0 tears the context down.
+int bn_peer_setup(int world, int rank, void* const* bases, unsigned int* seq, int* err) {
+    if (world == 0) { g_peer.world = 0; return VAE2_OK; }
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || bases == nullptr || seq == nullptr || err == nullptr)
+        return VAE2_ERR_ARG;
+    g_peer.world = world; g_peer.rank = rank; g_peer.seq = seq; g_peer.err = err;
+    for (int r = 0; r < world; ++r) g_peer.base[r] = reinterpret_cast<unsigned long long*>(bases[r]);
+    return VAE2_OK;
+}
+
+// 8-byte words one op needs in every rank's mailbox: 2 buffers x world senders x groups x values x lanes
+long long bn_peer_slot_words(int world, int groups, int Cp, int backward) {
+    return 2LL * world * groups * (backward ? 2 : 3) * Cp;
+}
+
+static int fill_peer(BnPeer& X, long long slot_word, int seq_index) {
+    if (g_peer.world < 1 || slot_word < 0 || seq_index < 0) return VAE2_ERR_ARG;
+    X.world = g_peer.world; X.rank = g_peer.rank;
+    for (int r = 0; r < kMaxPeers; ++r) X.box[r] = r < g_peer.world ? g_peer.base[r] + slot_word : nullptr;
+    X.seq = g_peer.seq + seq_index; X.err = g_peer.err;
+    return VAE2_OK;
+}
+
+// SyncBN forward in ONE cooperative launch: statistics, cross-rank merge through peer memory, running statistics, apply.
+// P = this rank's pixels per group; the merged count covers every rank.
+int bn_fwd_fused_peer(const void* y, const void* res, void* out, float* partials, int dtype, long long P, int C, int Cp,
+                      int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long long* nbt, float momentum, float eps, float* mean, float* invstd,
+                      float* scale, float* shift, int relu, int groups, int stat_stride, long long slot_word, int seq_index,
+                      cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_y % V || ld_out % V || (res && ld_res % V) || Cp / V > BN_THREADS || P < 1 || groups < 1 ||
+        groups > 64)
+        return VAE2_ERR_ARG;
+    BnFwdArgs A{g_bn_prof, y, res, out, partials, P, C, Cp, ld_y, ld_res, ld_out, relu, gamma, beta, running_mean, running_var,
+                nbt, momentum, eps, mean, invstd, scale, shift, groups, P * ld_y, P * ld_res, P * ld_out, stat_stride,
+                3, nullptr, nullptr, 0, 0};
+    if (int e = fill_peer(A.peer, slot_word, seq_index)) return e;
+    return dtype == VAE2_DT_F32 ? launch_fwd_fused<float>(A, st) : launch_fwd_fused<__nv_bfloat16>(A, st);
+}
+
+// SyncBN backward in ONE cooperative launch; inv_count = 1 / (pixels of a group over ALL ranks); d(gamma), d(beta) come
+// from the rank-local sums (DDP all-reduces parameter gradients), as in torch's SyncBatchNorm.
+int bn_bwd_fused_peer(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                      long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                      const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                      int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
+                      int stat_stride, float inv_count, long long slot_word, int seq_index, cudaStream_t st) {
+    const int V = vec_of(dtype);
+    if (Cp % V || ld_g % V || ld_y % V || ld_dy % V || (relu == 1 && (a == nullptr || ld_a % V)) ||
+        (relu == 2 && shift == nullptr) || relu < 0 || relu > 2 || (dres && ld_dres % V) || Cp / V > BN_THREADS || P < 1 ||
+        groups < 1 || groups > 64)
+        return VAE2_ERR_ARG;
+    BnBwdArgs A{g_bn_prof, g, a, y, dy, dres, partials, P, C, Cp, ld_g, ld_a, ld_y, ld_dy, ld_dres, relu, acc_dy, acc_dres,
+                accumulate_param, mean, invstd, scale, shift, dgamma, dbeta, c1, c2, inv_count, groups, P * ld_g,
+                P * ld_a, P * ld_y, P * ld_dy, P * ld_dres, stat_stride, 3, nullptr, nullptr};
+    if (int e = fill_peer(A.peer, slot_word, seq_index)) return e;
+    return dtype == VAE2_DT_F32 ? launch_bwd_fused<float>(A, st) : launch_bwd_fused<__nv_bfloat16>(A, st);
+}
+
+// CUDA IPC plumbing for the mailboxes (one cudaMalloc per process, zeroed; peers map it with cudaIpcOpenMemHandle)
+int ipc_alloc(long long bytes, void** ptr, void* handle64) {
+    if (bytes < 1 || ptr == nullptr || handle64 == nullptr) return VAE2_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (cudaMalloc(ptr, (size_t)bytes) != cudaSuccess) return VAE2_ERR_CUDA;
+    if (cudaMemset(*ptr, 0, (size_t)bytes) != cudaSuccess) return VAE2_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return VAE2_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, *ptr) != cudaSuccess) { cudaGetLastError(); return VAE2_ERR_CUDA; }
+    memcpy(handle64, &h, 64);
+    return VAE2_OK;
+}
+int ipc_open(const void* handle64, void** ptr) {
+    if (ptr == nullptr || handle64 == nullptr) return VAE2_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    if (cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return VAE2_ERR_CUDA; }
+    return VAE2_OK;
+}
+int ipc_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? VAE2_OK : VAE2_ERR_CUDA; }
+int ipc_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? VAE2_OK : VAE2_ERR_CUDA; }
 
 int bn_stats(const void* y, float* partials, int* n_partials_out, int dtype, long long P, int Cp, int ld, cudaStream_t st) {
     const int V = vec_of(dtype);

@@ -94,6 +94,22 @@ int bn_sync_bwd(int phase, const void* g, const void* a, const void* y, void* dy
                 const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
                 int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups, int stat_stride,
                 float* msg, const float* gsum, float inv_count, cudaStream_t st);
+int bn_peer_setup(int world, int rank, void* const* bases, unsigned int* seq, int* err);
+long long bn_peer_slot_words(int world, int groups, int Cp, int backward);
+int bn_fwd_fused_peer(const void* y, const void* res, void* out, float* partials, int dtype, long long P, int C, int Cp,
+                      int ld_y, int ld_res, int ld_out, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long long* nbt, float momentum, float eps, float* mean, float* invstd,
+                      float* scale, float* shift, int relu, int groups, int stat_stride, long long slot_word, int seq_index,
+                      cudaStream_t st);
+int bn_bwd_fused_peer(const void* g, const void* a, const void* y, void* dy, void* dres, float* partials, int dtype,
+                      long long P, int C, int Cp, int ld_g, int ld_a, int ld_y, int ld_dy, int ld_dres, const float* mean,
+                      const float* invstd, const float* scale, const float* shift, float* dgamma, float* dbeta,
+                      int accumulate_param, float* c1, float* c2, int relu, int acc_dy, int acc_dres, int groups,
+                      int stat_stride, float inv_count, long long slot_word, int seq_index, cudaStream_t st);
+int ipc_alloc(long long bytes, void** ptr, void* handle64);
+int ipc_open(const void* handle64, void** ptr);
+int ipc_close(void* ptr);
+int ipc_free(void* ptr);
 int bn_bwd_finalize(const float* partials, int n_partials, int C, int Cp, float* sums, cudaStream_t st);
 int bn_bwd_coeffs(const float* sums, int C, int Cp, float inv_count, float* dgamma, float* dbeta, int accumulate_param,
                   const float* sums_for_param, float* c1, float* c2, cudaStream_t st);

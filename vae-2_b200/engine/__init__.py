@@ -3,4 +3,5 @@ from .module import (EngineModule, set_precision, get_precision, use_cuda_graphs
                      activation_phase, ActArena)
 from .elbo import elbo_terms, check_finite, finite_check_mode  # noqa: F401
 from . import native  # noqa: F401
+from . import peer  # noqa: F401
 from .profiler import KernelProfile  # noqa: F401

@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from . import native as N
+from . import peer
 
 BN_EPS_DEFAULT = 1e-5
 
@@ -1131,6 +1132,45 @@ class BnOp:
             plan.fwd.append(lambda st, pt=pt: N.call.vae2_bn_apply(pt.yp, pt.resp, pt.outp, pr.code, npix, lanes, ldy, ldr,
                                                                   ldo, pt.scale, pt.shift, relu, st))
 
+    def _emit_fwd_peer(self, plan):
+        """SyncBN forward as ONE cooperative launch: the cross-rank merge runs inside it over NVLink peer memory
+        (engine/peer.py, csrc/bn.cu phase 3) -- no collective call."""
+        pr, y, out, res = plan.prec, self.y, self.out, self.res
+        ws = self._scratch(plan).data_ptr()
+        ldr = res.ld if res is not None else 0
+        gp, bp, rm, rv, nbt, mom, eps = self._bn_ptrs()
+        relu = 1 if self.relu else 0
+        p0, G, npix = self.parts[0], len(self.parts), self.npix_g
+        slot, seq = peer.alloc(G, y.Cp, False)
+        plan.fwd.append(lambda st: N.call.vae2_bn_fwd_fused_peer(
+            p0.yp, p0.resp, p0.outp, ws, pr.code, npix, y.C, y.Cp, y.ld, ldr, out.ld, gp, bp, rm, rv, nbt, mom, eps, p0.mean,
+            p0.invstd, p0.scale, p0.shift, relu, G, 6 * y.Cp, slot, seq, st))
+
+    def _emit_bwd_peer(self, plan):
+        pr = plan.prec
+        y, out, res, g = self.y, self.out, self.res, self.g
+        npix, lanes, C_ = self.npix_g, self.lanes, y.C
+        ws = self._scratch(plan).data_ptr()
+        want_p = self.param_grads
+        dgam = plan.grad_ptr(self.bn.weight) if want_p else None
+        dbet = plan.grad_ptr(self.bn.bias) if want_p else None
+        dy = y.grad()
+        acc_dy = y.take_acc_flag()
+        has_dres, ld_dres, acc_res = False, 0, 0
+        if res is not None and res.needs_grad:
+            acc_res = res.take_acc_flag()
+            has_dres, ld_dres = True, res.ld
+        relu = 0 if not self.relu else (1 if res is not None else 2)
+        p0, G = self.parts[0], len(self.parts)
+        dres0 = res.grad().ptr if has_dres else None
+        gp0, dyp0 = g.ptr, dy.ptr
+        inv_count = 1.0 / (npix * plan.world_size)
+        slot, seq = peer.alloc(G, y.Cp, True)
+        plan.bwd.append(lambda st: N.call.vae2_bn_bwd_fused_peer(
+            gp0, p0.outp, p0.yp, dyp0, dres0, ws, pr.code, npix, C_, lanes, g.ld, out.ld, y.ld, dy.ld, ld_dres, p0.mean,
+            p0.invstd, p0.scale, p0.shift, dgam, dbet, 0, p0.c1, p0.c2, relu, acc_dy, acc_res, G, 6 * y.Cp, inv_count,
+            slot, seq, st))
+
     def _emit_sync_fwd1(self, plan, msg_ptr):
         """SyncBN forward, first half: statistics + rank-local merge of every group in ONE cooperative launch."""
         pr, y = plan.prec, self.y
@@ -1277,6 +1317,11 @@ class BnGroupOp:
                 m._emit_finalize(plan)
                 m._emit_apply(plan)
             return
+        if peer.active() and all(m.out.Cp >= m.y.Cp for m in ms):
+            for m in ms:                     # exchange inside each launch: no collective, nothing to group
+                m._emit_fwd_peer(plan)
+            plan.n_peer_bn_fwd = getattr(plan, "n_peer_bn_fwd", 0) + len(ms)
+            return
         f32 = dict(dtype=torch.float32, device=plan.device)
         offs, total = [], 0
         for m in ms:
@@ -1316,6 +1361,11 @@ class BnGroupOp:
                     continue
                 m._emit_bwd_reduce(plan)
                 m._emit_bwd_apply(plan)
+            return
+        if peer.active() and all(m.lanes == m.y.Cp for m in ms):
+            for m in ms:
+                m._emit_bwd_peer(plan)
+            plan.n_peer_bn_bwd = getattr(plan, "n_peer_bn_bwd", 0) + len(ms)
             return
         f32 = dict(dtype=torch.float32, device=plan.device)
         offs, total = [], 0

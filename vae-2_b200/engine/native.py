@@ -94,6 +94,15 @@ _PROTOS = {
                                i32, i32, i32, vp, i32, i64, vp],
     "vae2_bn_sync_bwd": [i32, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                          i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, f32, vp],
+    "vae2_ipc_alloc": [i64, C.POINTER(vp), vp],
+    "vae2_ipc_open": [vp, C.POINTER(vp)],
+    "vae2_ipc_close": [vp],
+    "vae2_ipc_free": [vp],
+    "vae2_bn_peer_setup": [i32, i32, C.POINTER(vp), vp, vp],
+    "vae2_bn_fwd_fused_peer": [vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp,
+                               i32, i32, i32, i64, i32, vp],
+    "vae2_bn_bwd_fused_peer": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                               i32, vp, vp, i32, i32, i32, i32, i32, f32, i64, i32, vp],
     "vae2_fuse_sum": [C.POINTER(FuseSrc), i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "vae2_fuse_bwd_same": [vp, vp, C.POINTER(FuseDst), i32, i32, i64, i32, i32, i32, i32, vp],
     "vae2_fuse_bwd_up": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -139,6 +148,8 @@ def lib():
         h.vae2_conv2d_wgrad_f32x2_workspace.restype = C.c_longlong
         h.vae2_conv2d_tf32_dims.argtypes = [C.POINTER(ConvGeom), ip, ip, ip, ip]
         h.vae2_conv2d_tf32_dims.restype = None
+        h.vae2_bn_peer_slot_words.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        h.vae2_bn_peer_slot_words.restype = C.c_longlong
         h.vae2_status_string.argtypes = [C.c_int]
         h.vae2_status_string.restype = C.c_char_p
         h.vae2_last_cuda_error.argtypes = []
