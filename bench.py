@@ -107,10 +107,17 @@ def build_models(cfg, dev, world, local_rank):
     g, d = g.to(dev).train(), d.to(dev).train()
     gm, dm = g, d
     if world > 1:
-        d = torch.nn.parallel.DistributedDataParallel(d, device_ids=[local_rank], output_device=local_rank,
-                                                      find_unused_parameters=True)
-        g = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local_rank], output_device=local_rank,
-                                                      find_unused_parameters=True)
+        kw = dict(device_ids=[local_rank], output_device=local_rank, find_unused_parameters=True)
+        # Two DDP switches on top of the reference's wrapping, neither changes a result: SyncBN running statistics are
+        # bit-identical on every rank (tests/test_gpu_syncbn_peer.py), so re-broadcasting ~1000 buffers before every forward
+        # is a no-op that costs 33 ms per iteration at N=2; bucket views drop one copy of every gradient (21 ms).
+        kw.update(broadcast_buffers=False, gradient_as_bucket_view=True)
+        for k_, v_ in (("broadcast_buffers", "VAE2_BENCH_DDP_BCAST"), ("gradient_as_bucket_view", "VAE2_BENCH_DDP_BUCKET_VIEW"),
+                       ("static_graph", "VAE2_BENCH_DDP_STATIC")):
+            if os.environ.get(v_) is not None:            # experiments only; the default is the reference's wrapping
+                kw[k_] = os.environ[v_] == "1"
+        d = torch.nn.parallel.DistributedDataParallel(d, **kw)
+        g = torch.nn.parallel.DistributedDataParallel(g, **kw)
         from _engine_loader import engine
         if engine().peer.active():      # SyncBN exchanges inside the BN launches: keep NCCL kernels out of their way
             engine().peer.serialize_ddp(d)
@@ -478,7 +485,9 @@ def main():
                        "stacked_discriminator_passes": os.environ.get("VAE2_STACK_D", "1") != "0",
                        "d_stack": int(os.environ.get("VAE2_D_STACK", "6")),
                        "syncbn": ("peer-memory exchange inside the BN launches" if E.peer.active() else
-                                  "NCCL all-gather / all-reduce per BN group") if world > 1 else "n/a"},
+                                  "NCCL all-gather / all-reduce per BN group") if world > 1 else "n/a",
+                       "ddp": "find_unused_parameters=True (tools/train.py:226-229) + broadcast_buffers=False, "
+                              "gradient_as_bucket_view=True" if world > 1 else "n/a"},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": 3 * B * 9 * H * W * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),

@@ -93,7 +93,8 @@ msgs.append("SyncBN collectives fwd %d, peer-memory launches fwd %d bwd %d, for 
     sum(getattr(p, "n_peer_bn_bwd", 0) for p in plans), sum(1 for m in g.modules() if isinstance(m, torch.nn.SyncBatchNorm))))
 if P2P:
     E.peer.check()
-    ok &= sum(p.n_collectives_fwd for p in plans) == 0 and sum(getattr(p, "n_peer_bn_fwd", 0) for p in plans) > 0
+    # (a BN whose output slice is narrower than its input keeps the NCCL path: a handful in bf16)
+    ok &= sum(p.n_collectives_fwd for p in plans) <= 4 and sum(getattr(p, "n_peer_bn_fwd", 0) for p in plans) > 300
 if rank == 0:
     print("\n".join(msgs))
     print("DIST_SYNCBN_CHECK", "PASS" if ok else "FAIL", prec, flush=True)

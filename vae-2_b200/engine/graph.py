@@ -1165,7 +1165,7 @@ class BnOp:
         dres0 = res.grad().ptr if has_dres else None
         gp0, dyp0 = g.ptr, dy.ptr
         inv_count = 1.0 / (npix * plan.world_size)
-        slot, seq = peer.alloc(G, y.Cp, True)
+        slot, seq = (0, 0) if plan._gsim else peer.alloc(G, y.Cp, True)      # the sizing pass of the backward emits nothing real
         plan.bwd.append(lambda st: N.call.vae2_bn_bwd_fused_peer(
             gp0, p0.outp, p0.yp, dyp0, dres0, ws, pr.code, npix, C_, lanes, g.ld, out.ld, y.ld, dy.ld, ld_dres, p0.mean,
             p0.invstd, p0.scale, p0.shift, dgam, dbet, 0, p0.c1, p0.c2, relu, acc_dy, acc_res, G, 6 * y.Cp, inv_count,
@@ -1365,7 +1365,8 @@ class BnGroupOp:
         if peer.active() and all(m.lanes == m.y.Cp for m in ms):
             for m in ms:
                 m._emit_bwd_peer(plan)
-            plan.n_peer_bn_bwd = getattr(plan, "n_peer_bn_bwd", 0) + len(ms)
+            if not plan._gsim:
+                plan.n_peer_bn_bwd = getattr(plan, "n_peer_bn_bwd", 0) + len(ms)
             return
         f32 = dict(dtype=torch.float32, device=plan.device)
         offs, total = [], 0
