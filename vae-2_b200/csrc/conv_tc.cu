@@ -435,6 +435,8 @@ struct WParams {
     int a_atoms_stage;         // atoms reserved for A per stage
     int stages;
     int tmem_cols;
+    int dual;                  // fp32 gradient from bf16 hi/lo planes in ONE pass: A = {x_hi, x_lo}, B = {dy_hi, dy_lo};
+                               // per group two accumulators: x_hi*dy_hi | x_hi*dy_lo + x_lo*dy_hi, added in the epilogue
     float* ws;                 // [nranges][M_total][Cout_p]
 };
 
@@ -457,13 +459,15 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t row_by
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_dyl, const WParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t rowA = p.atomA * 2, rowB = p.atomB * 2;
     const uint32_t atomA_bytes = p.KP * rowA, atomB_bytes = p.KP * rowB;     // multiples of 1024 for KP = 32/64... (>= 512)
     const uint32_t a_bytes = (uint32_t)p.a_atoms_stage * atomA_bytes;
     const uint32_t b_bytes = (uint32_t)(p.NT / p.atomB) * atomB_bytes;
-    const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    const uint32_t planes = p.dual ? 2u : 1u;                                // stage = [A_hi][A_lo][B_hi][B_lo]
+    const uint32_t stage_bytes = ((planes * (a_bytes + b_bytes) + 1023) / 1024) * 1024;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;
@@ -500,7 +504,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(t1 - t0 + 1) * nchunkA * atomA_bytes + b_bytes;
+            const uint32_t tx_bytes = planes * ((uint32_t)(t1 - t0 + 1) * nchunkA * atomA_bytes + b_bytes);
             for (int i = 0; i < n_my_tiles; ++i) {
                 const int pt = range + i * p.nranges;
                 const int b = pt / per_img;
@@ -513,8 +517,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const int ky = tap / p.ksz, kx = tap - ky * p.ksz;
                     tma_load_5d(sa + (size_t)(tap - t0) * nchunkA * atomA_bytes, &map_x, &full[stage], 0,
                                 w0 * p.sA + kx - p.pad, h0 * p.sA + ky - p.pad, b, 0);
+                    if (p.dual)
+                        tma_load_5d(sa + a_bytes + (size_t)(tap - t0) * nchunkA * atomA_bytes, &map_xl, &full[stage], 0,
+                                    w0 * p.sA + kx - p.pad, h0 * p.sA + ky - p.pad, b, 0);
                 }
-                tma_load_5d(sa + a_bytes, &map_dy, &full[stage], 0, w0, h0, b, n0 / p.atomB);
+                tma_load_5d(sa + planes * a_bytes, &map_dy, &full[stage], 0, w0, h0, b, n0 / p.atomB);
+                if (p.dual) tma_load_5d(sa + 2 * a_bytes + b_bytes, &map_dyl, &full[stage], 0, w0, h0, b, n0 / p.atomB);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -523,19 +531,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = Cout_p, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(2 * p.NT >> 3) << 17);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < n_my_tiles; ++i) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint32_t sb = sa + planes * a_bytes;
                 for (int g = g_lo; g < g_hi; ++g) {
                     const uint32_t a_rel = (uint32_t)(g * 128 - t0 * p.Cin_p) / (uint32_t)p.atomA;   // first atom of this group
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_lo) * p.NT);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_lo) * p.NT) * planes;
                     for (int k = 0; k < p.KP / 16; ++k) {
-                        umma_bf16(d_tmem, make_desc_mn(sa + a_rel * atomA_bytes + k * 16 * rowA, rowA, atomA_bytes),
-                                  make_desc_mn(sb + k * 16 * rowB, rowB, atomB_bytes), idesc, (i | k) ? 1u : 0u);
+                        const uint64_t da = make_desc_mn(sa + a_rel * atomA_bytes + k * 16 * rowA, rowA, atomA_bytes);
+                        const uint64_t db = make_desc_mn(sb + k * 16 * rowB, rowB, atomB_bytes);
+                        const uint32_t acc = (i | k) ? 1u : 0u;
+                        if (!p.dual) {
+                            umma_bf16(d_tmem, da, db, idesc, acc);
+                            continue;
+                        }
+                        // x_hi * [dy_hi | dy_lo]: the two dy planes lie back to back, so one instruction of N = 2*NT
+                        // fills both accumulators (two instructions when 2*NT > 256); then x_lo * dy_hi into the second
+                        const uint64_t dal = make_desc_mn(sa + a_bytes + a_rel * atomA_bytes + k * 16 * rowA, rowA, atomA_bytes);
+                        if (2 * p.NT <= 256) {
+                            umma_bf16(d_tmem, da, db, idesc2, acc);
+                        } else {
+                            umma_bf16(d_tmem, da, db, idesc, acc);
+                            umma_bf16(d_tmem + (uint32_t)p.NT, da, make_desc_mn(sb + b_bytes + k * 16 * rowB, rowB, atomB_bytes), idesc, acc);
+                        }
+                        umma_bf16(d_tmem + (uint32_t)p.NT, dal, db, idesc, 1u);
                     }
                 }
                 umma_commit(&empty[stage]);
@@ -550,11 +574,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         float* ws = p.ws + (size_t)range * p.M_total * p.Cout_p;
         for (int g = g_lo; g < g_hi; ++g) {
             const int m = g * 128 + q * 32 + lane;
-            const uint32_t t0a = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_lo) * p.NT);
+            const uint32_t t0a = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_lo) * p.NT) * planes;
             for (int c0 = 0; c0 < p.NT; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(t0a + c0, v);
-                tmem_ld_wait();
+                if (p.dual) {
+                    uint32_t u[16];
+                    tmem_ld16(t0a + p.NT + c0, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+                } else {
+                    tmem_ld_wait();
+                }
                 if (m < p.M_total && n0 + c0 < p.Cout_p) {
                     float4* dst = reinterpret_cast<float4*>(ws + (size_t)m * p.Cout_p + n0 + c0);
                     if (n_my_tiles > 0) {
@@ -623,6 +655,7 @@ struct WHParams {
     int tiles_w, tiles_h, total_ptiles, nranges;
     int mmas_per_row;           // 1 (Cin_p = 32: kx 0..3 in one M=128) or 2 (Cin_p = 64: kx {0,1} and {2,3})
     int stages, tmem_cols;
+    int dual;                   // hi/lo planes of an fp32 gradient in one pass (see WParams::dual)
     float* ws;                  // [nranges][9][Cin_p][Cout_p]
 };
 
@@ -638,14 +671,16 @@ __device__ __forceinline__ uint64_t make_desc_mn_ex(uint32_t saddr, uint32_t row
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WHParams p) {
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_dyl, const WHParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t rowA = p.Cin_p * 2, rowB = p.atomB * 2;
     const uint32_t a_bytes = kHaloBW * kHaloBH * rowA;                         // TMA transaction size of the halo tile
     const uint32_t a_stage = (a_bytes + 4 * rowA + 1023) / 1024 * 1024;       // + the junk tap's overhang
     const uint32_t atomB_bytes = 128 * rowB;
     const uint32_t b_bytes = (uint32_t)(p.NT / p.atomB) * atomB_bytes;
-    const uint32_t stage_bytes = a_stage + ((b_bytes + 1023) / 1024) * 1024;
+    const uint32_t planes = p.dual ? 2u : 1u;                                  // stage = [A_hi][A_lo][B_hi B_lo]
+    const uint32_t stage_bytes = planes * a_stage + ((planes * b_bytes + 1023) / 1024) * 1024;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;
@@ -678,9 +713,13 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const int h0 = (r / p.tiles_w) * kHaloTH, w0 = (r % p.tiles_w) * kHaloTW;
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&full[stage], a_bytes + b_bytes);
+                mbar_expect_tx(&full[stage], planes * (a_bytes + b_bytes));
                 tma_load_4d(sa, &map_x, &full[stage], 0, w0 - 1, h0 - 1, b);
-                tma_load_5d(sa + a_stage, &map_dy, &full[stage], 0, w0, h0, b, 0);
+                tma_load_5d(sa + planes * a_stage, &map_dy, &full[stage], 0, w0, h0, b, 0);
+                if (p.dual) {
+                    tma_load_4d(sa + a_stage, &map_xl, &full[stage], 0, w0 - 1, h0 - 1, b);
+                    tma_load_5d(sa + 2 * a_stage + b_bytes, &map_dyl, &full[stage], 0, w0, h0, b, 0);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -689,6 +728,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = NT, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(2 * p.NT >> 3) << 17);
             const uint32_t atoms_per_mma = 128u / (uint32_t)p.Cin_p;            // 4 or 2 taps (kx) per instruction
             int stage = 0;
             uint32_t phase = 0;
@@ -696,14 +736,21 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sb = sa + a_stage;
+                const uint32_t sb = sa + planes * a_stage;
                 for (int ky = 0; ky < 3; ++ky)
                     for (int j = 0; j < p.mmas_per_row; ++j) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((ky * p.mmas_per_row + j) * p.NT);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((ky * p.mmas_per_row + j) * p.NT) * planes;
                         for (int ks = 0; ks < kHaloTH / 2; ++ks) {             // 16 pixels = two patch rows per K step
                             const uint32_t a0 = sa + (uint32_t)(((2 * ks + ky) * kHaloBW) + j * (int)atoms_per_mma) * rowA;
-                            umma_bf16(d_tmem, make_desc_mn_ex(a0, rowA, rowA, kHaloBW * rowA),
-                                      make_desc_mn(sb + (uint32_t)ks * 16 * rowB, rowB, atomB_bytes), idesc, (i | ks) ? 1u : 0u);
+                            const uint64_t da = make_desc_mn_ex(a0, rowA, rowA, kHaloBW * rowA);
+                            const uint64_t db = make_desc_mn(sb + (uint32_t)ks * 16 * rowB, rowB, atomB_bytes);
+                            const uint32_t acc = (i | ks) ? 1u : 0u;
+                            if (!p.dual) {
+                                umma_bf16(d_tmem, da, db, idesc, acc);
+                                continue;
+                            }
+                            umma_bf16(d_tmem, da, db, idesc2, acc);           // x_hi * [dy_hi | dy_lo], N = 2*NT <= 256
+                            umma_bf16(d_tmem + (uint32_t)p.NT, make_desc_mn_ex(a0 + a_stage, rowA, rowA, kHaloBW * rowA), db, idesc, 1u);
                         }
                     }
                 umma_commit(&empty[stage]);
@@ -721,11 +768,19 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int j = 0; j < p.mmas_per_row; ++j) {
                 const int m = q * 32 + lane;                                    // accumulator row = (kx_local, ci)
                 const int kx = j * atoms_per_mma + m / p.Cin_p, ci = m % p.Cin_p;
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ky * p.mmas_per_row + j) * p.NT);
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ky * p.mmas_per_row + j) * p.NT) * planes;
                 for (int c0 = 0; c0 < p.NT; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(t0 + c0, v);
-                    tmem_ld_wait();
+                    if (p.dual) {
+                        uint32_t u[16];
+                        tmem_ld16(t0 + p.NT + c0, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     if (kx < 3 && c0 < p.Cout_p) {
                         float4* dst = reinterpret_cast<float4*>(ws + ((size_t)(ky * 3 + kx) * p.Cin_p + ci) * p.Cout_p + c0);
 #pragma unroll
@@ -743,7 +798,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // fills p (except ws); returns the workspace floats, < 0 when the shape is not a halo candidate
-static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p) {
+static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p, int dual = 0) {
     if (const char* e = getenv("VAE2_WGRAD_HALO")) { if (atoi(e) == 0) return -1; }
     if (g.k != 3 || g.stride != 1 || g.H != g.Ho || g.W != g.Wo) return -1;
     if (!(g.Cin_p == 32 || g.Cin_p == 64) || g.ldx % 8 || g.Cout_p > 256 || g.Cout_p % 16) return -1;
@@ -751,8 +806,10 @@ static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p) {
     p.atomB = g.Cout_p % 64 == 0 ? 64 : (g.Cout_p % 32 == 0 ? 32 : 16);
     p.NT = g.Cout_p;
     p.mmas_per_row = g.Cin_p == 32 ? 1 : 2;
-    const int cols = 3 * p.mmas_per_row * p.NT;
-    if (cols > 512) return -1;
+    p.dual = dual ? 1 : 0;
+    const int planes = dual ? 2 : 1;
+    const int cols = 3 * p.mmas_per_row * p.NT * planes;
+    if (cols > 512 || (dual && 2 * p.NT > 256)) return -1;
     p.tmem_cols = next_pow2_cols(cols);
     p.tiles_w = (g.W + kHaloTW - 1) / kHaloTW;
     p.tiles_h = (g.H + kHaloTH - 1) / kHaloTH;
@@ -761,7 +818,9 @@ static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p) {
     const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
     const long long b_stage = ((long long)p.NT * 128 * 2 + 1023) / 1024 * 1024;
     const int ctas = p.tmem_cols <= 256 ? 2 : 1;
-    int stages = (int)((kSmemBudget / ctas - 2048) / (a_stage + b_stage));
+    const long long stage_b = planes * a_stage + ((long long)planes * p.NT * 128 * 2 + 1023) / 1024 * 1024;
+    (void)b_stage;
+    int stages = (int)((kSmemBudget / ctas - 2048) / stage_b);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -1;
     p.stages = stages;
@@ -774,10 +833,10 @@ static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p) {
 static int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
 // Fills p (everything except ws) and returns the workspace size in floats; <0 if unsupported.
-static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages, int ctas);
+static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages, int ctas, int dual);
 
 // 64 pixels per stage when that still leaves a 3-deep pipeline, else 32
-static long long plan_wgrad(const ConvGeom& g, WParams& p) {
+static long long plan_wgrad(const ConvGeom& g, WParams& p, int dual = 0) {
     int first = 64;
     if (const char* e = getenv("VAE2_WGRAD_KP")) { const int v = atoi(e); if (v == 32) first = 32; }
     // Two co-resident CTAs per SM (each half the shared memory, <= 256 TMEM columns) when the operands are narrow: the
@@ -787,20 +846,20 @@ static long long plan_wgrad(const ConvGeom& g, WParams& p) {
     if (const char* e = getenv("VAE2_WGRAD_CTAS")) { const int v = atoi(e); if (v == 1) ctas = 1; }
     if (ctas == 2) {
         if (first == 64) {
-            const long long r = plan_wgrad_kp(g, p, 64, 3, 2);
+            const long long r = plan_wgrad_kp(g, p, 64, 3, 2, dual);
             if (r >= 0) return r;
         }
-        const long long r = plan_wgrad_kp(g, p, 32, 3, 2);
+        const long long r = plan_wgrad_kp(g, p, 32, 3, 2, dual);
         if (r >= 0) return r;
     }
     if (first == 64) {
-        const long long r = plan_wgrad_kp(g, p, 64, 3, 1);
+        const long long r = plan_wgrad_kp(g, p, 64, 3, 1, dual);
         if (r >= 0) return r;
     }
-    return plan_wgrad_kp(g, p, 32, 2, 1);
+    return plan_wgrad_kp(g, p, 32, 2, 1, dual);
 }
 
-static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages, int ctas) {
+static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_stages, int ctas, int dual) {
     // K runs over OUTPUT pixels (Ho x Wo); x is sampled at stride g.stride
     p.B = g.B; p.H = g.Ho; p.W = g.Wo; p.sA = g.stride;
     p.n_tiles = (g.Cout_p + 255) / 256;
@@ -820,7 +879,9 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
     const int groups_total = (p.M_total + 127) / 128;
     // groups per CTA ("set"): as many as TMEM holds (512 columns), shrunk until the stage ring is deep enough
     const int nchunkA = g.Cin_p / p.atomA;
-    int sg_max = (512 / ctas) / p.NT;
+    const int planes = dual ? 2 : 1;
+    p.dual = dual ? 1 : 0;
+    int sg_max = (512 / ctas) / (p.NT * planes);
     if (sg_max > groups_total) sg_max = groups_total;
     if (sg_max < 1) return -1;
     if (ctas > 1 && (sg_max < groups_total || p.NT > 64)) return -1;   // co-residency: one set holds every accumulator, narrow N
@@ -841,7 +902,7 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
             if (atoms > w) w = atoms;
         }
         const long long a_b = (long long)w * p.KP * p.atomA * 2, b_b = (long long)p.NT * p.KP * 2;
-        const long long sb = ((a_b + b_b + 1023) / 1024) * 1024;
+        const long long sb = ((planes * (a_b + b_b) + 1023) / 1024) * 1024;
         int st_ = (int)((kSmemBudget / ctas - (ctas > 1 ? 2048 : 0)) / sb);
         if (st_ > kMaxStages) st_ = kMaxStages;
         if (st_ >= min_stages) { sg = cand; stages = st_; worst = w; break; }
@@ -849,7 +910,7 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
     if (sg == 0) return -1;
     p.set_groups = sg;
     p.nsets = (groups_total + sg - 1) / sg;
-    p.tmem_cols = next_pow2_cols(sg * p.NT);
+    p.tmem_cols = next_pow2_cols(sg * p.NT * planes);
     p.a_atoms_stage = worst;
     p.stages = stages;
     int nranges = ctas * kNumSMs / (p.nsets * p.n_tiles);
@@ -1119,58 +1180,73 @@ struct WgradPlan {
     long long n;        // floats of one slot = taps * Cin_p * Cout_p
 };
 
-static int plan_wgrad_any(const ConvGeom& g, WgradPlan& P) {
-    P.part = plan_wgrad_halo(g, P.h);
+static int plan_wgrad_any(const ConvGeom& g, WgradPlan& P, int dual = 0) {
+    P.part = plan_wgrad_halo(g, P.h, dual);
     if (P.part > 0) {
         P.halo = true; P.nslots = P.h.nranges; P.n = 9LL * g.Cin_p * g.Cout_p;
         return 0;
     }
     P.halo = false;
-    P.part = plan_wgrad(g, P.w);
+    P.part = plan_wgrad(g, P.w, dual);
     if (P.part < 0) return -1;
     P.nslots = P.w.nranges; P.n = (long long)P.w.M_total * g.Cout_p;
     return 0;
 }
 
 // ws[slot][tap][Cin_p][Cout_p] = partial weight gradients of bf16 x [B][H][W][ldx] and dy [B][Ho][Wo][ldy]
-static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGeom& g, const WgradPlan& P, cudaStream_t st) {
+// (xl, dyl: the low planes of a dual plan, else null)
+static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGeom& g, const WgradPlan& P, cudaStream_t st,
+                          const void* xl = nullptr, const void* dyl = nullptr) {
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) return VAE2_ERR_UNSUPPORTED;
-    CUtensorMap map_x, map_dy;
+    CUtensorMap map_x, map_dy, map_xl, map_dyl;
+    const bool dual = P.halo ? P.h.dual != 0 : P.w.dual != 0;
+    if (dual && (xl == nullptr || dyl == nullptr)) return VAE2_ERR_ARG;
     if (P.halo) {
         WHParams p = P.h;
         p.ws = ws;
-        {
+        for (int pl = 0; pl < (dual ? 2 : 1); ++pl) {
             cuuint64_t dims[4] = {(cuuint64_t)g.Cin_p, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
             cuuint64_t strides[3] = {(cuuint64_t)g.ldx * 2, (cuuint64_t)g.W * g.ldx * 2, (cuuint64_t)g.H * g.W * g.ldx * 2};
             cuuint32_t box[4] = {(cuuint32_t)g.Cin_p, (cuuint32_t)kHaloBW, (cuuint32_t)kHaloBH, 1};
             cuuint32_t es[4] = {1, 1, 1, 1};
-            if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz(g.Cin_p), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            if (enc(pl ? &map_xl : &map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(pl ? xl : x), dims, strides, box,
+                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz(g.Cin_p), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return VAE2_ERR_ARG;
         }
         if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, kHaloTW, kHaloTH, 1)) return VAE2_ERR_ARG;
-        const int rowA = g.Cin_p * 2;
+        if (dual) {
+            if (make_map5(enc, &map_dyl, dyl, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, kHaloTW, kHaloTH, 1)) return VAE2_ERR_ARG;
+        } else {
+            map_xl = map_x; map_dyl = map_dy;
+        }
+        const int rowA = g.Cin_p * 2, planes = dual ? 2 : 1;
         const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
-        const long long b_stage = ((long long)p.NT * 128 * 2 + 1023) / 1024 * 1024;
-        const size_t smem = (size_t)p.stages * (a_stage + b_stage) + 1024 + (2 * kMaxStages + 4) * 8 + 16;
+        const long long b_stage = ((long long)planes * p.NT * 128 * 2 + 1023) / 1024 * 1024;
+        const size_t smem = (size_t)p.stages * (planes * a_stage + b_stage) + 1024 + (2 * kMaxStages + 4) * 8 + 16;
         static bool attr_set = false;
         if (!attr_set) {
             if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
                 return VAE2_ERR_CUDA;
             attr_set = true;
         }
-        wgrad_halo_kernel<<<p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
+        wgrad_halo_kernel<<<p.nranges, kThreads, smem, st>>>(map_x, map_dy, map_xl, map_dyl, p);
         return check_launch();
     }
     WParams p = P.w;
     p.ws = ws;
     if (make_map5(enc, &map_x, x, p.atomA, g.Cin_p, g.Cin_p, g.ldx, g.B, g.H, g.W, p.TW, p.TH, g.stride)) return VAE2_ERR_ARG;
     if (make_map5(enc, &map_dy, dy, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, p.TW, p.TH, 1)) return VAE2_ERR_ARG;
+    if (dual) {
+        if (make_map5(enc, &map_xl, xl, p.atomA, g.Cin_p, g.Cin_p, g.ldx, g.B, g.H, g.W, p.TW, p.TH, g.stride)) return VAE2_ERR_ARG;
+        if (make_map5(enc, &map_dyl, dyl, p.atomB, g.Cout_p, p.NT, g.ldy, g.B, g.Ho, g.Wo, p.TW, p.TH, 1)) return VAE2_ERR_ARG;
+    } else {
+        map_xl = map_x; map_dyl = map_dy;
+    }
     const long long a_bytes = (long long)p.a_atoms_stage * p.KP * p.atomA * 2;
     const long long b_bytes = (long long)p.NT * p.KP * 2;
-    const long long stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    const long long stage_bytes = (((dual ? 2 : 1) * (a_bytes + b_bytes) + 1023) / 1024) * 1024;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 4) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1178,7 +1254,7 @@ static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGe
             return VAE2_ERR_CUDA;
         attr_set = true;
     }
-    wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, p);
+    wgrad_tc_kernel<<<p.nsets * p.n_tiles * p.nranges, kThreads, smem, st>>>(map_x, map_dy, map_xl, map_dyl, p);
     return check_launch();
 }
 }  // namespace tc
@@ -1263,6 +1339,20 @@ static ConvGeom geom16(const ConvGeom& g) {
     return q;
 }
 
+// plan of the plane products: the single-pass dual plan when it exists (VAE2_WGRAD_DUAL=0: three separate products)
+static int f32x2_plan(const ConvGeom& q, WgradPlan& P) {
+    bool dual = true;
+    if (const char* e = getenv("VAE2_WGRAD_DUAL")) { if (atoi(e) == 0) dual = false; }
+    WgradPlan D;
+    if (dual && plan_wgrad_any(q, D, 1) == 0) {
+        // the second accumulator halves the M groups a CTA holds; when that splits the problem into more sets (each re-reads
+        // the operand tiles: 270 -> 270 measured 1.04 vs 0.87 ms) the three separate products win
+        if (D.halo || plan_wgrad_any(q, P, 0) != 0 || P.halo || D.w.nsets <= P.w.nsets) { P = D; return 0; }
+        return 0;
+    }
+    return plan_wgrad_any(q, P, 0);
+}
+
 }  // namespace tc
 
 // bytes of workspace conv_wgrad_f32x2 needs (negative: unsupported geometry)
@@ -1270,8 +1360,8 @@ long long conv_wgrad_f32x2_workspace(const ConvGeom& g) {
     const ConvGeom q = tc::geom16(g);
     if (!conv_tc_supported(q)) return -1;
     tc::WgradPlan P;
-    if (tc::plan_wgrad_any(q, P)) return -1;
-    const long long part = P.part;                          // floats of ONE product's split-K slots
+    if (tc::f32x2_plan(q, P)) return -1;
+    const long long part = P.part;                          // floats of ONE product's split-K slots (dual plans: of the pass)
     const long long nx = (long long)g.B * g.H * g.W * q.Cin_p, ny = (long long)g.B * g.Ho * g.Wo * q.Cout_p;
     const long long dw16 = P.n;
     auto al = [](long long b) { return (b + 255) / 256 * 256; };
@@ -1283,7 +1373,8 @@ int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspac
     const ConvGeom q = geom16(g);
     if (!conv_tc_supported(q) || g.Cin_p % 4 || g.Cout_p % 4 || g.ldx % 4 || g.ldy % 4) return VAE2_ERR_UNSUPPORTED;
     WgradPlan P;
-    if (plan_wgrad_any(q, P)) return VAE2_ERR_UNSUPPORTED;
+    if (f32x2_plan(q, P)) return VAE2_ERR_UNSUPPORTED;
+    const bool dual = P.halo ? P.h.dual != 0 : P.w.dual != 0;
     const long long part = P.part;
     const long long npx = (long long)g.B * g.H * g.W, npy = (long long)g.B * g.Ho * g.Wo;
     const long long nx = npx * q.Cin_p, ny = npy * q.Cout_p;
@@ -1298,16 +1389,23 @@ int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspac
     float* slots = reinterpret_cast<float*>(w);
     w += al(3 * part * 4);
     float* dw16 = reinterpret_cast<float*>(w);
-    note_kernel(P.halo ? "tc::wgrad_halo_kernel (f32x2 planes)" : "tc::wgrad_tc_kernel (f32x2 planes)");
+    note_kernel(P.halo ? (dual ? "tc::wgrad_halo_kernel dual (f32x2 planes)" : "tc::wgrad_halo_kernel (f32x2 planes)")
+                       : (dual ? "tc::wgrad_tc_kernel dual (f32x2 planes)" : "tc::wgrad_tc_kernel (f32x2 planes)"));
     split_planes_kernel<<<stream_grid(npx * (q.Cin_p / 8), 256), 256, 0, st>>>(x, xh, xl, npx, g.Cin_p, g.ldx, q.Cin_p);
     split_planes_kernel<<<stream_grid(npy * (q.Cout_p / 8), 256), 256, 0, st>>>(dy, yh, yl, npy, g.Cout_p, g.ldy, q.Cout_p);
     if (int e = check_launch()) return e;
-    const __nv_bfloat16* xa[3] = {xl, xh, xh};      // smallest products first in the fold: lo*hi, hi*lo, hi*hi
-    const __nv_bfloat16* ya[3] = {yh, yl, yh};
-    for (int t = 0; t < 3; ++t)
-        if (int e = wgrad_partials(xa[t], ya[t], slots + (long long)t * part, q, P, st)) return e;
     const long long n = P.n;
-    wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, 3 * P.nslots);
+    if (dual) {
+        // one pass: x_hi*dy_hi in one accumulator, x_hi*dy_lo + x_lo*dy_hi in a second one, added in the epilogue
+        if (int e = wgrad_partials(xh, yh, slots, q, P, st, xl, yl)) return e;
+        wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, P.nslots);
+    } else {
+        const __nv_bfloat16* xa[3] = {xl, xh, xh};      // smallest products first in the fold: lo*hi, hi*lo, hi*hi
+        const __nv_bfloat16* ya[3] = {yh, yl, yh};
+        for (int t = 0; t < 3; ++t)
+            if (int e = wgrad_partials(xa[t], ya[t], slots + (long long)t * part, q, P, st)) return e;
+        wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, 3 * P.nslots);
+    }
     const int total = g.k * g.k * g.Cin_p * g.Cout_p;
     crop_dw_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw16, dwp, g.k * g.k, g.Cin_p, g.Cout_p, q.Cin_p, q.Cout_p);
     return check_launch();

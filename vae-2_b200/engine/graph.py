@@ -507,9 +507,19 @@ class Plan:
         x2_bytes = 0
         if self.training and os.environ.get("VAE2_FP32_TC_WGRAD", "1") != "0":
             wmin = int(os.environ.get("VAE2_FP32_TC_WGRAD_MIN_LANES", "40"))
-            for o in x3:
+            # the 3x3 stride-1 layers of <= 32 input lanes (18 -> 18) as well: their planes go through the halo-tile
+            # kernel in ONE pass (csrc/conv_tc.cu, dual mode) whatever engine runs their forward
+            narrow = os.environ.get("VAE2_FP32_TC_WGRAD_NARROW", "1") != "0" and self.fp32_tc not in ("0", "")
+            for o in convs:
+                if self.prec.code != 0 or dev.type != "cuda" or o.x.H * o.x.W <= 1:
+                    continue
+                wide = o in x3 and max(o.x.root_cp(), o.y.Cp) >= wmin
+                halo1 = (narrow and o.conv.kernel_size[0] == 3 and o.conv.stride[0] == 1 and 16 < o.x.root_cp() <= 32
+                         and o.y.Cp <= 80)
+                if not (wide or halo1):
+                    continue
                 need = N.lib().vae2_conv2d_wgrad_f32x2_workspace(C.byref(o._geom()))
-                o.wgrad_x2 = need > 0 and o.conv.weight.requires_grad and max(o.x.root_cp(), o.y.Cp) >= wmin
+                o.wgrad_x2 = need > 0 and o.conv.weight.requires_grad
                 if o.wgrad_x2:
                     x2_bytes = max(x2_bytes, need)
         self.wgrad_x2_ws = torch.empty(x2_bytes, dtype=torch.uint8, device=dev) if x2_bytes else None

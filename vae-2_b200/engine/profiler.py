@@ -52,7 +52,8 @@ def describe(name, args):
         if name == "vae2_conv2d_wgrad_tc":
             kern = kern + "+wgrad_reduce_kernel"
         if name == "vae2_conv2d_wgrad_f32x2":
-            kern = "split_planes+3x " + kern.replace(" (f32x2 planes)", "") + "+reduce (fp32 wgrad)"
+            dual = " dual" in kern
+            kern = "split_planes+" + ("" if dual else "3x ") + kern.replace(" (f32x2 planes)", "") + "+reduce (fp32 wgrad)"
         return kern, shape, flop, float(by)
     if name in ("vae2_bn_fwd_fused", "vae2_bn_fwd_fused_groups"):
         code, npix, C_ = args[4], args[5], args[6]
