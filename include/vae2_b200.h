@@ -214,7 +214,7 @@ int vae2_bn_sync_bwd(int phase, const void* g, const void* a, const void* y, voi
  * (nn/modules/_functions.py:39-122: all_gather of the statistics, all_reduce of the backward sums) for tools/train.py:217.
  *   vae2_ipc_alloc / vae2_ipc_open : one zeroed device allocation per process + its 64-byte CUDA IPC handle; peers map it.
  *   vae2_bn_peer_setup             : bases[r] = rank r's mailbox as mapped in this process, seq = zeroed uint32 per op,
- *                                    err = zeroed int (set when a peer did not answer within ~10 s; the host must raise).
+ *                                    err = zeroed int (set when a peer did not answer within ~60 s; the host must raise).
  *   vae2_bn_peer_slot_words        : 8-byte words an op needs in the mailbox; the host gives every op (and direction) its own
  *                                    slot_word offset and seq_index, identical on every rank.
  * Gradient all-reduce kernels must not be in flight while these launches wait for their peers. */

@@ -608,10 +608,10 @@ __device__ __forceinline__ void prof_mark(unsigned long long* prof, int i) {
 // bit-identical statistics.  Each value travels as one 8-byte word {float bits, sequence number}: an aligned 8-byte store
 // is single-copy atomic, so the flag can never be seen ahead of its data and no fence is needed (NCCL's LL protocol).  The
 // sequence number comes from a per-op device counter (the launch arguments are frozen inside CUDA graphs); words of
-// consecutive launches of an op alternate between two buffers.  A wait that exceeds kPeerSpinLimit sets a sticky error flag
+// consecutive launches of an op alternate between two buffers.  A wait that exceeds kPeerSpinLimit (~60 s) sets a sticky error flag
 // and gives up (the host raises at the end of the step) instead of hanging the GPU.
 constexpr int kMaxPeers = 8;
-constexpr long long kPeerSpinLimit = 20000000000LL;     // ~10 s of SM clocks
+constexpr long long kPeerSpinLimit = 120000000000LL;    // ~60 s of SM clocks (ranks record their plans at different speeds)
 
 struct BnPeer {
     int world, rank;

@@ -506,7 +506,7 @@ class Plan:
         # kernel (csrc/conv_tc.cu: conv_wgrad_f32x2); one shared workspace, the convs run one after another
         x2_bytes = 0
         if self.training and os.environ.get("VAE2_FP32_TC_WGRAD", "1") != "0":
-            wmin = int(os.environ.get("VAE2_FP32_TC_WGRAD_MIN_LANES", "40"))
+            wmin = int(os.environ.get("VAE2_FP32_TC_WGRAD_MIN_LANES", "36"))
             # the 3x3 stride-1 layers of <= 32 input lanes (18 -> 18) as well: their planes go through the halo-tile
             # kernel in ONE pass (csrc/conv_tc.cu, dual mode) whatever engine runs their forward
             narrow = os.environ.get("VAE2_FP32_TC_WGRAD_NARROW", "1") != "0" and self.fp32_tc not in ("0", "")

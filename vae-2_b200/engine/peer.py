@@ -12,7 +12,7 @@ Rules the host side has to keep (all checked or provided here):
   * no NCCL kernel may be waiting for SMs while a BN launch waits for its peers (a cooperative launch owns the whole GPU):
     `serialize_ddp(ddp)` registers a DDP communication hook that makes the compute stream wait for each bucket's
     all-reduce before it goes on (the gradient all-reduce is ~0.15 ms per iteration here, DESIGN.md §6);
-  * `check()` after a step raises if a launch gave up waiting for a peer (~10 s) instead of hanging the GPU.
+  * `check()` after a step raises if a launch gave up waiting for a peer (~60 s) instead of hanging the GPU.
 """
 import ctypes as C
 import os
@@ -51,26 +51,37 @@ def enable(group=None, mailbox_mb=None):
         return False
     lib = N.lib()
     nbytes = int(mailbox_mb if mailbox_mb is not None else os.environ.get("VAE2_PEER_MAILBOX_MB", "256")) << 20
+    dev = torch.device("cuda", torch.cuda.current_device())
     ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-    N.check(lib.vae2_ipc_alloc(nbytes, C.byref(ptr), handle), "vae2_ipc_alloc")
-    mine = (os.uname().nodename, bytes(handle.raw))
+    ok = lib.vae2_ipc_alloc(nbytes, C.byref(ptr), handle) == 0
+    mine = (os.uname().nodename, bytes(handle.raw) if ok else None)
     allh = [None] * W
     dist.all_gather_object(allh, mine, group=group)
-    if any(h[0] != mine[0] for h in allh):
-        lib.vae2_ipc_free(ptr)
-        return False                                   # ranks on several nodes: keep NCCL
+    ok = ok and all(h[1] is not None and h[0] == mine[0] for h in allh)      # every rank allocated, all on this node
     ctx = _Ctx()
     ctx.world, ctx.rank, ctx.group, ctx.nbytes = W, rank, group, nbytes
     ctx.local, ctx.opened, bases = ptr, [], []
     for r in range(W):
+        if not ok:
+            break
         if r == rank:
             bases.append(ptr.value)
             continue
         p = C.c_void_p()
-        N.check(lib.vae2_ipc_open(C.create_string_buffer(allh[r][1], 64), C.byref(p)), "vae2_ipc_open")
+        if lib.vae2_ipc_open(C.create_string_buffer(allh[r][1], 64), C.byref(p)) != 0:
+            ok = False                                 # no peer access / IPC not permitted here
+            break
         ctx.opened.append(p)
         bases.append(p.value)
-    dev = torch.device("cuda", torch.cuda.current_device())
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)                 # all ranks take the same path
+    if int(flag.item()) == 0:
+        for p in ctx.opened:
+            lib.vae2_ipc_close(p)
+        dist.barrier(group=group)
+        if ptr.value:
+            lib.vae2_ipc_free(ptr)
+        return False                                   # SyncBN stays on NCCL collectives
     ctx.seq = torch.zeros(_MAX_OPS, dtype=torch.int32, device=dev)
     ctx.err = torch.zeros(1, dtype=torch.int32, device=dev)
     arr = (C.c_void_p * W)(*bases)
