@@ -29,6 +29,7 @@ TC_CASES = [  # (B, Cin, Cout, H, W, k, bias, stride)
     (4, 18, 18, 64, 128, 3, False, 1),    # halo weight gradient: several patches per split-K range (stage ring wraps)
     (2, 30, 150, 19, 9, 3, False, 1),     # halo weight gradient: Cin_p=32, N=160 (3 x 160 TMEM columns), ragged patches
     (1, 64, 72, 40, 24, 3, False, 1),     # halo weight gradient: Cin_p=64, two M=128 instructions per kernel row, N=80
+    (2, 256, 18, 19, 21, 3, False, 1),    # halo weight gradient: four 64-lane channel chunks handled by different CTAs (transition layers)
 ]
 
 

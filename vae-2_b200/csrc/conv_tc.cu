@@ -650,7 +650,8 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long 
 // atom pair for 64 channels); split-K over patches with per-range partials, folded by wgrad_reduce_kernel as before.
 struct WHParams {
     int B, H, W;
-    int Cin_p, Cout_p;          // Cin_p = 32 or 64 (one swizzle atom per pixel row), Cout_p <= 256
+    int Cin_p, Cout_p;          // Cin_p = 32, or a multiple of 64 handled as `csets` chunks of Cc = 64 lanes by different CTAs
+    int Cc, csets;              // lanes per chunk (one swizzle atom per pixel row) and chunk count; Cout_p <= 256
     int atomB, NT;
     int tiles_w, tiles_h, total_ptiles, nranges;
     int mmas_per_row;           // 1 (Cin_p = 32: kx 0..3 in one M=128) or 2 (Cin_p = 64: kx {0,1} and {2,3})
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                   const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_dyl, const WHParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t rowA = p.Cin_p * 2, rowB = p.atomB * 2;
+    const uint32_t rowA = p.Cc * 2, rowB = p.atomB * 2;
     const uint32_t a_bytes = kHaloBW * kHaloBH * rowA;                         // TMA transaction size of the halo tile
     const uint32_t a_stage = (a_bytes + 4 * rowA + 1023) / 1024 * 1024;       // + the junk tap's overhang
     const uint32_t atomB_bytes = 128 * rowB;
@@ -688,7 +689,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* acc_full = bars + 2 * kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int range = blockIdx.x;
+    const int cset = blockIdx.x % p.csets, range = blockIdx.x / p.csets;       // channel chunk, split-K range
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
@@ -714,10 +715,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&full[stage], planes * (a_bytes + b_bytes));
-                tma_load_4d(sa, &map_x, &full[stage], 0, w0 - 1, h0 - 1, b);
+                tma_load_4d(sa, &map_x, &full[stage], cset * p.Cc, w0 - 1, h0 - 1, b);
                 tma_load_5d(sa + planes * a_stage, &map_dy, &full[stage], 0, w0, h0, b, 0);
                 if (p.dual) {
-                    tma_load_4d(sa + a_stage, &map_xl, &full[stage], 0, w0 - 1, h0 - 1, b);
+                    tma_load_4d(sa + a_stage, &map_xl, &full[stage], cset * p.Cc, w0 - 1, h0 - 1, b);
                     tma_load_5d(sa + 2 * a_stage + b_bytes, &map_dyl, &full[stage], 0, w0, h0, b, 0);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -729,7 +730,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(2 * p.NT >> 3) << 17);
-            const uint32_t atoms_per_mma = 128u / (uint32_t)p.Cin_p;            // 4 or 2 taps (kx) per instruction
+            const uint32_t atoms_per_mma = 128u / (uint32_t)p.Cc;               // 4 or 2 taps (kx) per instruction
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < n_my; ++i) {
@@ -763,11 +764,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         mbar_wait(acc_full, 0);
         tc_fence_after();
         float* ws = p.ws + (size_t)range * 9 * p.Cin_p * p.Cout_p;
-        const int atoms_per_mma = 128 / p.Cin_p;
+        const int atoms_per_mma = 128 / p.Cc;
         for (int ky = 0; ky < 3; ++ky)
             for (int j = 0; j < p.mmas_per_row; ++j) {
                 const int m = q * 32 + lane;                                    // accumulator row = (kx_local, ci)
-                const int kx = j * atoms_per_mma + m / p.Cin_p, ci = m % p.Cin_p;
+                const int kx = j * atoms_per_mma + m / p.Cc, ci = cset * p.Cc + m % p.Cc;
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ky * p.mmas_per_row + j) * p.NT) * planes;
                 for (int c0 = 0; c0 < p.NT; c0 += 16) {
                     uint32_t v[16];
@@ -801,11 +802,13 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p, int dual = 0) {
     if (const char* e = getenv("VAE2_WGRAD_HALO")) { if (atoi(e) == 0) return -1; }
     if (g.k != 3 || g.stride != 1 || g.H != g.Ho || g.W != g.Wo) return -1;
-    if (!(g.Cin_p == 32 || g.Cin_p == 64) || g.ldx % 8 || g.Cout_p > 256 || g.Cout_p % 16) return -1;
+    if (!(g.Cin_p == 32 || g.Cin_p % 64 == 0) || g.Cin_p > 512 || g.ldx % 8 || g.Cout_p > 256 || g.Cout_p % 16) return -1;
     p.B = g.B; p.H = g.H; p.W = g.W; p.Cin_p = g.Cin_p; p.Cout_p = g.Cout_p;
+    p.Cc = g.Cin_p == 32 ? 32 : 64;
+    p.csets = g.Cin_p / p.Cc;
     p.atomB = g.Cout_p % 64 == 0 ? 64 : (g.Cout_p % 32 == 0 ? 32 : 16);
     p.NT = g.Cout_p;
-    p.mmas_per_row = g.Cin_p == 32 ? 1 : 2;
+    p.mmas_per_row = p.Cc == 32 ? 1 : 2;
     p.dual = dual ? 1 : 0;
     const int planes = dual ? 2 : 1;
     const int cols = 3 * p.mmas_per_row * p.NT * planes;
@@ -814,7 +817,7 @@ static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p, int dual = 0) {
     p.tiles_w = (g.W + kHaloTW - 1) / kHaloTW;
     p.tiles_h = (g.H + kHaloTH - 1) / kHaloTH;
     p.total_ptiles = g.B * p.tiles_w * p.tiles_h;
-    const int rowA = g.Cin_p * 2;
+    const int rowA = p.Cc * 2;
     const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
     const long long b_stage = ((long long)p.NT * 128 * 2 + 1023) / 1024 * 1024;
     const int ctas = p.tmem_cols <= 256 ? 2 : 1;
@@ -824,7 +827,8 @@ static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p, int dual = 0) {
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -1;
     p.stages = stages;
-    int nranges = ctas * kNumSMs;
+    int nranges = ctas * kNumSMs / p.csets;
+    if (nranges < 1) nranges = 1;
     if (nranges > p.total_ptiles) nranges = p.total_ptiles;
     p.nranges = nranges;
     return (long long)nranges * 9 * g.Cin_p * g.Cout_p;
@@ -1208,10 +1212,10 @@ static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGe
         for (int pl = 0; pl < (dual ? 2 : 1); ++pl) {
             cuuint64_t dims[4] = {(cuuint64_t)g.Cin_p, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
             cuuint64_t strides[3] = {(cuuint64_t)g.ldx * 2, (cuuint64_t)g.W * g.ldx * 2, (cuuint64_t)g.H * g.W * g.ldx * 2};
-            cuuint32_t box[4] = {(cuuint32_t)g.Cin_p, (cuuint32_t)kHaloBW, (cuuint32_t)kHaloBH, 1};
+            cuuint32_t box[4] = {(cuuint32_t)p.Cc, (cuuint32_t)kHaloBW, (cuuint32_t)kHaloBH, 1};
             cuuint32_t es[4] = {1, 1, 1, 1};
             if (enc(pl ? &map_xl : &map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(pl ? xl : x), dims, strides, box,
-                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz(g.Cin_p), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz(p.Cc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return VAE2_ERR_ARG;
         }
@@ -1221,7 +1225,7 @@ static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGe
         } else {
             map_xl = map_x; map_dyl = map_dy;
         }
-        const int rowA = g.Cin_p * 2, planes = dual ? 2 : 1;
+        const int rowA = p.Cc * 2, planes = dual ? 2 : 1;
         const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
         const long long b_stage = ((long long)planes * p.NT * 128 * 2 + 1023) / 1024 * 1024;
         const size_t smem = (size_t)p.stages * (planes * a_stage + b_stage) + 1024 + (2 * kMaxStages + 4) * 8 + 16;
@@ -1231,7 +1235,7 @@ static int wgrad_partials(const void* x, const void* dy, float* ws, const ConvGe
                 return VAE2_ERR_CUDA;
             attr_set = true;
         }
-        wgrad_halo_kernel<<<p.nranges, kThreads, smem, st>>>(map_x, map_dy, map_xl, map_dyl, p);
+        wgrad_halo_kernel<<<p.nranges * p.csets, kThreads, smem, st>>>(map_x, map_dy, map_xl, map_dyl, p);
         return check_launch();
     }
     WParams p = P.w;
