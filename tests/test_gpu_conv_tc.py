@@ -208,3 +208,58 @@ def test_conv_wgrad_f32x2(case):
     assert e_tc < 3e-5, (e_tc, e_simt)
     pads = dwp.view(k * k, Cin_p, Cout_p)
     assert float(pads[:, Cin:, :].abs().sum()) == 0.0 and float(pads[:, :, Cout:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("slot", [0, 1, 2])
+def test_conv_tc_prediction_head_writes_an_8_lane_slice(slot):
+    """The 270 -> 3 prediction heads (lib/models/enc_hrnet.py:324-337, last_layer) write an 8-lane slice of the 9-frame clip
+    buffer: Cout_p = 8 inside ldy = 32.  On the tcgen05 path N is padded to 16 by TMA zero fill and the epilogues store 8
+    lanes -- the neighbouring slices must stay untouched; forward (+bias), data gradient and weight gradient against torch."""
+    B, Cin, Cout, H, W, k = 2, 270, 3, 19, 23, 1
+    tag = "head%d" % slot
+    x = O.det_normal(tag + "x", (B, Cin, H, W)).bfloat16().float()
+    w = O.det_normal(tag + "w", (Cout, Cin, k, k), (2.0 / Cin) ** 0.5).bfloat16().float()
+    bias = O.det_normal(tag + "b", (Cout,), 0.1)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, bias)
+    gy = O.det_normal(tag + "gy", tuple(yr.shape)).bfloat16().float()
+    yr.backward(gy)
+    xa, Cin_p = to_act(x, "bf16", pad(Cin, 16))
+    Cout_p, ldy = 8, 32
+    wq, wqT = pack_bf16(w, Cin_p, Cout_p)
+    g = N.ConvGeom(B=B, H=H, W=W, Cin_p=Cin_p, ldx=Cin_p, Ho=H, Wo=W, Cout_p=Cout_p, ldy=ldy, k=k, stride=1, pad=0)
+    assert N.lib().vae2_conv2d_tc_supported(C.byref(g)) == 1
+    clip = torch.full((B * H * W, ldy), 3.0, dtype=torch.bfloat16, device=dev())
+    bp = torch.zeros(Cout_p, dtype=torch.float32, device=dev())
+    bp[:Cout] = bias.to(dev())
+    off = slot * 8
+    N.call.vae2_conv2d_fwd(xa.data_ptr(), wq.data_ptr(), bp.data_ptr(), clip.data_ptr() + 2 * off, 1, C.byref(g), 1, st())
+    torch.cuda.synchronize()
+    y = clip[:, off:off + Cout].float().reshape(B, H, W, Cout).permute(0, 3, 1, 2).cpu()
+    assert rel_err(y, yr.detach()) < 6e-3, "head fwd rel err %.3e" % rel_err(y, yr.detach())
+    mask = torch.ones(ldy, dtype=torch.bool)
+    mask[off:off + 8] = False
+    assert bool((clip[:, mask.to(dev())] == 3.0).all()), "neighbouring slices were overwritten"
+    assert float(clip[:, off + Cout:off + 8].float().abs().sum()) == 0.0
+    # backward: dy lives in the same kind of slice, other lanes hold garbage that must not leak in
+    gclip = torch.full((B * H * W, ldy), 5.0, dtype=torch.bfloat16, device=dev())
+    gclip[:, off:off + 8] = 0
+    gclip[:, off:off + Cout] = gy.permute(0, 2, 3, 1).reshape(-1, Cout).to(dev()).bfloat16()
+    dxa = torch.zeros_like(xa)
+    N.call.vae2_conv2d_dgrad(gclip.data_ptr() + 2 * off, wqT.data_ptr(), dxa.data_ptr(), 1, C.byref(g), 0, 1, st())
+    torch.cuda.synchronize()
+    dx = from_act(dxa, "bf16", B, Cin, H, W, Cin_p)
+    assert rel_err(dx, xr.grad) < 6e-3, "head dgrad rel err %.3e" % rel_err(dx, xr.grad)
+    need = N.lib().vae2_conv2d_wgrad_tc_workspace(C.byref(g))
+    assert need > 0
+    ws = torch.zeros(need, dtype=torch.float32, device=dev())
+    dwp = torch.full((Cin_p * Cout_p + 64,), 7.0, dtype=torch.float32, device=dev())
+    N.call.vae2_conv2d_wgrad_tc(xa.data_ptr(), gclip.data_ptr() + 2 * off, dwp.data_ptr(), ws.data_ptr(), C.byref(g), st())
+    dw = torch.zeros_like(w).to(dev())
+    d = (N.PackDesc * 1)()
+    d[0] = N.PackDesc(w=dw.data_ptr(), wp=dwp.data_ptr(), Cout=Cout, Cin=Cin, k=k, Cin_p=Cin_p, Cout_p=Cout_p)
+    t = table(d)
+    N.call.vae2_unpack_wgrad(t.data_ptr(), 1, 0, st())
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu(), wr.grad) < 6e-3, "head wgrad rel err %.3e" % rel_err(dw.cpu(), wr.grad)
+    assert bool((dwp[Cin_p * Cout_p:] == 7.0).all()), "weight-gradient rows overflowed"

@@ -463,9 +463,56 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ d
     }
 }
 
+// Vectorised variant: a thread owns one 16-byte piece of the lane range and walks the block's pixel range with it
+// (the scalar kernel above re-walked the pixels once per 32 channels with 2-byte loads: 885 GB/s on the 270-lane heads).
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+bias_grad_vec_kernel(const T* __restrict__ dy, float* __restrict__ dbias, long long P, int C, int ld, int nc, long long per_block) {
+    __shared__ float red[2048];
+    const int R = 256 / nc;                               // pixel rows in flight per block
+    const int chunk = threadIdx.x % nc, r = threadIdx.x / nc;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    const long long p0 = blockIdx.x * per_block, p1 = min(P, p0 + per_block);
+    if (r < R) {
+        for (long long p = p0 + r; p < p1; p += R) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + p * ld + chunk * V));
+            if constexpr (V == 4) {
+                acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
+                acc[2] += __uint_as_float(q.z); acc[3] += __uint_as_float(q.w);
+            } else {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) red[(r * nc + chunk) * V + e] = acc[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int rr = 0; rr < R; ++rr) t += red[rr * nc * V + c];
+        atomicAdd(dbias + c, t);
+    }
+}
+
 int bias_grad(const void* dy, float* dbias, int dtype, long long P, int C, int ld, int accumulate, cudaStream_t st) {
     if (!accumulate) {
         if (cudaMemsetAsync(dbias, 0, sizeof(float) * C, st) != cudaSuccess) return VAE2_ERR_CUDA;
+    }
+    const int V = dtype == VAE2_DT_F32 ? 4 : 8;
+    const int nc = (C + V - 1) / V;                       // 16-byte pieces that hold real channels (the tail piece may read pad lanes)
+    if (ld % V == 0 && nc * V <= ld && nc <= 256 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+        int grid = 4 * kNumSMs;
+        if ((long long)grid * 64 > P) grid = (int)((P + 63) / 64);
+        const long long per_block = (P + grid - 1) / grid;
+        if (dtype == VAE2_DT_F32)
+            bias_grad_vec_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)dy, dbias, P, C, ld, nc, per_block);
+        else
+            bias_grad_vec_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, dbias, P, C, ld, nc, per_block);
+        return check_launch();
     }
     const int grid = stream_grid(P, 8 * 64, 2);
     if (dtype == VAE2_DT_F32)

@@ -171,16 +171,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld_wait();
                 const int n = nt * p.NT + c0;
                 if (in_img && n < p.Cn) {
+                    const bool half = n + 8 >= p.Cn;          // 8-lane tail (prediction heads): only one 16-byte store
                     float f[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
                     if (p.bias != nullptr) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + n + i);
+                        for (int i = 0; i < 16; ++i) f[i] += (i < 8 || !half) ? __ldg(p.bias + n + i) : 0.f;
                     }
                     uint4* dst = reinterpret_cast<uint4*>(orow + n);
                     if (p.accumulate) {
-                        uint4 o[2] = {dst[0], dst[1]};
+                        uint4 o[2];
+                        o[0] = dst[0];
+                        o[1] = half ? make_uint4(0u, 0u, 0u, 0u) : dst[1];
                         const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(o);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { float2 t = __bfloat1622float2(oh[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
@@ -190,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 8; ++i) oh[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                     dst[0] = o[0];
-                    dst[1] = o[1];
+                    if (!half) dst[1] = o[1];
                 }
             }
             tc_fence_before();
@@ -589,14 +592,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
                 if (m < p.M_total && n0 + c0 < p.Cout_p) {
                     float4* dst = reinterpret_cast<float4*>(ws + (size_t)m * p.Cout_p + n0 + c0);
+                    const int nq = min(4, (p.Cout_p - n0 - c0) / 4);        // 8-lane outputs: two float4 of the 16-column group
                     if (n_my_tiles > 0) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                 __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                            if (i < nq)
+                                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 4; ++i)
+                            if (i < nq) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
             }
@@ -607,19 +613,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// dwp[i] = sum over split-K slots.  32 float4 columns x 8 slot groups per CTA: a thread adds every 8th slot
-// (independent loads, a short dependent chain), the groups are folded through shared memory in a fixed order.
+// dwp[i] = sum over split-K slots.  COLS float4 columns x (256 / COLS) slot groups per CTA: a thread adds every
+// (256/COLS)-th slot (independent loads, a short dependent chain), the groups are folded through shared memory in a fixed
+// order.  Small gradients (18 -> 18: 9216 floats in 296 slots) take COLS = 8 so that 4x more CTAs share the slots -- with
+// 32 columns only 72 CTAs ran 37 dependent rounds each (ncu r2f: 14.4 us for 11 MB).
+template <int COLS>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long long n, int nslots) {
-    __shared__ float4 sm[8][32];
-    const int ex = threadIdx.x & 31, sg = threadIdx.x >> 5;
+    constexpr int GROUPS = 256 / COLS;
+    __shared__ float4 sm[GROUPS][COLS];
+    const int ex = threadIdx.x % COLS, sg = threadIdx.x / COLS;
     const long long n4 = n / 4;
-    const long long i = (long long)blockIdx.x * 32 + ex;
+    const long long i = (long long)blockIdx.x * COLS + ex;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n4) {
         const float4* src = reinterpret_cast<const float4*>(ws) + i;
 #pragma unroll 4
-        for (int s = sg; s < nslots; s += 8) {
+        for (int s = sg; s < nslots; s += GROUPS) {
             const float4 v = src[(long long)s * n4];
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
@@ -628,12 +638,20 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dwp, long 
     __syncthreads();
     if (sg == 0 && i < n4) {
 #pragma unroll
-        for (int g = 1; g < 8; ++g) {
+        for (int g = 1; g < GROUPS; ++g) {
             const float4 v = sm[g][ex];
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         reinterpret_cast<float4*>(dwp)[i] = a;
     }
+}
+
+static void launch_wgrad_reduce(const float* ws, float* dwp, long long n, int nslots, cudaStream_t st) {
+    const long long n4 = n / 4;
+    if (n4 < 2LL * kNumSMs * 32 && nslots >= 64)
+        wgrad_reduce_kernel<8><<<(unsigned)((n4 + 7) / 8), 256, 0, st>>>(ws, dwp, n, nslots);
+    else
+        wgrad_reduce_kernel<32><<<(unsigned)((n4 + 31) / 32), 256, 0, st>>>(ws, dwp, n, nslots);
 }
 
 // ---- weight gradient of 3x3 stride-1 layers with ONE halo tile per pixel patch --------------------------------------------
@@ -932,7 +950,11 @@ static long long plan_wgrad_kp(const ConvGeom& g, WParams& p, int kp, int min_st
 int conv_tc_supported(const ConvGeom& g) {
     if (!(g.stride == 1 || (g.stride == 2 && g.k == 3))) return 0;
     if (!(g.k == 1 || g.k == 3)) return 0;
-    if (g.Cin_p % 16 || g.Cout_p % 16 || g.ldx % 8 || g.ldy % 8) return 0;
+    // lanes in multiples of 16; the one exception are 8-lane OUTPUTS of 1x1 layers (the 270 -> 3 prediction heads write an
+    // 8-lane slice of the clip buffer): N is padded to 16 by TMA zero fill and the epilogues store 8 lanes
+    const bool head8 = g.Cout_p == 8 && g.k == 1 && g.stride == 1;
+    if (g.Cin_p % 16 || (g.Cout_p % 16 && !head8) || g.ldx % 8 || g.ldy % 8) return 0;
+    if (head8) { if (const char* e = getenv("VAE2_TC_HEAD8")) { if (atoi(e) == 0) return 0; } }
     if (g.stride == 1 && (g.H != g.Ho || g.W != g.Wo)) return 0;
     if (g.stride == 2 && (g.Ho != (g.H + 1) / 2 || g.Wo != (g.W + 1) / 2)) return 0;
     return tc::encode_fn() != nullptr ? 1 : 0;
@@ -971,7 +993,7 @@ static int launch_tc(const tc::Launch& L, cudaStream_t st) {
     // ---- halo path: 3x3, unit strides, all taps' weights resident in shared memory ----
     {
         bool halo = L.ntaps == 9 && L.sA == 1 && L.a_estride == 1 && L.sO == 1 && L.oh_off == 0 && L.ow_off == 0 &&
-                    p.n_tiles == 1 && 2 * p.NT <= 512;
+                    p.n_tiles == 1 && 2 * p.NT <= 512 && L.Cn % 16 == 0;
         for (int i = 0; halo && i < 9; ++i) halo = L.dh[i] >= -1 && L.dh[i] <= 1 && L.dw[i] >= -1 && L.dw[i] <= 1;
         if (const char* e = getenv("VAE2_TC_HALO")) { if (atoi(e) == 0) halo = false; }
         // K chunk: a halo stage costs one barrier round trip per chunk (not per tap), so the MMA count decides:
@@ -1164,7 +1186,9 @@ namespace vae2 {
 static int make_map5(tc::EncodeTiledFn enc, CUtensorMap* m, const void* base, int atom, int C, int boxC, int ld, int B, int H,
                      int W, int TW, int TH, int estride) {
     const cuuint32_t e = (cuuint32_t)estride;
-    cuuint64_t dims[5] = {(cuuint64_t)atom, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / atom)};
+    // C < atom (8-lane head outputs): the inner dimension is the real width, the box still spans `atom` lanes (zero fill)
+    cuuint64_t dims[5] = {(cuuint64_t)(C < atom ? C : atom), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B,
+                          (cuuint64_t)((C + atom - 1) / atom)};
     cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)atom * 2};
     cuuint32_t box[5] = {(cuuint32_t)atom, (cuuint32_t)TW * e, (cuuint32_t)TH * e, 1, (cuuint32_t)(boxC / atom)};
     cuuint32_t es[5] = {1, e, e, 1, 1};
@@ -1277,7 +1301,7 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dwp, float* ws, const Co
     if (plan_wgrad_any(g, P)) return VAE2_ERR_UNSUPPORTED;
     note_kernel(P.halo ? "tc::wgrad_halo_kernel" : "tc::wgrad_tc_kernel");
     if (int e = wgrad_partials(x, dy, ws, g, P, st)) return e;
-    wgrad_reduce_kernel<<<(unsigned)((P.n / 4 + 31) / 32), 256, 0, st>>>(ws, dwp, P.n, P.nslots);
+    launch_wgrad_reduce(ws, dwp, P.n, P.nslots, st);
     return check_launch();
 }
 
@@ -1402,13 +1426,13 @@ int conv_wgrad_f32x2(const float* x, const float* dy, float* dwp, void* workspac
     if (dual) {
         // one pass: x_hi*dy_hi in one accumulator, x_hi*dy_lo + x_lo*dy_hi in a second one, added in the epilogue
         if (int e = wgrad_partials(xh, yh, slots, q, P, st, xl, yl)) return e;
-        wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, P.nslots);
+        launch_wgrad_reduce(slots, dw16, n, P.nslots, st);
     } else {
         const __nv_bfloat16* xa[3] = {xl, xh, xh};      // smallest products first in the fold: lo*hi, hi*lo, hi*hi
         const __nv_bfloat16* ya[3] = {yh, yl, yh};
         for (int t = 0; t < 3; ++t)
             if (int e = wgrad_partials(xa[t], ya[t], slots + (long long)t * part, q, P, st)) return e;
-        wgrad_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(slots, dw16, n, 3 * P.nslots);
+        launch_wgrad_reduce(slots, dw16, n, 3 * P.nslots, st);
     }
     const int total = g.k * g.k * g.Cin_p * g.Cout_p;
     crop_dw_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw16, dwp, g.k * g.k, g.Cin_p, g.Cout_p, q.Cin_p, q.Cout_p);
