@@ -434,11 +434,16 @@ def main():
     l0 = E.launch_count()
     clocks = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncu_range = os.environ.get("VAE2_BENCH_PROFILER_RANGE") == "1"   # `ncu --profile-from-start off`: the timed steps only
+    if ncu_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         lg, ld = train_step(g, d, opt_g, opt_d, *resident[i % nb])
     e1.record()
     sync()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = E.launch_count() - l0
 
