@@ -151,6 +151,49 @@ def test_syncbn_message_algebra_world2_gloo():
     assert res == [(0, True, True, True, 11.0), (1, True, True, True, 11.0)]
 
 
+def _ddp_hook_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2)).double()
+    import copy
+    a = torch.nn.parallel.DistributedDataParallel(copy.deepcopy(ref))
+    b = torch.nn.parallel.DistributedDataParallel(copy.deepcopy(ref), broadcast_buffers=False, gradient_as_bucket_view=True)
+    E.peer.serialize_ddp(b)                       # the hook the peer-memory SyncBN path installs (engine/peer.py)
+    x = torch.randn(world, 4, 6, dtype=torch.float64)[rank]
+    a(x).square().sum().backward()
+    b(x).square().sum().backward()
+    same = all(torch.allclose(pa.grad, pb.grad, atol=1e-14) for pa, pb in zip(a.parameters(), b.parameters()))
+    q.put((rank, bool(same)))
+    dist.destroy_process_group()
+
+
+def test_serialized_ddp_hook_averages_like_default_ddp_world2_gloo():
+    """engine.peer.serialize_ddp: same averaged gradients as DDP's built-in all-reduce (tools/train.py:226-229), only the
+    stream ordering differs; also with the two constructor switches bench.py uses."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_ddp_hook_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_peer_mailbox_slot_words_and_inactive_default():
+    """Host side of the peer-memory SyncBN exchange: slot sizes (2 buffers x world x groups x values x lanes 8-byte words)
+    and that nothing is active unless enable() succeeded (single process: it must refuse)."""
+    lib = E.native.lib()
+    assert lib.vae2_bn_peer_slot_words(8, 6, 272, 0) == 2 * 8 * 6 * 3 * 272
+    assert lib.vae2_bn_peer_slot_words(2, 1, 32, 1) == 2 * 2 * 1 * 2 * 32
+    assert not E.peer.active() and E.peer.world() == 1
+    assert E.peer.enable() is False               # no process group
+    E.peer.check()                                # no-op when inactive
+
+
 def test_activation_arena_shares_memory_across_phases_only():
     """engine.ActArena (host logic, CPU tensors): buffers of one phase are disjoint, the next phase walks the same
     chunks from the start, an allocation larger than a chunk gets a chunk of its own, and nothing is shared outside
