@@ -11,17 +11,21 @@
 // tcgen05.mma), and with all six products in one accumulator that bias grows with 6 x (taps x K/16) instructions --
 // measured 1e-6..1.5e-5 per conv in round 1, which pushed the encoder prediction to 1.35e-4.  Here the leading product
 // x1*w1 accumulates in D_main, the five correction products (<= 2^-8 of it) in D_corr, whose truncation is 2^-8 smaller
-// in absolute terms; the epilogue adds the two with one rounded fp32 add.  D_main sees a sixth of the instructions.  Same implicit GEMM as conv_tc.cu (M tile =
-// TH x TW pixel patch, taps x 32-channel chunks on K, N tile <= 256), different operand plumbing:
-//   * activations stay plain fp32 in HBM; four PRODUCER warps (one pixel row per thread) gather the shifted
-//     pixel's 32 channels with 16-byte loads (bounds / padding by predicate, stride-2 by address), split them
-//     and write three bf16 tiles into shared memory in the 64-byte-swizzled K-major layout the tensor core
-//     reads (fence.proxy.async before the mbarrier arrive);
+// in absolute terms; the epilogue adds them with one rounded fp32 add.
+//
+// Same implicit GEMM as conv_tc.cu (M tile = TH x TW pixel patch, taps x 32-channel chunks on K, N tile <= 256),
+// different operand plumbing:
+//   * activations stay plain fp32 in HBM; four PRODUCER warps gather 16-byte pieces (bounds / padding by predicate,
+//     stride-2 by address), split them and write three bf16 tiles into shared memory in the 64-byte-swizzled K-major
+//     layout the tensor core reads (fence.proxy.async before the mbarrier arrive);
 //   * weights are split once per step by the pack kernel into three bf16 planes [3][tap][N][K], one TMA per stage;
-//   * one thread issues 6 x 2 tcgen05.mma.kind::f16 (M=128, N=NT, K=16) per stage; epilogue warps read TMEM and
-//     store fp32 (+bias, optional accumulate for the data gradient).
-// Forward and data gradient (stride 1 and 2, 3x3 and 1x1) share the kernel through a tap table, exactly like the
-// bf16 kernel; the weight gradient of the fp32 path stays on conv_simt.cu.
+//   * one thread issues the products of a 16-channel K step -- products that share an A plane as ONE instruction over the
+//     stacked weight planes (issue_kstep: 3 or 4 tcgen05.mma.kind::f16 instead of 6); epilogue warps read TMEM, add the
+//     accumulator blocks and store fp32 (+bias, optional accumulate for the data gradient).
+// Two kernels: conv_f32x3_kernel (any 1x1 / 3x3, stride 1 / 2: one gathered tile per tap) and conv_f32x3_halo_kernel
+// (3x3 stride 1: ONE halo tile per patch and K chunk, taps as descriptor start rows, weights through their own ring).
+// Forward and data gradient share them through a tap table, exactly like the bf16 kernels; the fp32 weight gradient runs on
+// the bf16 wgrad kernels of conv_tc.cu through hi/lo planes (conv_wgrad_f32x2).
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"

@@ -837,10 +837,8 @@ static long long plan_wgrad_halo(const ConvGeom& g, WHParams& p, int dual = 0) {
     p.total_ptiles = g.B * p.tiles_w * p.tiles_h;
     const int rowA = p.Cc * 2;
     const long long a_stage = ((long long)kHaloBW * kHaloBH * rowA + 4 * rowA + 1023) / 1024 * 1024;
-    const long long b_stage = ((long long)p.NT * 128 * 2 + 1023) / 1024 * 1024;
     const int ctas = p.tmem_cols <= 256 ? 2 : 1;
     const long long stage_b = planes * a_stage + ((long long)planes * p.NT * 128 * 2 + 1023) / 1024 * 1024;
-    (void)b_stage;
     int stages = (int)((kSmemBudget / ctas - 2048) / stage_b);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -1;
