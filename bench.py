@@ -452,25 +452,9 @@ def main():
     # end-to-end: host pinned inputs -> device every step, loss scalars read back every step
     sync()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # The copy of step i+1's clips runs on a side stream under step i's kernels (what utils.device_pipeline does for a real
-    # loader); the first copy is not hidden.  Every step still copies its own inputs and reads its losses inside the region.
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            xb = tuple(t.to(dev, non_blocking=True) for t in host[i % nb])
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return xb, ev
     f0.record()
-    nxt = prefetch(0)
     for i in range(args.steps):
-        xb, ev = nxt
-        torch.cuda.current_stream(dev).wait_event(ev)
-        for t_ in xb:
-            t_.record_stream(torch.cuda.current_stream(dev))
-        if i + 1 < args.steps:
-            nxt = prefetch(i + 1)
+        xb = tuple(t.to(dev, non_blocking=True) for t in host[i % nb])
         lg, ld = train_step(g, d, opt_g, opt_d, *xb)
         _ = (lg.item(), ld.item())
     f1.record()
