@@ -15,4 +15,4 @@ for f in sorted(glob.glob('gpurun_out/r2_bench10*.json')):
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, round(d['value'],2), d.get('ms_per_step'), d['config'].get('per_gpu_batch'), d.get('hbm_peak_gb'), d['roofline']['kernel'], d['roofline']['share_of_step'])
     except Exception as e: print(f, 'ERR', e)
 "
-bash tools/gpu_run9.sh
+bash tools/runs/gpu_run9.sh
