@@ -44,6 +44,9 @@ def check_finite(block=False):
             keep.append((names, flags, ev))
     _pending_flags[:] = keep        # a reported launch is consumed even when it raises
     assert failed is None, "{} got nan or inf".format(failed)
+    if block:
+        from . import peer
+        peer.check()                # multi-GPU: a SyncBN launch that gave up waiting for a peer rank (engine/peer.py)
 
 
 def _bound_pending():
